@@ -1,0 +1,25 @@
+# Builds libspike_b200.so (hand-written sm_100a CUDA + C ABI), the PETSc-shaped host glue and the
+# CPU oracle.  `make` here is what __graft_entry__.build() runs.
+NVCC    ?= /usr/local/cuda/bin/nvcc
+ARCH    := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+CSRC    := spike_petsc_b200/csrc
+LIBDIR  := spike_petsc_b200/lib
+OBJS    := $(LIBDIR)/layout.o $(LIBDIR)/lu.o $(LIBDIR)/tips.o $(LIBDIR)/solve.o $(LIBDIR)/krylov.o $(LIBDIR)/capi.o
+
+all: $(LIBDIR)/libspike_b200.so oracle
+
+$(LIBDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/spike_b200.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/$*.ptxas.log || (cat $(LIBDIR)/$*.ptxas.log; exit 1)
+
+$(LIBDIR)/libspike_b200.so: $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf $(LIBDIR)/*.o $(LIBDIR)/*.so $(LIBDIR)/*.log
+	$(MAKE) -C oracle clean
+.PHONY: all oracle clean

@@ -1,0 +1,136 @@
+/*
+ * spike_b200.h -- C ABI of the B200-native SPIKE banded engine (libspike_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of spikegpu/spike-petsc: plain C, opaque handle,
+ * pointers + sizes, int return codes (0 = success, never throws/aborts -- the PetscErrorCode
+ * convention of the reference, e.g. src/matbanded.c:95, src/kspreorder.c:121).  Each entry point
+ * names the reference interface it replaces (paths relative to the reference tree).  The
+ * PETSc-shaped glue that binds these calls into PC/KSP ops tables is spike_petsc_b200/host/
+ * (see INTEGRATION.md).
+ *
+ * Threading: one host thread per context (PETSc objects are not thread safe).
+ * All work is enqueued on the context's CUDA stream; calls that return host-visible results
+ * synchronise that stream before returning.  There is NO CPU fallback: every call fails with
+ * SPK_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SPIKE_B200_H
+#define SPIKE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spk_ctx spk_ctx;
+
+enum { SPK_OK = 0, SPK_ERR_ARG = 1, SPK_ERR_CUDA = 2, SPK_ERR_STATE = 3, SPK_ERR_UNSUPPORTED = 4, SPK_ERR_NOMEM = 5 };
+enum { SPK_MEM_HOST = 0, SPK_MEM_DEVICE = 1 };                    /* where caller buffers live      */
+enum { SPK_LAYOUT_ROWS = 0, SPK_LAYOUT_DIAGS = 1 };               /* dense band input layouts       */
+enum { SPK_KSP_GMRES = 0, SPK_KSP_BCGS = 1 };                     /* inner KSP types used by HOWTO  */
+
+typedef struct spk_opts {
+  int     device;        /* CUDA device ordinal                                                      */
+  void   *stream;        /* cudaStream_t to enqueue on; NULL = legacy default stream                 */
+  int     partitions;    /* SPIKE partitions on this device; 0 = auto (multiple of the SM count)     */
+  int     tip_tiles;     /* truncation window, in 8-row tiles, of the W^(t) tip pass and of the apply
+                            corrections; 0 = auto, <0 = whole partition (SaP-style full passes)      */
+  double  boost_rel;     /* pivot boosting: |pivot| < boost_rel*max|a_ij| is replaced by +-that      */
+  int     mem;           /* SPK_MEM_HOST / SPK_MEM_DEVICE for vector arguments of solve/mult/krylov  */
+  int     rank, nranks;  /* this device's position in a row-block sharding (0,1 = single device)     */
+  int64_t row_offset;    /* global index of this shard's first row (generator counters, bookkeeping) */
+  int64_t n_global;      /* global rows; 0 = same as local n                                         */
+} spk_opts;
+
+typedef struct spk_info {
+  int64_t n, n_padded;
+  int     k, k_padded, kt;           /* half-bandwidth, padded to 8*kt                                 */
+  int     partitions, tip_tiles;
+  int64_t boosted_pivots;
+  int     factored;
+  double  frac;                      /* norm fraction of the extracted band (PC_Banded.f)             */
+  double  anorm_max;                 /* max |a_ij| of the band                                        */
+  double  factor_ms, solve_ms;       /* device time of the last spk_factor / spk_solve (CUDA events)  */
+  int64_t band_bytes;                /* bytes of the device band (tile-major, padded)                 */
+  int     kernel_launches;           /* kernels launched by the last spk_factor + spk_solve           */
+} spk_info;
+
+void spk_default_opts(spk_opts *o);
+const char *spk_last_error(const spk_ctx *ctx);       /* message of the last failing call            */
+const char *spk_version(void);
+
+/* lifecycle -- PCCreate_Banded / PCReset_Banded / PCDestroy_Banded (src/matbanded.c:251-283,120-145) */
+int spk_create(spk_ctx **ctx, const spk_opts *opts);
+int spk_destroy(spk_ctx **ctx);
+
+/* ---- band definition -------------------------------------------------------------------------- */
+/* Dense band in host or device memory.  ROWS: a[i*(2k+1) + (j-i+k)];  DIAGS: a[(j-i+k)*n + i].
+ * Replaces holding B as AIJ (PC_Banded.B, src/matbanded.c:114). */
+int spk_set_band_dense(spk_ctx *ctx, int64_t n, int k, const double *band, int layout, int mem);
+
+/* MatCreateSubMatrixBanded (src/matbanded.h:5, src/matbanded.c:22-107) fused with the MatPermute of
+ * KSPSetUp_Reorder (src/kspreorder.c:20): B = band_k( A(rowperm[i], colperm[j]) ).  CSR is 0-based,
+ * host memory; rowperm/colperm may be NULL (identity).  *kmax in/out and *frac in/out exactly as
+ * the reference (k chosen in row-major summation order on the host, including the fall-through
+ * quirk); the pack + gather runs on the GPU. */
+int spk_set_band_csr(spk_ctx *ctx, int n, const int *ia, const int *ja, const double *a,
+                     const int *rowperm, const int *colperm, int *kmax, double *frac);
+
+/* Counter-based synthetic band generated directly in device memory:
+ * a_ij = 2*u01(splitmix64(seed ^ (gi*(2k+1)+d+k))) - 1, a_ii = delta * sum|a_ij|, gi = global row. */
+int spk_set_band_synthetic(spk_ctx *ctx, int64_t n, int k, uint64_t seed, double delta);
+
+/* copy the device band (original or factored) back in ROWS layout -- test / debug hook */
+int spk_get_band_rows(spk_ctx *ctx, double *band_rows_host);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+/* PCSetUp(b->pc) at src/matbanded.c:178 (and MatLUFactor of a MATBANDED): per-partition banded LU
+ * (no pivoting, diagonal boosting), spike tips V^(b)/W^(t), reduced-system factorisation. In place. */
+int spk_factor(spk_ctx *ctx);
+/* PCApply(b->pc,x,y) at src/matbanded.c:190 (and MatSolve): x = B^{-1} b for nrhs vectors of
+ * leading dimension n.  b and x may alias. */
+int spk_solve(spk_ctx *ctx, const double *b, double *x, int nrhs);
+/* MatMult (src/testbed2.c:122 and inside the inner KSP) with the UNFACTORED band kept by
+ * spk_keep_original(ctx,1) or, before spk_factor, with the band itself. */
+int spk_mult(spk_ctx *ctx, const double *x, double *y);
+int spk_keep_original(spk_ctx *ctx, int keep);
+
+/* VecPermute (src/kspreorder.c:122-127): inverse=0: v[i] <- v[idx[i]];  inverse=1: v[idx[i]] <- v[i].
+ * idx is a host int array of length n; v follows opts.mem. */
+int spk_permute(spk_ctx *ctx, const int *idx, int inverse, double *v, int64_t n);
+
+/* Inner KSPSolve at src/kspreorder.c:124: left-preconditioned GMRES(restart) / BiCGStab on the
+ * device with M^{-1} = this context's SPIKE solve.  A is the CSR matrix registered with
+ * spk_set_operator_csr (permuted like the band) or, if none, the unfactored band. */
+int spk_set_operator_csr(spk_ctx *ctx, int n, const int *ia, const int *ja, const double *a,
+                         const int *rowperm, const int *colperm);
+int spk_krylov(spk_ctx *ctx, int method, int restart, double rtol, int maxit, const double *b,
+               double *x, int *its, double *rnorm, int *converged);
+
+/* PCView_Banded (src/matbanded.c:196-211) */
+int spk_view(spk_ctx *ctx, spk_info *info);
+
+/* ---- multi-GPU row-block sharding: spike-tip exchange hooks (the host moves these buffers between
+ * neighbouring ranks with NCCL send/recv; sizes are (8*kt)^2 doubles for tips, 8*kt for vectors) -- */
+int spk_tip_size(spk_ctx *ctx, int *kp);
+int spk_get_boundary(spk_ctx *ctx, int which, double *dev_buf);   /* see SPK_BND_* */
+int spk_set_boundary(spk_ctx *ctx, int which, const double *dev_buf);
+enum {
+  SPK_BND_WT_FIRST = 0,  /* out: W^(t) pre-image of my first partition (St and C block) -> left rank   */
+  SPK_BND_VB_LAST  = 1,  /* out: V^(b) of my last partition                                           */
+  SPK_BND_REMOTE_WT = 2, /* in : right neighbour's W^(t)                                              */
+  SPK_BND_G_TOP = 3,     /* out: g^(t) of my first partition (per solve)                              */
+  SPK_BND_REMOTE_G_TOP = 4, /* in: right neighbour's g^(t)                                            */
+  SPK_BND_X_BOT = 5,     /* out: x^(b) of my last partition (per solve) -> right rank                 */
+  SPK_BND_REMOTE_X_BOT = 6, /* in: left neighbour's x^(b)                                             */
+  SPK_BND_X_TOP_REMOTE = 7, /* out: x^(t) solved for the right neighbour's first partition            */
+  SPK_BND_X_TOP = 8      /* in : my first partition's x^(t) as solved by the left rank                */
+};
+/* split-phase versions of factor/solve used when nranks > 1 (the host performs the exchanges
+ * between phases); with nranks == 1 spk_factor/spk_solve run all phases back to back. */
+int spk_factor_phase(spk_ctx *ctx, int phase);
+int spk_solve_phase(spk_ctx *ctx, int phase, const double *b, double *x, int nrhs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPIKE_B200_H */

@@ -1,0 +1,488 @@
+// capi.cu -- the C ABI declared in include/spike_b200.h: context management, partition planning,
+// factor / solve orchestration.  No CPU fallback: every entry point needs a usable sm_100 device.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "common.cuh"
+
+int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, const double* b_dev, double* x_dev,
+                   int* its, double* rnorm, int* converged);  // krylov.cu
+
+static char g_err[512] = "";
+
+extern "C" const char* spk_version(void) { return "spike_b200 0.1 (sm_100a, fp64 DMMA)"; }
+extern "C" const char* spk_last_error(const spk_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+extern "C" void spk_default_opts(spk_opts* o) {
+  memset(o, 0, sizeof(*o));
+  o->device = 0; o->stream = nullptr; o->partitions = 0; o->tip_tiles = 0; o->boost_rel = 1e-13;
+  o->mem = SPK_MEM_HOST; o->rank = 0; o->nranks = 1; o->row_offset = 0; o->n_global = 0;
+}
+
+static void free_band(spk_ctx* c) {
+  auto F = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
+  F(c->band); F(c->orig); F(c->dinv); F(c->d_pstart); F(c->Sb); F(c->St); F(c->Vb); F(c->Wt); F(c->Red);
+  F(c->RedPiv); F(c->work); F(c->gtip); F(c->xtip); F(c->xb); F(c->xt); F(c->corr);
+  F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->xtopRemote);
+  F(c->opA.ia); F(c->opA.ja); F(c->opA.a);
+  free(c->h_pstart); c->h_pstart = nullptr;
+  c->have_band = c->factored = 0;
+}
+
+extern "C" int spk_create(spk_ctx** out, const spk_opts* opts) {
+  if (!out) return SPK_ERR_ARG;
+  *out = nullptr;
+  spk_opts o;
+  if (opts) o = *opts; else spk_default_opts(&o);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device available (%s): the SPIKE engine has no CPU fallback",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return SPK_ERR_CUDA;
+  }
+  if (o.device < 0 || o.device >= ndev) { snprintf(g_err, sizeof(g_err), "bad device ordinal %d", o.device); return SPK_ERR_ARG; }
+  e = cudaSetDevice(o.device);
+  if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaSetDevice: %s", cudaGetErrorString(e)); return SPK_ERR_CUDA; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, o.device);
+  if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return SPK_ERR_CUDA; }
+  if (prop.major != 10) {
+    snprintf(g_err, sizeof(g_err), "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    return SPK_ERR_UNSUPPORTED;
+  }
+  spk_ctx* c = (spk_ctx*)calloc(1, sizeof(spk_ctx));
+  if (!c) return SPK_ERR_NOMEM;
+  c->opts = o;
+  if (c->opts.nranks <= 0) c->opts.nranks = 1;
+  c->stream = (cudaStream_t)o.stream;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaMalloc(&c->d_boost, sizeof(int64_t)) != cudaSuccess || cudaMalloc(&c->d_scalar, 64 * sizeof(double)) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaEventCreate(&c->evs0) != cudaSuccess || cudaEventCreate(&c->evs1) != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    free(c);
+    return SPK_ERR_CUDA;
+  }
+  *out = c;
+  return SPK_OK;
+}
+
+extern "C" int spk_destroy(spk_ctx** pc) {
+  if (!pc || !*pc) return SPK_OK;
+  spk_ctx* c = *pc;
+  cudaSetDevice(c->opts.device);
+  cudaStreamSynchronize(c->stream);
+  free_band(c);
+  cudaFree(c->d_boost); cudaFree(c->d_scalar);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evs0); cudaEventDestroy(c->evs1);
+  free(c);
+  *pc = nullptr;
+  return SPK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout + partition planning
+// ---------------------------------------------------------------------------------------------
+static int plan(spk_ctx* c, int64_t n, int k) {
+  if (n <= 0 || k < 0) { SPK_SET_ERR(c, "bad size n=%lld k=%d", (long long)n, k); return SPK_ERR_ARG; }
+  int kt = (k + 7) / 8;
+  if (kt < 2) kt = 2;
+  if (kt > SPK_MAX_KT) {
+    SPK_SET_ERR(c, "half-bandwidth %d > %d: the register-resident window kernel does not cover wide bands yet", k, 8 * SPK_MAX_KT);
+    return SPK_ERR_UNSUPPORTED;
+  }
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  free_band(c);
+  BandLayout& L = c->L;
+  L.n = n; L.k = k; L.kt = kt; L.tpr = 2 * kt + 1; L.nt = (n + 7) / 8;
+  c->kp = 8 * kt;
+  // partitions: every partition needs >= 2*kt tile rows (distinct top and bottom tips)
+  const int64_t minlen = std::max<int64_t>(2 * kt, 4);
+  int64_t P = c->opts.partitions > 0 ? c->opts.partitions : 2 * (int64_t)c->sm_count;
+  // keep partitions long enough that the truncation window is a small fraction of them
+  const int64_t want_len = std::max<int64_t>(minlen, 8 * kt);
+  if (c->opts.partitions <= 0) P = std::min<int64_t>(P, std::max<int64_t>(1, L.nt / want_len));
+  P = std::min<int64_t>(P, std::max<int64_t>(1, L.nt / minlen));
+  if (P < 1) P = 1;
+  c->P = (int)P;
+  c->h_pstart = (int64_t*)malloc(sizeof(int64_t) * (P + 1));
+  for (int64_t p = 0; p <= P; ++p) c->h_pstart[p] = L.nt * p / P;
+  int64_t minp = L.nt;
+  for (int64_t p = 0; p < P; ++p) minp = std::min(minp, c->h_pstart[p + 1] - c->h_pstart[p]);
+  int tip = c->opts.tip_tiles;
+  if (tip == 0) tip = 12 * kt;            // auto: 12 bandwidths of decay
+  if (tip < 0 || tip > minp) tip = (int)minp;
+  if (tip < kt) tip = (int)std::min<int64_t>(minp, kt);
+  c->tipT = tip;
+  if (P > 1 && minp < minlen) { SPK_SET_ERR(c, "partition too short (%lld tile rows < %lld)", (long long)minp, (long long)minlen); return SPK_ERR_ARG; }
+  if (L.nt < kt) { SPK_SET_ERR(c, "matrix smaller than one band window (n=%lld, k=%d)", (long long)n, k); return SPK_ERR_UNSUPPORTED; }
+
+  const size_t kk = (size_t)c->kp * c->kp;
+  SPK_CUDA(c, cudaMalloc(&c->band, sizeof(double) * (size_t)L.elems()));
+  SPK_CUDA(c, cudaMalloc(&c->dinv, sizeof(double) * (size_t)L.nt * 64));
+  SPK_CUDA(c, cudaMalloc(&c->d_pstart, sizeof(int64_t) * (P + 1)));
+  SPK_CUDA(c, cudaMemcpyAsync(c->d_pstart, c->h_pstart, sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, c->stream));
+  SPK_CUDA(c, cudaMalloc(&c->Sb, sizeof(double) * kk * P));
+  SPK_CUDA(c, cudaMalloc(&c->St, sizeof(double) * kk * P));
+  SPK_CUDA(c, cudaMalloc(&c->Vb, sizeof(double) * kk * P));
+  SPK_CUDA(c, cudaMalloc(&c->Wt, sizeof(double) * kk * P));
+  SPK_CUDA(c, cudaMalloc(&c->Red, sizeof(double) * kk * P));
+  SPK_CUDA(c, cudaMalloc(&c->work, sizeof(double) * (size_t)L.nt * 8 * 3));
+  SPK_CUDA(c, cudaMalloc(&c->gtip, sizeof(double) * 2 * (size_t)P * c->kp));
+  SPK_CUDA(c, cudaMemsetAsync(c->gtip, 0, sizeof(double) * 2 * (size_t)P * c->kp, c->stream));
+  SPK_CUDA(c, cudaMalloc(&c->remoteWt, sizeof(double) * kk));
+  c->work_elems = L.nt * 8;
+  return SPK_OK;
+}
+
+static int finish_band(spk_ctx* c) {
+  int rc = spk_launch_absmax(c, c->band, c->d_scalar);
+  if (rc) return rc;
+  SPK_CUDA(c, cudaMemcpyAsync(&c->anorm_max, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->have_band = 1; c->factored = 0; c->boosted = 0;
+  if (c->keep_orig) {
+    SPK_CUDA(c, cudaMalloc(&c->orig, sizeof(double) * (size_t)c->L.elems()));
+    SPK_CUDA(c, cudaMemcpyAsync(c->orig, c->band, sizeof(double) * (size_t)c->L.elems(), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return SPK_OK;
+}
+
+extern "C" int spk_keep_original(spk_ctx* c, int keep) {
+  if (!c) return SPK_ERR_ARG;
+  c->keep_orig = keep ? 1 : 0;
+  if (keep && c->have_band && !c->factored && !c->orig) {
+    SPK_CUDA(c, cudaSetDevice(c->opts.device));
+    SPK_CUDA(c, cudaMalloc(&c->orig, sizeof(double) * (size_t)c->L.elems()));
+    SPK_CUDA(c, cudaMemcpyAsync(c->orig, c->band, sizeof(double) * (size_t)c->L.elems(), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return SPK_OK;
+}
+
+extern "C" int spk_set_band_dense(spk_ctx* c, int64_t n, int k, const double* band, int layout, int mem) {
+  if (!c || !band) return SPK_ERR_ARG;
+  if (layout != SPK_LAYOUT_ROWS && layout != SPK_LAYOUT_DIAGS) { SPK_SET_ERR(c, "bad layout %d", layout); return SPK_ERR_ARG; }
+  int rc = plan(c, n, k);
+  if (rc) return rc;
+  const size_t bytes = sizeof(double) * (size_t)n * (2 * (size_t)k + 1);
+  const double* src = band;
+  double* tmp = nullptr;
+  if (mem == SPK_MEM_HOST) {
+    SPK_CUDA(c, cudaMalloc(&tmp, bytes));
+    SPK_CUDA(c, cudaMemcpyAsync(tmp, band, bytes, cudaMemcpyHostToDevice, c->stream));
+    src = tmp;
+  }
+  rc = spk_launch_pack_dense(c, src, layout);
+  if (rc == SPK_OK) rc = finish_band(c);
+  if (tmp) { cudaStreamSynchronize(c->stream); cudaFree(tmp); }
+  return rc;
+}
+
+extern "C" int spk_set_band_synthetic(spk_ctx* c, int64_t n, int k, uint64_t seed, double delta) {
+  if (!c) return SPK_ERR_ARG;
+  int rc = plan(c, n, k);
+  if (rc) return rc;
+  rc = spk_launch_generate(c, seed, delta);
+  if (rc) return rc;
+  return finish_band(c);
+}
+
+static int upload_csr(spk_ctx* c, CsrDev& A, int n, const int* ia, const int* ja, const double* a) {
+  const int64_t nnz = ia[n];
+  A.n = n; A.nnz = nnz;
+  SPK_CUDA(c, cudaMalloc(&A.ia, sizeof(int) * (size_t)(n + 1)));
+  SPK_CUDA(c, cudaMalloc(&A.ja, sizeof(int) * (size_t)std::max<int64_t>(nnz, 1)));
+  SPK_CUDA(c, cudaMalloc(&A.a, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
+  SPK_CUDA(c, cudaMemcpyAsync(A.ia, ia, sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream));
+  SPK_CUDA(c, cudaMemcpyAsync(A.ja, ja, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+  SPK_CUDA(c, cudaMemcpyAsync(A.a, a, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+  return SPK_OK;
+}
+
+// k / frac decision of MatCreateSubMatrixBanded on the PERMUTED matrix, in the reference's row-major
+// summation order (host; O(nnz)).  /root/reference/src/matbanded.c:38-56,104-105.
+static int band_select_host(int n, const int* ia, const int* ja, const double* a, const int* rowperm, const int* icol,
+                            int kmax, double frac, int* k_out, double* frac_out) {
+  std::vector<double> w((size_t)std::max(n, 1), 0.0);
+  double normA = 0.0, normB = 0.0;
+  std::vector<std::pair<int, double>> rowbuf;
+  for (int i = 0; i < n; ++i) {
+    const int r = rowperm ? rowperm[i] : i;
+    if (icol) {
+      // MatPermute stores each permuted row sorted by (new) column; the weights are summed in that order
+      rowbuf.clear();
+      for (int q = ia[r]; q < ia[r + 1]; ++q) rowbuf.emplace_back(icol[ja[q]], a[q]);
+      std::stable_sort(rowbuf.begin(), rowbuf.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+      for (auto& e : rowbuf) { w[std::abs(i - e.first)] += std::fabs(e.second); normA += std::fabs(e.second); }
+    } else {
+      for (int q = ia[r]; q < ia[r + 1]; ++q) { w[std::abs(i - ja[q])] += std::fabs(a[q]); normA += std::fabs(a[q]); }
+    }
+  }
+  int k;
+  for (k = 0; k < kmax; ++k) {
+    if (k >= n) return -1;  // the reference would read past the weight vector here (matbanded.c:54)
+    normB += w[k];
+    if (normB >= frac * normA) break;
+  }
+  *k_out = k; *frac_out = normB / normA;
+  return 0;
+}
+
+extern "C" int spk_set_band_csr(spk_ctx* c, int n, const int* ia, const int* ja, const double* a, const int* rowperm,
+                                const int* colperm, int* kmax, double* frac) {
+  if (!c || !ia || !ja || !a || !kmax || !frac || n <= 0) return SPK_ERR_ARG;
+  std::vector<int> icol;
+  if (colperm) {
+    icol.assign(n, -1);
+    for (int j = 0; j < n; ++j) {
+      if (colperm[j] < 0 || colperm[j] >= n || icol[colperm[j]] >= 0) { SPK_SET_ERR(c, "colperm is not a permutation"); return SPK_ERR_ARG; }
+      icol[colperm[j]] = j;
+    }
+  }
+  if (rowperm) for (int i = 0; i < n; ++i) if (rowperm[i] < 0 || rowperm[i] >= n) { SPK_SET_ERR(c, "rowperm out of range"); return SPK_ERR_ARG; }
+  int k; double f;
+  if (band_select_host(n, ia, ja, a, rowperm, colperm ? icol.data() : nullptr, *kmax, *frac, &k, &f)) {
+    SPK_SET_ERR(c, "kmax=%d exceeds the matrix order %d before the norm fraction is reached (out of bounds in the reference)", *kmax, n);
+    return SPK_ERR_ARG;
+  }
+  int rc = plan(c, n, k);
+  if (rc) return rc;
+  CsrDev A;
+  rc = upload_csr(c, A, n, ia, ja, a);
+  int *d_rp = nullptr, *d_ic = nullptr;
+  if (rc == SPK_OK && rowperm) {
+    SPK_CUDA(c, cudaMalloc(&d_rp, sizeof(int) * (size_t)n));
+    SPK_CUDA(c, cudaMemcpyAsync(d_rp, rowperm, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (rc == SPK_OK && colperm) {
+    SPK_CUDA(c, cudaMalloc(&d_ic, sizeof(int) * (size_t)n));
+    SPK_CUDA(c, cudaMemcpyAsync(d_ic, icol.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (rc == SPK_OK) rc = spk_launch_pack_csr(c, A, d_rp, d_ic);
+  if (rc == SPK_OK) rc = finish_band(c);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(A.ia); cudaFree(A.ja); cudaFree(A.a); cudaFree(d_rp); cudaFree(d_ic);
+  if (rc == SPK_OK) { *kmax = k; *frac = f; c->frac = f; }
+  return rc;
+}
+
+extern "C" int spk_set_operator_csr(spk_ctx* c, int n, const int* ia, const int* ja, const double* a, const int* rowperm,
+                                    const int* colperm) {
+  if (!c || !ia || !ja || !a || n <= 0) return SPK_ERR_ARG;
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  if (c->opA.ia) { cudaFree(c->opA.ia); cudaFree(c->opA.ja); cudaFree(c->opA.a); c->opA = CsrDev(); }
+  // permute on the host exactly like MatPermute (rows gathered, columns renumbered), then upload
+  const int64_t nnz = ia[n];
+  std::vector<int> icol;
+  if (colperm) { icol.assign(n, 0); for (int j = 0; j < n; ++j) icol[colperm[j]] = j; }
+  std::vector<int> pia(n + 1), pja((size_t)nnz);
+  std::vector<double> pa((size_t)nnz);
+  pia[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const int r = rowperm ? rowperm[i] : i;
+    int o = pia[i];
+    for (int q = ia[r]; q < ia[r + 1]; ++q, ++o) { pja[o] = colperm ? icol[ja[q]] : ja[q]; pa[o] = a[q]; }
+    pia[i + 1] = o;
+  }
+  int rc = upload_csr(c, c->opA, n, pia.data(), pja.data(), pa.data());
+  SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return rc;
+}
+
+extern "C" int spk_get_band_rows(spk_ctx* c, double* rows_host) {
+  if (!c || !rows_host) return SPK_ERR_ARG;
+  if (!c->have_band) { SPK_SET_ERR(c, "no band set"); return SPK_ERR_STATE; }
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  const size_t bytes = sizeof(double) * (size_t)c->L.n * (2 * (size_t)c->L.k + 1);
+  double* tmp;
+  SPK_CUDA(c, cudaMalloc(&tmp, bytes));
+  int rc = spk_launch_unpack_rows(c, c->band, tmp);
+  if (rc == SPK_OK) {
+    cudaError_t e = cudaMemcpyAsync(rows_host, tmp, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { SPK_SET_ERR(c, "copy back failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
+  }
+  cudaFree(tmp);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// factor
+// ---------------------------------------------------------------------------------------------
+extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
+  if (!c) return SPK_ERR_ARG;
+  if (!c->have_band) { SPK_SET_ERR(c, "spk_factor: no band set"); return SPK_ERR_STATE; }
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  int rc = SPK_OK;
+  if (phase == 0) {
+    if (c->factored) { SPK_SET_ERR(c, "band already factored (factorisation is in place)"); return SPK_ERR_STATE; }
+    c->launches = 0;
+    SPK_CUDA(c, cudaMemsetAsync(c->d_boost, 0, sizeof(int64_t), c->stream));
+    SPK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    // W^(t) needs the unfactored top windows: UL pass first (read only), then the in-place LU
+    rc = spk_launch_ul_tips(c);
+    if (rc == SPK_OK) rc = spk_launch_lu(c);
+    if (rc) return rc;
+    return SPK_OK;
+  }
+  if (phase == 1) {
+    rc = spk_launch_tips(c, 0, c->P - 1);
+    if (rc) return rc;
+    SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    c->factored = 1; c->timed_factor = 1;
+    return SPK_OK;
+  }
+  SPK_SET_ERR(c, "bad factor phase %d", phase);
+  return SPK_ERR_ARG;
+}
+
+extern "C" int spk_factor(spk_ctx* c) {
+  int rc = spk_factor_phase(c, 0);
+  if (rc == SPK_OK) rc = spk_factor_phase(c, 1);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// solve (device pointers, one right-hand side)
+// ---------------------------------------------------------------------------------------------
+int spk_solve_dev(spk_ctx* c, const double* b, double* x) {
+  int rc = spk_launch_sweep(c, b, x, 1, c->L.n);
+  if (rc) return rc;
+  if (c->P > 1) {
+    rc = spk_launch_reduced_solve(c, x, 1, c->L.n, 0, c->P - 1);
+    if (rc) return rc;
+    rc = spk_launch_corrections(c, x, 1, c->L.n);
+  }
+  return rc;
+}
+
+extern "C" int spk_solve_phase(spk_ctx* c, int phase, const double* b, double* x, int nrhs) {
+  (void)phase; (void)b; (void)x; (void)nrhs;
+  SPK_SET_ERR(c, "split-phase solve is only needed for nranks > 1 and is not wired in this build");
+  return SPK_ERR_UNSUPPORTED;
+}
+
+extern "C" int spk_solve(spk_ctx* c, const double* b, double* x, int nrhs) {
+  if (!c || !b || !x || nrhs < 1) return SPK_ERR_ARG;
+  if (!c->factored) { SPK_SET_ERR(c, "spk_solve before spk_factor"); return SPK_ERR_STATE; }
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  const int64_t n = c->L.n;
+  const double* bd = b; double* xd = x;
+  double* tmp = nullptr;
+  if (c->opts.mem == SPK_MEM_HOST) {
+    SPK_CUDA(c, cudaMalloc(&tmp, sizeof(double) * (size_t)n * nrhs));
+    SPK_CUDA(c, cudaMemcpyAsync(tmp, b, sizeof(double) * (size_t)n * nrhs, cudaMemcpyHostToDevice, c->stream));
+    bd = tmp; xd = tmp;
+  }
+  const int launches0 = c->launches;
+  SPK_CUDA(c, cudaEventRecord(c->evs0, c->stream));
+  int rc = SPK_OK;
+  for (int r = 0; r < nrhs && rc == SPK_OK; ++r) rc = spk_solve_dev(c, bd + (size_t)r * n, xd + (size_t)r * n);
+  if (rc == SPK_OK) {
+    cudaError_t e = cudaEventRecord(c->evs1, c->stream);
+    c->timed_solve = 1;
+    if (e == cudaSuccess && tmp) e = cudaMemcpyAsync(x, tmp, sizeof(double) * (size_t)n * nrhs, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && tmp) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { SPK_SET_ERR(c, "solve copy-back failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
+  }
+  (void)launches0;
+  if (tmp) { cudaStreamSynchronize(c->stream); cudaFree(tmp); }
+  return rc;
+}
+
+extern "C" int spk_mult(spk_ctx* c, const double* x, double* y) {
+  if (!c || !x || !y) return SPK_ERR_ARG;
+  if (!c->have_band) { SPK_SET_ERR(c, "spk_mult: no band set"); return SPK_ERR_STATE; }
+  const double* A = c->factored ? c->orig : c->band;
+  if (!A) { SPK_SET_ERR(c, "spk_mult after spk_factor needs spk_keep_original(ctx,1) before the band is set"); return SPK_ERR_STATE; }
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  const int64_t n = c->L.n;
+  if (c->opts.mem == SPK_MEM_HOST) {
+    double* tx; double* ty;
+    SPK_CUDA(c, cudaMalloc(&tx, sizeof(double) * (size_t)n));
+    SPK_CUDA(c, cudaMalloc(&ty, sizeof(double) * (size_t)n));
+    SPK_CUDA(c, cudaMemcpyAsync(tx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    int rc = spk_launch_matmult(c, A, tx, ty);
+    cudaError_t e = cudaMemcpyAsync(y, ty, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(tx); cudaFree(ty);
+    if (rc == SPK_OK && e != cudaSuccess) { SPK_SET_ERR(c, "mult copy failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
+    return rc;
+  }
+  return spk_launch_matmult(c, A, x, y);
+}
+
+extern "C" int spk_permute(spk_ctx* c, const int* idx, int inverse, double* v, int64_t n) {
+  if (!c || !idx || !v || n <= 0) return SPK_ERR_ARG;
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  int* d_idx; double *d_in, *d_out;
+  SPK_CUDA(c, cudaMalloc(&d_idx, sizeof(int) * (size_t)n));
+  SPK_CUDA(c, cudaMalloc(&d_out, sizeof(double) * (size_t)n));
+  SPK_CUDA(c, cudaMemcpyAsync(d_idx, idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  const bool host = (c->opts.mem == SPK_MEM_HOST);
+  if (host) {
+    SPK_CUDA(c, cudaMalloc(&d_in, sizeof(double) * (size_t)n));
+    SPK_CUDA(c, cudaMemcpyAsync(d_in, v, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  } else d_in = v;
+  int rc = spk_launch_gather(c, d_idx, inverse, d_in, d_out, n);
+  cudaError_t e = cudaMemcpyAsync(v, d_out, sizeof(double) * (size_t)n, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_idx); cudaFree(d_out); if (host) cudaFree(d_in);
+  if (rc == SPK_OK && e != cudaSuccess) { SPK_SET_ERR(c, "permute copy failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
+  return rc;
+}
+
+extern "C" int spk_krylov(spk_ctx* c, int method, int restart, double rtol, int maxit, const double* b, double* x, int* its,
+                          double* rnorm, int* converged) {
+  if (!c || !b || !x || !its || !rnorm) return SPK_ERR_ARG;
+  if (!c->factored) { SPK_SET_ERR(c, "spk_krylov before spk_factor"); return SPK_ERR_STATE; }
+  if (!c->opA.ia && !c->orig) { SPK_SET_ERR(c, "spk_krylov needs an operator: spk_set_operator_csr or spk_keep_original"); return SPK_ERR_STATE; }
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  const int64_t n = c->L.n;
+  const double* bd = b; double* xd = x;
+  double *tb = nullptr, *tx = nullptr;
+  if (c->opts.mem == SPK_MEM_HOST) {
+    SPK_CUDA(c, cudaMalloc(&tb, sizeof(double) * (size_t)n));
+    SPK_CUDA(c, cudaMalloc(&tx, sizeof(double) * (size_t)n));
+    SPK_CUDA(c, cudaMemcpyAsync(tb, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    bd = tb; xd = tx;
+  }
+  int conv = 0;
+  int rc = spk_krylov_run(c, method, restart, rtol, maxit, bd, xd, its, rnorm, &conv);
+  if (converged) *converged = conv;
+  if (rc == SPK_OK && tx) {
+    cudaError_t e = cudaMemcpyAsync(x, tx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { SPK_SET_ERR(c, "krylov copy-back failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
+  }
+  if (tb) { cudaFree(tb); cudaFree(tx); }
+  return rc;
+}
+
+extern "C" int spk_view(spk_ctx* c, spk_info* info) {
+  if (!c || !info) return SPK_ERR_ARG;
+  memset(info, 0, sizeof(*info));
+  if (!c->have_band) return SPK_OK;
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+  SPK_CUDA(c, cudaMemcpy(&c->boosted, c->d_boost, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  info->n = c->L.n; info->n_padded = c->L.nt * 8; info->k = c->L.k; info->k_padded = c->kp; info->kt = c->L.kt;
+  info->partitions = c->P; info->tip_tiles = c->tipT; info->boosted_pivots = c->boosted; info->factored = c->factored;
+  info->frac = c->frac; info->anorm_max = c->anorm_max; info->band_bytes = (int64_t)sizeof(double) * c->L.elems();
+  info->kernel_launches = c->launches;
+  if (c->timed_factor) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) info->factor_ms = ms; }
+  if (c->timed_solve) { float ms = 0; if (cudaEventElapsedTime(&ms, c->evs0, c->evs1) == cudaSuccess) info->solve_ms = ms; }
+  return SPK_OK;
+}
+
+// ---- multi-GPU boundary hooks (wired in a later milestone) -----------------------------------
+extern "C" int spk_tip_size(spk_ctx* c, int* kp) { if (!c || !kp) return SPK_ERR_ARG; *kp = c->kp; return SPK_OK; }
+extern "C" int spk_get_boundary(spk_ctx* c, int which, double* dev_buf) {
+  (void)which; (void)dev_buf; SPK_SET_ERR(c, "boundary exchange not wired in this build"); return SPK_ERR_UNSUPPORTED;
+}
+extern "C" int spk_set_boundary(spk_ctx* c, int which, const double* dev_buf) {
+  (void)which; (void)dev_buf; SPK_SET_ERR(c, "boundary exchange not wired in this build"); return SPK_ERR_UNSUPPORTED;
+}

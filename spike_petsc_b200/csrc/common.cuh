@@ -1,0 +1,154 @@
+// common.cuh -- shared definitions of the SPIKE engine (device band layout, context, helpers).
+//
+// Device band layout ("tile-major band"): the matrix is cut into 8x8 tiles; tile row I holds the
+// 2*KT+1 tiles (I, I-KT .. I+KT) contiguously, each tile 64 doubles row-major (512 B):
+//     tile(I,J) at  band + ((I*(2KT+1) + (J-I+KT)) * 64),   element (r,c) at  + r*8 + c
+// KT = ceil(K/8).  Rows are padded to NT*8 with identity rows; tiles that stick out of the matrix
+// are stored as zeros.  A tile is exactly one DMMA m8n8k4 accumulator fragment (lane l holds the
+// 16 B at doubles 2l,2l+1), so LU tiles move between HBM and tensor-core registers with one
+// coalesced 128-bit access per lane, and a tile row is one contiguous chunk for bulk copies.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../include/spike_b200.h"
+
+#define SPK_TILE 8
+#define SPK_TILE_ELEMS 64
+#define SPK_MAX_KT 16
+
+struct BandLayout {
+  int64_t n;    // rows of the matrix
+  int64_t nt;   // tile rows (ceil(n/8))
+  int k;        // half bandwidth
+  int kt;       // ceil(k/8)
+  int tpr;      // tiles per tile row = 2*kt+1
+  __host__ __device__ int64_t tile_off(int64_t I, int64_t J) const { return (I * tpr + (J - I + kt)) * SPK_TILE_ELEMS; }
+  __host__ __device__ int64_t elems() const { return nt * (int64_t)tpr * SPK_TILE_ELEMS; }
+  // element (i,j), |i-j| <= 8*kt+7 assumed in band storage range
+  __host__ __device__ int64_t elem_off(int64_t i, int64_t j) const {
+    return tile_off(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7);
+  }
+};
+
+struct CsrDev {
+  int n = 0; int64_t nnz = 0;
+  int *ia = nullptr, *ja = nullptr; double *a = nullptr;
+};
+
+struct spk_ctx {
+  spk_opts opts;
+  cudaStream_t stream;
+  int sm_count;
+  BandLayout L;
+  int have_band, factored, keep_orig;
+  double *band;        // device band, factored in place
+  double *orig;        // optional copy of the unfactored band (for spk_mult after factor)
+  double *dinv;        // nt tiles: inverse diagonal blocks (Linv strictly-lower | Uinv upper)
+  // partitions
+  int P;               // partitions
+  int tipT;            // truncation window in tile rows (>= 2*kt), <= min partition length
+  int64_t *h_pstart;   // host copy, P+1 tile-row boundaries
+  int64_t *d_pstart;
+  // tips / reduced system: interface i couples partition i (bottom) and i+1 (top), i in [0,P-1)
+  // plus one extra slot (index P-1) for the boundary with the right-neighbour rank.
+  int kp;              // 8*kt
+  double *Sb;          // P   * kp*kp : bottom Schur blocks S_b (row-major kp x kp)
+  double *St;          // P   * kp*kp : top Schur blocks from the UL window
+  double *Vb;          // P   * kp*kp : V^(b)
+  double *Wt;          // P   * kp*kp : W^(t)  (Wt[i] belongs to partition i; partition 0 unused unless rank>0)
+  double *Red;         // P   * kp*kp : LU (partial pivoting) of I - Wt[i+1] Vb[i]
+  int    *RedPiv;      // P   * kp
+  // per-solve work
+  double *work;        // n_padded * max_nrhs
+  double *gtip, *xtip; // (P+1) * 2 * kp
+  double *xb, *xt;     // P * kp each
+  double *corr;        // P * 2 * tipT*8
+  int64_t work_elems;
+  // remote (multi-GPU) boundary buffers
+  double *remoteWt, *remoteGtop, *remoteXbot, *xtopRemote;
+  int have_remote_wt;
+  // operator for Krylov
+  CsrDev opA;
+  // bookkeeping
+  double anorm_max, frac;
+  int64_t *d_boost;    // device counter
+  double *d_scalar;    // small device scratch (64 doubles)
+  int64_t boosted;
+  float factor_ms, solve_ms;
+  int launches;
+  cudaEvent_t ev0, ev1;     // factor start/stop
+  cudaEvent_t evs0, evs1;   // solve start/stop
+  int timed_factor, timed_solve;
+  char err[512];
+};
+
+#define SPK_SET_ERR(ctx, ...) do { if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); } while (0)
+#define SPK_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+    SPK_SET_ERR(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); return SPK_ERR_CUDA; } } while (0)
+#define SPK_KERNEL_CHECK(ctx) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { \
+    SPK_SET_ERR(ctx, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); return SPK_ERR_CUDA; } \
+    (ctx)->launches++; } while (0)
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spk_splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double spk_u01(uint64_t seed, uint64_t counter) {
+  return (double)(spk_splitmix64(seed ^ counter) >> 11) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// D(8x8) += A(8x4) * B(4x8), fp64 tensor core (SASS DMMA.8x8x4).
+// Fragments: a = A[lane/4][lane%4], b = B[lane%4][lane/4], c0/c1 = C[lane/4][2*(lane%4) + 0/1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- kernels' host launchers (defined in the .cu files) ---------------------------------------
+int spk_launch_generate(spk_ctx* c, uint64_t seed, double delta);
+int spk_launch_pack_dense(spk_ctx* c, const double* src_dev, int layout);
+int spk_launch_pack_csr(spk_ctx* c, const CsrDev& A, const int* rowperm_dev, const int* icolperm_dev);
+int spk_launch_unpack_rows(spk_ctx* c, const double* band, double* rows_dev);
+int spk_launch_absmax(spk_ctx* c, const double* band, double* out_dev);
+int spk_launch_matmult(spk_ctx* c, const double* band, const double* x, double* y);
+int spk_launch_lu(spk_ctx* c);            // per-partition LU (+ S_b capture, dinv)
+int spk_launch_ul_tips(spk_ctx* c);       // UL window -> S_t
+int spk_launch_tips(spk_ctx* c, int iface_lo, int iface_hi);  // Vb, Wt, reduced LU for interfaces [lo,hi)
+int spk_launch_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld);   // g = D^-1 b
+int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int iface_lo, int iface_hi);
+int spk_launch_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld);
+int spk_launch_gather(spk_ctx* c, const int* idx_dev, int inverse, const double* in, double* out, int64_t n);
+int spk_launch_csr_mult(spk_ctx* c, const CsrDev& A, const double* x, double* y);

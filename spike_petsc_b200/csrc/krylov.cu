@@ -1,0 +1,196 @@
+// krylov.cu -- device-resident left-preconditioned GMRES(m) / BiCGStab around the SPIKE apply.
+// Replaces the inner KSPSolve of KSPSolve_Reorder (/root/reference/src/kspreorder.c:124) with PETSc's
+// defaults restated: x0 = 0, left preconditioning, preconditioned residual norm,
+// convergence ||r_k|| <= rtol * ||M^{-1} b||, GMRES restart 30 with classical Gram-Schmidt.
+// Vectors never leave the GPU; only the (j+1) Hessenberg entries / scalars per iteration do.
+#include <cmath>
+#include <vector>
+#include "common.cuh"
+
+int spk_solve_dev(spk_ctx* c, const double* b, double* x);
+
+// out[v] = <V_v, w>, v < nv <= 8, all in one pass over w (warp-shuffle + atomic accumulation)
+__global__ void k_multi_dot(const double* __restrict__ V, int64_t ld, int nv, const double* __restrict__ w, int64_t n,
+                            double* __restrict__ out) {
+  double acc[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) acc[v] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double wi = w[i];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) if (v < nv) acc[v] = fma(V[(int64_t)v * ld + i], wi, acc[v]);
+  }
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    if (v < nv) {
+      double s = acc[v];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(out + v, s);
+    }
+  }
+}
+// w -= sum_v h[v] V_v
+__global__ void k_multi_axpy(const double* __restrict__ V, int64_t ld, int nv, const double* __restrict__ h, double* __restrict__ w, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double s = w[i];
+    for (int v = 0; v < nv; ++v) s = fma(-h[v], V[(int64_t)v * ld + i], s);
+    w[i] = s;
+  }
+}
+// y = a*x + b*y   (b may be 0 -> y = a*x without reading y)
+__global__ void k_axpby(double a, const double* __restrict__ x, double b, double* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
+}
+// z = x + a*y + b*w   (pointers may alias z)
+__global__ void k_lin3(const double* x, double a, const double* y, double b, const double* w, double* z, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    z[i] = x[i] + a * y[i] + (w ? b * w[i] : 0.0);
+}
+
+namespace {
+struct Kry {
+  spk_ctx* c; int64_t n; int grid;
+  double* hdev;  // 64 doubles scratch on device (c->d_scalar)
+  int fail = 0;
+  void check() { if (cudaGetLastError() != cudaSuccess) fail = 1; c->launches++; }
+  int amul(const double* x, double* y) {
+    if (c->opA.ia) return spk_launch_csr_mult(c, c->opA, x, y);
+    return spk_launch_matmult(c, c->orig, x, y);
+  }
+  int pc(const double* x, double* y) { return spk_solve_dev(c, x, y); }
+  void dots(const double* V, int64_t ld, int nv, const double* w, double* host) {
+    for (int v0 = 0; v0 < nv; v0 += 8) {
+      const int m = nv - v0 < 8 ? nv - v0 : 8;
+      cudaMemsetAsync(hdev + v0, 0, sizeof(double) * m, c->stream);
+      k_multi_dot<<<grid, 256, 0, c->stream>>>(V + (int64_t)v0 * ld, ld, m, w, n, hdev + v0);
+      check();
+    }
+    cudaMemcpyAsync(host, hdev, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) fail = 1;
+  }
+  double dot(const double* x, const double* y) { double h; dots(x, n, 1, y, &h); return h; }
+  void axpby(double a, const double* x, double b, double* y) { k_axpby<<<grid, 256, 0, c->stream>>>(a, x, b, y, n); check(); }
+  void lin3(const double* x, double a, const double* y, double b, const double* w, double* z) { k_lin3<<<grid, 256, 0, c->stream>>>(x, a, y, b, w, z, n); check(); }
+};
+}  // namespace
+
+int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, const double* b, double* x, int* its,
+                   double* rnorm, int* converged) {
+  const int64_t n = c->L.n;
+  Kry K{c, n, c->sm_count * 8, c->d_scalar};
+  const int m = restart > 0 ? restart : 30;
+  if (m > 60) { SPK_SET_ERR(c, "restart %d too large (max 60)", m); return SPK_ERR_ARG; }
+  int it = 0, conv = 0;
+  double res = 0.0;
+  int rc = SPK_OK;
+  SPK_CUDA(c, cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, c->stream));
+  if (method == SPK_KSP_GMRES) {
+    double *V, *t;
+    SPK_CUDA(c, cudaMalloc(&V, sizeof(double) * (size_t)n * (m + 1)));
+    SPK_CUDA(c, cudaMalloc(&t, sizeof(double) * (size_t)n));
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
+    if ((rc = K.pc(b, V))) goto gdone;
+    {
+      const double bnorm = std::sqrt(K.dot(V, V));
+      res = bnorm;
+      if (bnorm == 0.0) { conv = 1; goto gdone; }
+      bool first = true;
+      while (it < maxit && !conv) {
+        if (!first) {  // r = M^{-1}(b - A x)
+          if ((rc = K.amul(x, t))) goto gdone;
+          K.axpby(1.0, b, -1.0, t);
+          if ((rc = K.pc(t, V))) goto gdone;
+          res = std::sqrt(K.dot(V, V));
+          if (res <= rtol * bnorm) { conv = 1; break; }
+        }
+        first = false;
+        K.axpby(1.0 / res, V, 0.0, V);
+        std::fill(g.begin(), g.end(), 0.0);
+        g[0] = res;
+        int j;
+        for (j = 0; j < m && it < maxit; ++j) {
+          double* vj1 = V + (size_t)(j + 1) * n;
+          if ((rc = K.amul(V + (size_t)j * n, t))) goto gdone;
+          if ((rc = K.pc(t, vj1))) goto gdone;
+          K.dots(V, n, j + 1, vj1, hcol.data());  // classical Gram-Schmidt: all dots against the unmodified w
+          SPK_CUDA(c, cudaMemcpyAsync(K.hdev, hcol.data(), sizeof(double) * (j + 1), cudaMemcpyHostToDevice, c->stream));
+          k_multi_axpy<<<K.grid, 256, 0, c->stream>>>(V, n, j + 1, K.hdev, vj1, n);
+          K.check();
+          const double hn = std::sqrt(K.dot(vj1, vj1));
+          for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
+          H[(size_t)(j + 1) * m + j] = hn;
+          if (hn != 0.0) K.axpby(1.0 / hn, vj1, 0.0, vj1);
+          for (int i = 0; i < j; ++i) {
+            const double a0 = H[(size_t)i * m + j], a1 = H[(size_t)(i + 1) * m + j];
+            H[(size_t)i * m + j] = cs[i] * a0 + sn[i] * a1;
+            H[(size_t)(i + 1) * m + j] = -sn[i] * a0 + cs[i] * a1;
+          }
+          const double a0 = H[(size_t)j * m + j], a1 = H[(size_t)(j + 1) * m + j], d = std::hypot(a0, a1);
+          cs[j] = a0 / d; sn[j] = a1 / d;
+          H[(size_t)j * m + j] = d; H[(size_t)(j + 1) * m + j] = 0.0;
+          g[j + 1] = -sn[j] * g[j]; g[j] = cs[j] * g[j];
+          ++it;
+          res = std::fabs(g[j + 1]);
+          if (res <= rtol * bnorm) { conv = 1; ++j; break; }
+        }
+        const int jj = j;
+        for (int i = jj - 1; i >= 0; --i) {
+          double s = g[i];
+          for (int q = i + 1; q < jj; ++q) s -= H[(size_t)i * m + q] * y[q];
+          y[i] = s / H[(size_t)i * m + i];
+        }
+        // x += V y  (reuse multi_axpy with negated coefficients)
+        for (int i = 0; i < jj; ++i) hcol[i] = -y[i];
+        SPK_CUDA(c, cudaMemcpyAsync(K.hdev, hcol.data(), sizeof(double) * jj, cudaMemcpyHostToDevice, c->stream));
+        k_multi_axpy<<<K.grid, 256, 0, c->stream>>>(V, n, jj, K.hdev, x, n);
+        K.check();
+        SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+      }
+    }
+  gdone:
+    cudaStreamSynchronize(c->stream);
+    cudaFree(V); cudaFree(t);
+  } else {
+    double *r, *rh, *p, *v, *s, *t, *tmp;
+    SPK_CUDA(c, cudaMalloc(&r, sizeof(double) * (size_t)n * 7));
+    rh = r + n; p = rh + n; v = p + n; s = v + n; t = s + n; tmp = t + n;
+    SPK_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * (size_t)n * 2, c->stream));
+    double rho = 1.0, alpha = 1.0, omega = 1.0;
+    if ((rc = K.pc(b, r))) goto bdone;
+    {
+      const double bnorm = std::sqrt(K.dot(r, r));
+      res = bnorm;
+      SPK_CUDA(c, cudaMemcpyAsync(rh, r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+      if (bnorm == 0.0) conv = 1;
+      while (!conv && it < maxit) {
+        const double rho1 = K.dot(rh, r);
+        if (rho1 == 0.0) break;
+        const double beta = (rho1 / rho) * (alpha / omega);
+        // p = r + beta (p - omega v)
+        K.lin3(r, beta, p, -beta * omega, v, p);
+        if ((rc = K.amul(p, tmp))) goto bdone;
+        if ((rc = K.pc(tmp, v))) goto bdone;
+        alpha = rho1 / K.dot(rh, v);
+        K.lin3(r, -alpha, v, 0.0, nullptr, s);
+        if ((rc = K.amul(s, tmp))) goto bdone;
+        if ((rc = K.pc(tmp, t))) goto bdone;
+        const double tt = K.dot(t, t);
+        omega = (tt == 0.0) ? 0.0 : K.dot(t, s) / tt;
+        K.lin3(x, alpha, p, omega, s, x);
+        K.lin3(s, -omega, t, 0.0, nullptr, r);
+        rho = rho1;
+        ++it;
+        res = std::sqrt(K.dot(r, r));
+        if (res <= rtol * bnorm) conv = 1;
+        if (omega == 0.0) break;
+      }
+    }
+  bdone:
+    cudaStreamSynchronize(c->stream);
+    cudaFree(r);
+  }
+  if (K.fail && rc == SPK_OK) { SPK_SET_ERR(c, "CUDA failure inside the Krylov loop: %s", cudaGetErrorString(cudaGetLastError())); rc = SPK_ERR_CUDA; }
+  *its = it; *rnorm = res; *converged = conv;
+  return rc;
+}

@@ -1,0 +1,333 @@
+// solve.cu -- the SPIKE preconditioner apply  x = B^{-1} b   (replaces PCApply(inner) = PETSc
+// MatSolve_SeqAIJ, /root/reference/src/matbanded.c:190).
+//
+//   (1) k_sweep<MAIN>   g_i = A_i^{-1} b_i : forward (L) and backward (U) sweeps of every partition,
+//                       factors streamed exactly once through a cp.async.bulk ring.
+//   (2) k_reduced_solve per interface: (I - W V) x_t = g_t - W g_b ; x_b = g_b - V x_t ; coupling
+//                       right-hand sides r_top = C x_b, r_bot = B x_t for the corrections.
+//   (3) k_sweep<CORR>   x_i = g_i - A_i^{-1}[r_top;0] - A_i^{-1}[0;r_bot], restricted to the
+//                       truncation window (tipT tile rows) where the spikes have not yet decayed;
+//                       tipT = whole partition reproduces the classical second full sweep.
+//
+// Sweep kernel anatomy (one CTA per partition / correction job, 4 warps):
+//   warp 0 ("near")  carries the sequential recurrence  y_I = Linv_I (c_I - L(I,I-1) y_{I-1})
+//                    with 8x8 tiles spread over the lanes and warp-shuffle reductions;
+//   warps 1-3 ("far") accumulate the part of the dot products that only needs y_{<=I-2} for the
+//                    NEXT tile row (warp-shuffle reductions over the 4 lanes of a row);
+//   one elected lane keeps SW_NST tile rows in flight with bulk async copies (mbarrier tx-count).
+#include "common.cuh"
+
+#define SW_NST 8
+#define SW_THREADS 128
+
+enum { SWEEP_MAIN = 0, SWEEP_CORR = 1 };
+
+struct SweepArgs {
+  const double* band; const double* dinv; int tpr;
+  const int64_t* pstart; int P;
+  int mode;
+  const double* in;    // MAIN: right-hand side b
+  double* x;           // MAIN: output (y then x, in place); CORR: vector being corrected
+  const double* rtop;  // CORR: P * kp   r_top of partition p   (C_p x_b(p-1))
+  const double* rbot;  // CORR: P * kp   r_bot of partition p   (B_p x_t(p+1))
+  int tipT;            // CORR window (tile rows)
+  int has_left, has_right;  // remote neighbours present (multi-GPU): partition 0 top / P-1 bottom active
+  int64_t n;           // rows of the user vectors (padded rows are neither read nor written)
+};
+
+template <int KT>
+struct SweepSmem {
+  double stage[SW_NST][KT + 1][64];  // [0..KT-1] = off-diagonal tiles of the tile row, [KT] = dinv tile
+  double ybuf[KT + 1][8];            // ring of the last KT+1 solved tile-row blocks
+  double farpart[2][3][8];
+  unsigned long long full[SW_NST];
+};
+
+// One directional sweep over tile rows.  DIR=+1: forward with L (rows r0..r1-1 ascending),
+// DIR=-1: backward with U (rows r1-1..r0 descending).  Tile columns outside [vlo,vhi) are ignored.
+// rhs(row_tile, g) supplies the right-hand side; sink(row_tile, g, value) consumes the result.
+template <int KT, int DIR, class Rhs, class Sink>
+__device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, int64_t& itbase, int64_t r0, int64_t r1,
+                                          int64_t vlo, int64_t vhi, Rhs rhs, Sink sink) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int64_t nrows = r1 - r0;
+  if (nrows <= 0) return;
+  auto row_of = [&](int64_t it) -> int64_t { return DIR > 0 ? r0 + it : r1 - 1 - it; };
+  // the ring's mbarriers keep counting across sweeps: global iteration index = itbase + it
+  const int64_t ib = itbase;
+  itbase += nrows;
+  __syncthreads();
+  for (int e = threadIdx.x; e < (KT + 1) * 8; e += blockDim.x) (&S.ybuf[0][0])[e] = 0.0;
+  for (int e = threadIdx.x; e < 2 * 3 * 8; e += blockDim.x) (&S.farpart[0][0][0])[e] = 0.0;
+  __syncthreads();
+  auto issue = [&](int64_t it) {  // executed by one thread
+    const int st = (int)((ib + it) % SW_NST);
+    const int64_t I = row_of(it);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(&S.full[st]);
+    mbar_expect_tx(bar, (uint32_t)((KT + 1) * 512));
+    const double* src = a.band + (I * a.tpr + (DIR > 0 ? 0 : KT + 1)) * SPK_TILE_ELEMS;  // d=-KT..-1  or  d=1..KT
+    bulk_g2s(&S.stage[st][0][0], src, KT * 512, bar);
+    bulk_g2s(&S.stage[st][KT][0], a.dinv + I * SPK_TILE_ELEMS, 512, bar);
+  };
+  if (threadIdx.x == 32) {
+    for (int64_t it = 0; it < SW_NST && it < nrows; ++it) issue(it);
+  }
+  // slot of tile row I in the y ring
+  auto yslot = [&](int64_t I) -> int { return (int)(((I % (KT + 1)) + (KT + 1)) % (KT + 1)); };
+
+  for (int64_t it = 0; it < nrows; ++it) {
+    const int64_t I = row_of(it);
+    if (warp == 0) {
+      // -------- near warp: finish tile row I
+      // (the far warps already waited for this stage one iteration ago; only row 0 is unseen)
+      const int st = (int)((ib + it) % SW_NST);
+      if (it == 0) mbar_wait(reinterpret_cast<uint64_t*>(&S.full[st]), (uint32_t)(((ib + it) / SW_NST) & 1));
+      const int par = (int)(it & 1);
+      double cg = rhs(I, g) - (S.farpart[par][0][g] + S.farpart[par][1][g] + S.farpart[par][2][g]);
+      // adjacent tile: forward L(I,I-1) is stage tile KT-1 (d=-1); backward U(I,I+1) is stage tile 0 (d=+1)
+      const int64_t Jn = I - DIR;
+      double part = 0.0;
+      if (Jn >= vlo && Jn < vhi && it > 0) {
+        const double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 0][2 * lane]);
+        const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[yslot(Jn)][2 * tq]);
+        part = fma(t.x, yp.x, t.y * yp.y);
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      const double tg = cg - part;  // replicated in the 4 lanes of row g
+      // y_g = sum_c Dinv[g][c] t_c  (forward: unit lower, c<g plus t_g; backward: upper incl. diagonal, c>=g)
+      const double2 dv = *reinterpret_cast<const double2*>(&S.stage[st][KT][2 * lane]);
+      const int c0 = 2 * tq, c1 = 2 * tq + 1;
+      const double t0 = __shfl_sync(0xffffffffu, tg, 4 * c0);
+      const double t1 = __shfl_sync(0xffffffffu, tg, 4 * c1);
+      double yv;
+      if (DIR > 0) {
+        yv = ((c0 < g) ? dv.x * t0 : 0.0) + ((c1 < g) ? dv.y * t1 : 0.0);
+      } else {
+        yv = ((c0 >= g) ? dv.x * t0 : 0.0) + ((c1 >= g) ? dv.y * t1 : 0.0);
+      }
+      yv += __shfl_xor_sync(0xffffffffu, yv, 1);
+      yv += __shfl_xor_sync(0xffffffffu, yv, 2);
+      if (DIR > 0) yv += tg;
+      if (tq == 0) { S.ybuf[yslot(I)][g] = yv; sink(I, g, yv); }
+    } else {
+      // -------- far warps: partial sums for the NEXT tile row from blocks at distance >= 2
+      const int64_t itn = it + 1;
+      if (itn < nrows) {
+        const int64_t In = row_of(itn);
+        const int stn = (int)((ib + itn) % SW_NST);
+        mbar_wait(reinterpret_cast<uint64_t*>(&S.full[stn]), (uint32_t)(((ib + itn) / SW_NST) & 1));
+        const int fw = warp - 1;
+        double acc = 0.0;
+        // forward: stage tile t <-> J = In-KT+t, t = 0..KT-2 ; backward: stage tile t <-> J = In+1+t, t = 1..KT-1
+#pragma unroll
+        for (int t = fw; t < KT - 1; t += 3) {
+          const int tt = DIR > 0 ? t : t + 1;
+          const int64_t J = DIR > 0 ? In - KT + tt : In + 1 + tt;
+          // only blocks already solved in THIS sweep contribute (others are outside the window / zero)
+          const bool ok = (J >= vlo && J < vhi) && (DIR > 0 ? (J >= r0) : (J < r1));
+          if (ok) {
+            const double2 tv = *reinterpret_cast<const double2*>(&S.stage[stn][tt][2 * lane]);
+            const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[yslot(J)][2 * tq]);
+            acc = fma(tv.x, yp.x, acc);
+            acc = fma(tv.y, yp.y, acc);
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (tq == 0) S.farpart[(int)(itn & 1)][fw][g] = acc;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 32 && it + SW_NST < nrows) issue(it + SW_NST);
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(SW_THREADS) k_sweep(const SweepArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SweepSmem<KT>& S = *reinterpret_cast<SweepSmem<KT>*>(smem_raw);
+  const int kp = KT * 8;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SW_NST; ++i) mbar_init(reinterpret_cast<uint64_t*>(&S.full[i]), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  int64_t itbase = 0;
+  const int64_t n = a.n;
+  if (a.mode == SWEEP_MAIN) {
+    const int p = blockIdx.x;
+    const int64_t t0 = a.pstart[p], t1 = a.pstart[p + 1];
+    const double* in = a.in; double* x = a.x;
+    sweep_dir<KT, +1>(S, a, itbase, t0, t1, t0, t1,
+                      [&](int64_t I, int g) { return (I * 8 + g < n) ? in[I * 8 + g] : 0.0; },
+                      [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] = v; });
+    sweep_dir<KT, -1>(S, a, itbase, t0, t1, t0, t1,
+                      [&](int64_t I, int g) { return (I * 8 + g < n) ? x[I * 8 + g] : 0.0; },
+                      [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] = v; });
+    return;
+  }
+  // ---- corrections: blockIdx = 2*p + side (0 top, 1 bottom); when the window covers the whole
+  //      partition both right-hand sides are folded into the side-0 job.
+  const int p = blockIdx.x >> 1, side = blockIdx.x & 1;
+  const int64_t t0 = a.pstart[p], t1 = a.pstart[p + 1];
+  const int64_t plen = t1 - t0;
+  const bool top_on = (p > 0) || a.has_left;
+  const bool bot_on = (p < a.P - 1) || a.has_right;
+  const bool full = 2 * (int64_t)a.tipT > plen;
+  const int64_t W = full ? plen : a.tipT;
+  double* x = a.x;
+  const double* rt = a.rtop + (size_t)p * kp;
+  const double* rb = a.rbot + (size_t)p * kp;
+  if (full) {
+    if (side == 1 || (!top_on && !bot_on)) return;
+    // scratch for y: reuse x? no -- keep the intermediate in the ring only is impossible for the
+    // backward pass, so the forward result is parked in x's shadow: we use the correction identity
+    // x <- x - A^{-1} r  with r sparse, computing w in place in a private global scratch is avoided by
+    // running the forward sweep into shared ybuf only for the rows that matter: rows below the top
+    // KT tile rows get y from the recurrence, which needs every row -> stream them through `work`.
+    double* w = const_cast<double*>(a.in);  // CORR full mode: a.in is a scratch vector (n_padded)
+    sweep_dir<KT, +1>(S, a, itbase, t0, t1, t0, t1,
+                      [&](int64_t I, int g) {
+                        double v = 0.0;
+                        if (top_on && I < t0 + KT) v += rt[(I - t0) * 8 + g];
+                        if (bot_on && I >= t1 - KT) v += rb[(I - (t1 - KT)) * 8 + g];
+                        return v;
+                      },
+                      [&](int64_t I, int g, double v) { w[I * 8 + g] = v; });
+    sweep_dir<KT, -1>(S, a, itbase, t0, t1, t0, t1,
+                      [&](int64_t I, int g) { return w[I * 8 + g]; },
+                      [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] -= v; });
+    return;
+  }
+  double* w = const_cast<double*>(a.in);
+  if (side == 0) {
+    if (!top_on) return;
+    const int64_t lo = t0, hi = t0 + W;
+    sweep_dir<KT, +1>(S, a, itbase, lo, hi, lo, hi,
+                      [&](int64_t I, int g) { return (I < t0 + KT) ? rt[(I - t0) * 8 + g] : 0.0; },
+                      [&](int64_t I, int g, double v) { w[I * 8 + g] = v; });
+    sweep_dir<KT, -1>(S, a, itbase, lo, hi, lo, hi,
+                      [&](int64_t I, int g) { return w[I * 8 + g]; },
+                      [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] -= v; });
+  } else {
+    if (!bot_on) return;
+    const int64_t lo = t1 - W, hi = t1;
+    // forward: the right-hand side is zero above the last KT tile rows, so is y
+    sweep_dir<KT, +1>(S, a, itbase, t1 - KT, hi, t1 - KT, hi,
+                      [&](int64_t I, int g) { return rb[(I - (t1 - KT)) * 8 + g]; },
+                      [&](int64_t I, int g, double v) { w[I * 8 + g] = v; });
+    sweep_dir<KT, -1>(S, a, itbase, lo, hi, lo, hi,
+                      [&](int64_t I, int g) { return (I >= t1 - KT) ? w[I * 8 + g] : 0.0; },
+                      [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] -= v; });
+  }
+}
+
+template <int KT>
+static int launch_sweep_kt(spk_ctx* c, const SweepArgs& a, int grid) {
+  const size_t smem = sizeof(SweepSmem<KT>);
+  SPK_CUDA(c, cudaFuncSetAttribute(k_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_sweep<KT><<<grid, SW_THREADS, smem, c->stream>>>(a);
+  SPK_KERNEL_CHECK(c);
+  return SPK_OK;
+}
+static int launch_sweep_any(spk_ctx* c, const SweepArgs& a, int grid) {
+  switch (c->L.kt) {
+#define CASE(K_) case K_: return launch_sweep_kt<K_>(c, a, grid);
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
+#undef CASE
+    default: SPK_SET_ERR(c, "unsupported kt=%d", c->L.kt); return SPK_ERR_UNSUPPORTED;
+  }
+}
+
+int spk_launch_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld) {
+  for (int r = 0; r < nrhs; ++r) {
+    SweepArgs a{};
+    a.band = c->band; a.dinv = c->dinv; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.P = c->P;
+    a.mode = SWEEP_MAIN; a.in = b + (size_t)r * ld; a.x = x + (size_t)r * ld; a.tipT = c->tipT; a.n = c->L.n;
+    const int rc = launch_sweep_any(c, a, c->P);
+    if (rc) return rc;
+  }
+  return SPK_OK;
+}
+
+int spk_launch_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld) {
+  for (int r = 0; r < nrhs; ++r) {
+    SweepArgs a{};
+    a.band = c->band; a.dinv = c->dinv; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.P = c->P;
+    a.mode = SWEEP_CORR; a.in = c->work; a.x = x + (size_t)r * ld; a.tipT = c->tipT; a.n = c->L.n;
+    a.rtop = c->gtip + (size_t)r * 2 * c->P * c->kp;
+    a.rbot = a.rtop + (size_t)c->P * c->kp;
+    a.has_left = (c->opts.rank > 0); a.has_right = (c->opts.rank + 1 < c->opts.nranks);
+    const int rc = launch_sweep_any(c, a, 2 * c->P);
+    if (rc) return rc;
+  }
+  return SPK_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// reduced system solve + coupling right-hand sides, one CTA (4 warps) per interface
+// --------------------------------------------------------------------------------------------
+struct RedSolveArgs {
+  const double* band; BandLayout L; const int64_t* pstart;
+  const double* Vb; const double* Wt; const double* Rinv;
+  const double* x;          // g (after the main sweep)
+  double* rtop; double* rbot;  // P * kp each
+  int first_iface;
+};
+// y[r] = sum_c M[r*kp+c] v[c] for r = warp, warp+4, ... ; lanes stride the columns; shuffle reduction
+__device__ __forceinline__ double row_dot(const double* __restrict__ Mrow, const double* v, int kp, int lane) {
+  double s = 0.0;
+  for (int c = lane; c < kp; c += 32) s = fma(Mrow[c], v[c], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+__global__ void __launch_bounds__(128) k_reduced_solve(const RedSolveArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int kp = a.L.kt * 8, KT = a.L.kt;
+  double* gb = sm; double* gt = gb + kp; double* tv = gt + kp; double* xt = tv + kp; double* xb = xt + kp;
+  const int i = blockIdx.x + a.first_iface;
+  const int64_t tb = a.pstart[i + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e = threadIdx.x; e < kp; e += blockDim.x) {
+    gb[e] = a.x[(tb - KT) * 8 + e];
+    gt[e] = (tb * 8 + e < a.L.n) ? a.x[tb * 8 + e] : 0.0;
+  }
+  __syncthreads();
+  const double* W = a.Wt + (size_t)(i + 1) * kp * kp;
+  const double* V = a.Vb + (size_t)i * kp * kp;
+  const double* R = a.Rinv + (size_t)i * kp * kp;
+  for (int r = warp; r < kp; r += 4) { const double s = row_dot(W + (size_t)r * kp, gb, kp, lane); if (lane == 0) tv[r] = gt[r] - s; }
+  __syncthreads();
+  for (int r = warp; r < kp; r += 4) { const double s = row_dot(R + (size_t)r * kp, tv, kp, lane); if (lane == 0) xt[r] = s; }
+  __syncthreads();
+  for (int r = warp; r < kp; r += 4) { const double s = row_dot(V + (size_t)r * kp, xt, kp, lane); if (lane == 0) xb[r] = gb[r] - s; }
+  __syncthreads();
+  // r_top of partition i+1: C_{i+1} x_b ;  r_bot of partition i: B_i x_t
+  for (int r = warp; r < kp; r += 4) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = lane; c < kp; c += 32) {
+      if ((c >> 3) >= (r >> 3)) s1 = fma(a.band[a.L.elem_off(tb * 8 + r, (tb - KT) * 8 + c)], xb[c], s1);
+      if ((c >> 3) <= (r >> 3)) s2 = fma(a.band[a.L.elem_off((tb - KT) * 8 + r, tb * 8 + c)], xt[c], s2);
+    }
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (lane == 0) { a.rtop[(size_t)(i + 1) * kp + r] = s1; a.rbot[(size_t)i * kp + r] = s2; }
+  }
+}
+
+int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int iface_lo, int iface_hi) {
+  const int n = iface_hi - iface_lo;
+  if (n <= 0) return SPK_OK;
+  for (int r = 0; r < nrhs; ++r) {
+    RedSolveArgs a;
+    a.band = c->band; a.L = c->L; a.pstart = c->d_pstart; a.Vb = c->Vb; a.Wt = c->Wt; a.Rinv = c->Red;
+    a.x = x + (size_t)r * ld;
+    a.rtop = c->gtip + (size_t)r * 2 * c->P * c->kp;
+    a.rbot = a.rtop + (size_t)c->P * c->kp;
+    a.first_iface = iface_lo;
+    k_reduced_solve<<<n, 128, sizeof(double) * 5 * c->kp, c->stream>>>(a);
+    SPK_KERNEL_CHECK(c);
+  }
+  return SPK_OK;
+}
