@@ -1,0 +1,323 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs; size-independent properties at BASELINE.json's full sizes.
+
+Bars (north_star): band structure / permutation application bit-exact; solution vectors within
+1e-10 relative of the reference CPU path (exact band LU solve); Krylov iteration counts within +-1.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+RTOL = 1e-10  # north_star: solution vectors within 1e-10 relative error (fp64)
+
+
+def relerr(x, ref):
+    return np.linalg.norm(x - ref) / np.linalg.norm(ref)
+
+
+# ------------------------------------------------------------------ layout / generator (bit exact)
+@pytest.mark.parametrize("n,k", [(64, 5), (1000, 10), (4099, 37), (2048, 100), (777, 128)])
+def test_synthetic_band_bit_exact(spk, oracle, n, k):
+    S = spk.Spike()
+    S.set_band_synthetic(n, k, seed=20140601, delta=1.2)
+    np.testing.assert_array_equal(S.get_band_rows(), oracle.gen_band(n, k, 20140601, 1.2))
+    S.close()
+
+
+def test_generator_golden_on_gpu(spk):
+    g = GOLD["synthetic_n64_k5"]
+    S = spk.Spike()
+    S.set_band_synthetic(64, 5, seed=g["seed"], delta=g["delta"])
+    a = S.get_band_rows()
+    np.testing.assert_array_equal(a[0], g["band_row0"])
+    np.testing.assert_array_equal(a[17], g["band_row17"])
+    np.testing.assert_array_equal(a[63], g["band_row63"])
+    S.close()
+
+
+@pytest.mark.parametrize("layout", ["rows", "diags"])
+def test_dense_pack_round_trip_bit_exact(spk, oracle, layout):
+    n, k = 1237, 21
+    a = oracle.gen_band(n, k, seed=3)
+    S = spk.Spike()
+    if layout == "rows":
+        S.set_band_dense(a, k, spk.LAYOUT_ROWS)
+    else:
+        S.set_band_dense(np.ascontiguousarray(a.T), k, spk.LAYOUT_DIAGS)
+    np.testing.assert_array_equal(S.get_band_rows(), a)
+    S.close()
+
+
+# ------------------------------------------------------------------ MatMult
+@pytest.mark.parametrize("n,k", [(100, 3), (5000, 10), (20000, 50), (9999, 100)])
+def test_matmult_vs_oracle(spk, oracle, n, k):
+    a = oracle.gen_band(n, k)
+    x = oracle.gen_vec(n, 5) - 0.5
+    S = spk.Spike()
+    S.set_band_dense(a, k)
+    y = S.mult(x)
+    ref = oracle.band_mult(a, x)
+    assert relerr(y, ref) < 1e-14
+    S.close()
+
+
+# ------------------------------------------------------------------ factor: LU entries vs oracle
+@pytest.mark.parametrize("n,k", [(512, 10), (4096, 20), (3000, 50), (4096, 100), (2500, 128), (1001, 64)])
+def test_lu_factors_match_oracle_single_partition(spk, oracle, n, k):
+    a = oracle.gen_band(n, k, seed=n + k)
+    lu, nb = oracle.band_lu(a)
+    S = spk.Spike(partitions=1, tip_tiles=-1)
+    S.set_band_dense(a, k)
+    S.factor()
+    f = S.get_band_rows()
+    scale = np.abs(lu).max()
+    assert np.abs(f - lu).max() <= 1e-12 * scale
+    assert S.view()["boosted_pivots"] == 0
+    S.close()
+
+
+# ------------------------------------------------------------------ SPIKE solve vs exact band solve
+CASES = [
+    # n, k, partitions, tip_tiles (-1 = full windows), delta
+    (4000, 10, 4, -1, 1.2),
+    (100_000, 10, 0, 0, 1.2),      # BASELINE config[0] shape: N=100k K=10
+    (20_000, 50, 8, -1, 1.2),
+    (20_001, 37, 5, -1, 1.2),      # ragged: n not a multiple of 8, k not a multiple of 8
+    (60_000, 100, 12, -1, 1.2),
+    (60_000, 100, 12, 0, 1.2),     # auto truncation window
+    (50_000, 128, 6, 0, 1.2),      # widest band of the register-window kernel
+    (30_000, 50, 16, 0, 1.0),      # weak dominance (delta = 1.0)
+]
+
+
+@pytest.mark.parametrize("n,k,P,tip,delta", CASES)
+def test_spike_solve_matches_reference_cpu_path(spk, oracle, n, k, P, tip, delta):
+    a = oracle.gen_band(n, k, delta=delta)
+    lu, _ = oracle.band_lu(a)
+    S = spk.Spike(partitions=P, tip_tiles=tip)
+    S.set_band_dense(a, k)
+    S.factor()
+    for u in (np.ones(n), oracle.gen_vec(n, 20140601)):      # u = 1 and -random_exact_sol (src/testbed2.c:112-121)
+        b = oracle.band_mult(a, u)
+        x = S.solve(b)
+        xref = oracle.band_solve(lu, b)
+        assert relerr(x, xref) < RTOL, (relerr(x, xref), S.view())
+        assert relerr(x, u) < 1e-9
+    S.close()
+
+
+def test_multiple_rhs(spk, oracle):
+    n, k = 12_000, 30
+    a = oracle.gen_band(n, k)
+    lu, _ = oracle.band_lu(a)
+    U = np.stack([oracle.gen_vec(n, s) for s in range(4)])
+    Bm = np.stack([oracle.band_mult(a, u) for u in U])
+    S = spk.Spike(partitions=6)
+    S.set_band_dense(a, k)
+    S.factor()
+    X = S.solve(Bm, nrhs=4)
+    for r in range(4):
+        assert relerr(X[r], oracle.band_solve(lu, Bm[r])) < RTOL
+    S.close()
+
+
+def test_gpu_tips_match_oracle_tips(spk, oracle):
+    """Same partitioning on CPU and GPU -> identical truncated-SPIKE answer (not only the exact one)."""
+    n, k, P = 24_000, 40, 6
+    a = oracle.gen_band(n, k, delta=1.0)
+    b = oracle.band_mult(a, np.ones(n))
+    So = oracle.Spike(n, k, P, align=8, tip_rows=0)
+    So.factor(a)
+    xo = So.solve(b)
+    S = spk.Spike(partitions=P, tip_tiles=-1)
+    S.set_band_dense(a, k)
+    S.factor()
+    assert relerr(S.solve(b), xo) < 1e-12
+    S.close()
+
+
+def test_boosting_counts_zero_pivots(spk, oracle):
+    n, k = 4096, 16
+    a = oracle.gen_band(n, k)
+    a[100, :] = 0.0
+    a[:, :] = a  # row 100 entirely zero -> pivot 100 is exactly zero after elimination
+    for d in range(1, k + 1):
+        a[100 - d, k + d] = 0.0  # and nothing in column 100 above it
+    S = spk.Spike(partitions=1, boost_rel=1e-10)
+    S.set_band_dense(a, k)
+    S.factor()
+    info = S.view()
+    assert info["boosted_pivots"] >= 1
+    lu, nb = oracle.band_lu(a, boost=1e-10 * info["anorm_max"])
+    assert nb == info["boosted_pivots"]
+    S.close()
+
+
+def test_error_paths(spk, oracle):
+    S = spk.Spike()
+    with pytest.raises(spk.SpikeError):
+        S.factor()                                   # no band yet
+    a = oracle.gen_band(400, 4)
+    S.set_band_dense(a, 4)
+    with pytest.raises(spk.SpikeError):
+        S.solve(np.ones(400))                        # solve before factor
+    S.factor()
+    with pytest.raises(spk.SpikeError):
+        S.factor()                                   # in-place factorisation cannot be repeated
+    with pytest.raises(spk.SpikeError):
+        S.mult(np.ones(400))                         # band overwritten, keep_original not requested
+    S2 = spk.Spike()
+    with pytest.raises(spk.SpikeError):
+        S2.set_band_synthetic(100_000, 1000)         # wide band: not covered by the window kernel
+    S.close(); S2.close()
+
+
+# ------------------------------------------------------------------ CSR (+permutation) -> band, bit exact
+def _sparse_case(n, k, seed, extra=2):
+    rng = np.random.default_rng(seed)
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        for d in range(-k, k + 1):
+            j = i + d
+            if 0 <= j < n and (d == 0 or rng.uniform() < 0.6):
+                rows.append(i); cols.append(j); vals.append(rng.uniform(-1, 1) if d else 2.5 * k)
+    for _ in range(extra * n):
+        i, j = rng.integers(0, n, 2)
+        rows.append(i); cols.append(j); vals.append(0.01 * rng.standard_normal())
+    A = sp.csr_matrix(sp.coo_matrix((vals, (rows, cols)), shape=(n, n)))
+    A.sum_duplicates(); A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("kmax,frac", [(50, 0.95), (12, 1.0), (5, 0.9), (12, 0.5)])
+def test_band_selection_and_extraction_bit_exact(spk, oracle, kmax, frac):
+    n = 3000
+    A = _sparse_case(n, 12, seed=4)
+    k_ref, f_ref = oracle.band_select(A.indptr, A.indices, A.data, kmax, frac)
+    S = spk.Spike()
+    k, f = S.set_band_csr(A.indptr, A.indices, A.data, kmax, frac)
+    assert (k, f) == (k_ref, f_ref)                   # bit-exact k and norm fraction (src/matbanded.c:104-105)
+    if k > 0:
+        np.testing.assert_array_equal(S.get_band_rows(), oracle.csr_to_band(A.indptr, A.indices, A.data, k))
+    S.close()
+
+
+def test_permuted_band_bit_exact(spk, oracle):
+    """MatPermute (src/kspreorder.c:20) fused with the band extraction, orderings from the oracle."""
+    n = 2500
+    A = _sparse_case(n, 9, seed=8)
+    rng = np.random.default_rng(3)
+    q = rng.permutation(n).astype(np.int32)
+    Aq = sp.csr_matrix(A[q, :][:, q]); Aq.sort_indices()          # hide the band behind a symmetric permutation
+    inv = np.argsort(q).astype(np.int32)                           # the ordering that recovers it
+    ib, jb, b = oracle.mat_permute_csr(Aq.indptr, Aq.indices, Aq.data, inv, inv)
+    k_ref, f_ref = oracle.band_select(ib, jb, b, 20, 0.99)
+    S = spk.Spike()
+    k, f = S.set_band_csr(Aq.indptr, Aq.indices, Aq.data, 20, 0.99, rowperm=inv, colperm=inv)
+    assert (k, f) == (k_ref, f_ref)
+    np.testing.assert_array_equal(S.get_band_rows(), oracle.csr_to_band(ib, jb, b, k))
+    S.close()
+
+
+def test_vec_permute_bit_exact(spk, oracle):
+    rng = np.random.default_rng(0)
+    n = 100_003
+    idx = rng.permutation(n).astype(np.int32)
+    x = rng.standard_normal(n)
+    S = spk.Spike()
+    y = S.permute(idx, x, inverse=False)
+    np.testing.assert_array_equal(y, oracle.vec_permute(x, idx, False))
+    np.testing.assert_array_equal(S.permute(idx, y, inverse=True), x)
+    S.close()
+
+
+def test_wbm_3x3_permutation_applied_on_gpu(spk, oracle):
+    """Reference KAT (src/wbm.c:483-497): MC64's column IS applied by the GPU gather gives the
+    matrix the reference's MatPermute would give."""
+    g = GOLD["wbm3x3"]
+    n = 3
+    ib, jb, b = oracle.mat_permute_csr(g["ia"], g["ja"], g["a"], g["row_is"], g["col_is"])
+    S = spk.Spike()
+    S.set_operator_csr(g["ia"], g["ja"], g["a"], rowperm=g["row_is"], colperm=g["col_is"])
+    P = sp.csr_matrix((b, jb, ib), shape=(n, n)).toarray()
+    np.testing.assert_array_equal(P, sp.csr_matrix((g["a"], g["ja"], g["ia"]), shape=(n, n)).toarray()[:, g["col_is"]])
+    S.close()
+
+
+# ------------------------------------------------------------------ Krylov iteration parity (+-1)
+@pytest.mark.parametrize("method", ["gmres", "bcgs"])
+def test_krylov_iteration_parity(spk, oracle, method):
+    n, k = 6000, 10
+    A = _sparse_case(n, k, seed=21, extra=3)
+    kk, f = oracle.band_select(A.indptr, A.indices, A.data, k, 1.0)
+    band = oracle.csr_to_band(A.indptr, A.indices, A.data, kk)
+    lu, _ = oracle.band_lu(band)
+    u = np.ones(n)
+    b = A @ u
+    m_o = oracle.GMRES if method == "gmres" else oracle.BICGSTAB
+    xo, its_o, _, rc = oracle.krylov_csr_band(A.indptr, A.indices, A.data, lu, b, m_o, rtol=1e-8)
+    assert rc == 0
+    S = spk.Spike(partitions=4, tip_tiles=-1)
+    k2, f2 = S.set_band_csr(A.indptr, A.indices, A.data, k, 1.0)
+    assert (k2, f2) == (kk, f)
+    S.set_operator_csr(A.indptr, A.indices, A.data)
+    S.factor()
+    x, its, rn, conv = S.krylov(b, spk.GMRES if method == "gmres" else spk.BCGS, rtol=1e-8)
+    assert conv and abs(its - its_o) <= 1, (its, its_o)
+    assert relerr(x, u) < 1e-6 and relerr(x, xo) < 1e-6
+    S.close()
+
+
+def test_reordered_solve_end_to_end(spk, oracle):
+    """testbed2 flow (src/testbed2.c:110-132) through KSPREORDER semantics (src/kspreorder.c:17-24,
+    122-127): b = A u, permute operators and vectors, SPIKE-preconditioned BiCGStab, un-permute."""
+    n, k = 5000, 8
+    A0 = _sparse_case(n, k, seed=33, extra=1)
+    rng = np.random.default_rng(7)
+    q = rng.permutation(n).astype(np.int32)
+    A = sp.csr_matrix(A0[q, :][:, q]); A.sort_indices()
+    rorder = np.argsort(q).astype(np.int32); corder = rorder.copy()
+    u = np.ones(n); b = A @ u
+    S = spk.Spike(partitions=4)
+    kk, f = S.set_band_csr(A.indptr, A.indices, A.data, 50, 0.95, rowperm=rorder, colperm=corder)
+    assert 0 < kk <= k
+    S.set_operator_csr(A.indptr, A.indices, A.data, rowperm=rorder, colperm=corder)
+    S.factor()
+    bp = S.permute(rorder, b, inverse=False)                     # VecPermute(b, rorder, FALSE)
+    xp, its, rn, conv = S.krylov(bp, spk.BCGS, rtol=1e-10)
+    x = S.permute(corder, xp, inverse=True)                      # VecPermute(x, corder, TRUE)
+    assert conv and np.linalg.norm(x - u) / np.sqrt(n) < 1e-7
+    S.close()
+
+
+# ------------------------------------------------------------------ full-size properties (no oracle at this size)
+@pytest.mark.parametrize("n,k", [(1_000_000, 50), (10_000_000, 100)])
+def test_full_size_manufactured_solution(spk, n, k):
+    """BASELINE configs C2 / C3 on one GPU: b = A*1 built on the device, factor, solve, ||x-1||/||1||;
+    linearity: solve(2b) == 2 solve(b) bit-for-bit up to fp64 scaling exactness."""
+    import torch
+    S = spk.Spike(mem=spk.MEM_DEVICE)
+    S.keep_original(True)
+    S.set_band_synthetic(n, k)
+    u = torch.ones(n, dtype=torch.float64, device="cuda")
+    b = torch.empty_like(u); x = torch.empty_like(u); y = torch.empty_like(u)
+    S.mult(u.data_ptr(), b.data_ptr())
+    S.factor()
+    S.solve(b.data_ptr(), x.data_ptr())
+    torch.cuda.synchronize()
+    err = ((x - u).norm() / u.norm()).item()
+    assert err < RTOL, err
+    S.mult(x.data_ptr(), y.data_ptr())                            # residual through the kept original band
+    torch.cuda.synchronize()
+    assert ((y - b).norm() / b.norm()).item() < 1e-12
+    b2 = 2.0 * b
+    S.solve(b2.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(y, 2.0 * x)                                # scaling by 2 is exact in fp64
+    assert S.view()["boosted_pivots"] == 0
+    S.close()
