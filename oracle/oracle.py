@@ -302,3 +302,59 @@ def krylov_csr_band(ia, ja, a, lu, b, method=BICGSTAB, restart=30, rtol=1e-5, ma
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+# ------------------------------------------------------------------ block LU (factor-entry parity)
+def _gj_inverse_nopivot(D: np.ndarray, boost: float):
+    """In-place Gauss-Jordan inverse without pivoting and with the same boosting rule as band_lu."""
+    n = D.shape[0]
+    A = D.copy()
+    nb = 0
+    for k in range(n):
+        piv = A[k, k]
+        if abs(piv) < boost:
+            piv = -boost if piv < 0.0 else boost
+            nb += 1
+        rc = 1.0 / piv
+        f = A[:, k] * rc
+        f[k] = 0.0
+        rowk = A[k, :].copy()
+        A -= np.outer(f, rowk)
+        A[k, :] = rowk * rc
+        A[:, k] = -f
+        A[k, k] = rc
+    return A, nb
+
+
+def block_lu(a: np.ndarray, tile: int = 8, boost: float = 0.0):
+    """Block LU of the band (rows layout) grouped by `tile` pivots, the factorisation the GPU kernel
+    stores: Lb(I,J) = A~(I,J) D_J^-1 below the diagonal, A~(I,J) above it, D_I^-1 in the diagonal tile.
+    Same Schur complements / pivots / boosting as the scalar no-pivot LU (band_lu).  Returns the
+    factors in a rows layout widened to the tile band (half-width kw = tile*ceil(k/tile) + tile-1)."""
+    n, bw = a.shape
+    k = (bw - 1) // 2
+    kt = max(2, -(-k // tile))
+    kw = tile * kt + tile - 1
+    wide = np.zeros((n, 2 * kw + 1))
+    wide[:, kw - k:kw + k + 1] = a
+    nboost = 0
+    nt = -(-n // tile)
+    for s in range(nt):
+        r0 = s * tile
+        r1 = min(n, r0 + tile)
+        e = min(n, r0 + tile * (kt + 1))           # rows/cols touched by this step
+        idx = np.arange(r0, e)
+        ii, jj = np.meshgrid(idx, idx, indexing="ij")
+        dd = jj - ii + kw
+        ok = (dd >= 0) & (dd <= 2 * kw)
+        Wd = np.zeros((e - r0, e - r0))
+        Wd[ok] = wide[ii[ok], dd[ok]]
+        m = r1 - r0
+        Dinv, nb = _gj_inverse_nopivot(Wd[:m, :m], boost)
+        nboost += nb
+        L = Wd[m:, :m] @ Dinv
+        Wd[m:, m:] -= L @ Wd[:m, m:]
+        Wd[m:, :m] = L
+        Wd[:m, :m] = Dinv
+        wide[ii[ok], dd[ok]] = Wd[ok]
+    return wide, nboost, kw

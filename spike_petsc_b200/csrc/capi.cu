@@ -122,7 +122,6 @@ static int plan(spk_ctx* c, int64_t n, int k) {
 
   const size_t kk = (size_t)c->kp * c->kp;
   SPK_CUDA(c, cudaMalloc(&c->band, sizeof(double) * (size_t)L.elems()));
-  SPK_CUDA(c, cudaMalloc(&c->dinv, sizeof(double) * (size_t)L.nt * 64));
   SPK_CUDA(c, cudaMalloc(&c->d_pstart, sizeof(int64_t) * (P + 1)));
   SPK_CUDA(c, cudaMemcpyAsync(c->d_pstart, c->h_pstart, sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, c->stream));
   SPK_CUDA(c, cudaMalloc(&c->Sb, sizeof(double) * kk * P));
@@ -486,3 +485,7 @@ extern "C" int spk_get_boundary(spk_ctx* c, int which, double* dev_buf) {
 extern "C" int spk_set_boundary(spk_ctx* c, int which, const double* dev_buf) {
   (void)which; (void)dev_buf; SPK_SET_ERR(c, "boundary exchange not wired in this build"); return SPK_ERR_UNSUPPORTED;
 }
+
+// debug hook used by tools/lu_trace.py (not part of the public header): attach a device buffer of
+// 64*16 int64 that CTA 0 of the LU kernel fills with clock64 stamps for steps 100..163.
+extern "C" int spk_debug_set_lu_trace(spk_ctx* c, void* dev_buf) { if (!c) return SPK_ERR_ARG; c->lu_trace = dev_buf; return SPK_OK; }

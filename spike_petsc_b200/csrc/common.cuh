@@ -80,6 +80,7 @@ struct spk_ctx {
   cudaEvent_t ev0, ev1;     // factor start/stop
   cudaEvent_t evs0, evs1;   // solve start/stop
   int timed_factor, timed_solve;
+  void* lu_trace;           // debug: device buffer for clock64 stamps of the LU kernel (tools only)
   char err[512];
 };
 

@@ -23,11 +23,12 @@
 enum { SWEEP_MAIN = 0, SWEEP_CORR = 1 };
 
 struct SweepArgs {
-  const double* band; const double* dinv; int tpr;
+  const double* band; int tpr;
   const int64_t* pstart; int P;
   int mode;
   const double* in;    // MAIN: right-hand side b
   double* x;           // MAIN: output (y then x, in place); CORR: vector being corrected
+  double* work;        // CORR: scratch vector (n_padded) holding the correction w
   const double* rtop;  // CORR: P * kp   r_top of partition p   (C_p x_b(p-1))
   const double* rbot;  // CORR: P * kp   r_bot of partition p   (B_p x_t(p+1))
   int tipT;            // CORR window (tile rows)
@@ -37,18 +38,21 @@ struct SweepArgs {
 
 template <int KT>
 struct SweepSmem {
-  double stage[SW_NST][KT + 1][64];  // [0..KT-1] = off-diagonal tiles of the tile row, [KT] = dinv tile
+  // forward : [0..KT-1] = Lb tiles d=-KT..-1,                      [KT+1] = right-hand-side block (8 doubles)
+  // backward: [0] = D^-1 (diagonal slot), [1..KT] = Ub tiles d=1..KT, [KT+1] = right-hand-side block
+  double stage[SW_NST][KT + 2][64];
   double ybuf[KT + 1][8];            // ring of the last KT+1 solved tile-row blocks
   double farpart[2][3][8];
   unsigned long long full[SW_NST];
 };
 
-// One directional sweep over tile rows.  DIR=+1: forward with L (rows r0..r1-1 ascending),
-// DIR=-1: backward with U (rows r1-1..r0 descending).  Tile columns outside [vlo,vhi) are ignored.
-// rhs(row_tile, g) supplies the right-hand side; sink(row_tile, g, value) consumes the result.
-template <int KT, int DIR, class Rhs, class Sink>
+// One directional sweep over tile rows.  DIR=+1: forward with Lb (rows r0..r1-1 ascending, unit block
+// diagonal), DIR=-1: backward with Ub and the explicit D^-1 (rows r1-1..r0 descending).
+// Tile columns outside [vlo,vhi) are ignored.  vin[row] is the right-hand side (streamed through the
+// bulk-copy ring together with the factor tiles), sink(I, g, value) consumes the result.
+template <int KT, int DIR, class Sink>
 __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, int64_t& itbase, int64_t r0, int64_t r1,
-                                          int64_t vlo, int64_t vhi, Rhs rhs, Sink sink) {
+                                          int64_t vlo, int64_t vhi, const double* vin, int64_t nvalid, Sink sink) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const int64_t nrows = r1 - r0;
@@ -57,18 +61,24 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
   // the ring's mbarriers keep counting across sweeps: global iteration index = itbase + it
   const int64_t ib = itbase;
   itbase += nrows;
+  const bool bulk_rhs = ((reinterpret_cast<uintptr_t>(vin) & 15) == 0);
+  // earlier generic-proxy writes of this CTA (previous sweep's results) must be visible to the async proxy
+  asm volatile("fence.proxy.async;" ::: "memory");
   __syncthreads();
   for (int e = threadIdx.x; e < (KT + 1) * 8; e += blockDim.x) (&S.ybuf[0][0])[e] = 0.0;
   for (int e = threadIdx.x; e < 2 * 3 * 8; e += blockDim.x) (&S.farpart[0][0][0])[e] = 0.0;
   __syncthreads();
+  constexpr int NTILE = DIR > 0 ? KT : KT + 1;
+  auto rhs_bulk_ok = [&](int64_t I) -> bool { return bulk_rhs && (I * 8 + 8 <= nvalid); };
   auto issue = [&](int64_t it) {  // executed by one thread
     const int st = (int)((ib + it) % SW_NST);
     const int64_t I = row_of(it);
     uint64_t* bar = reinterpret_cast<uint64_t*>(&S.full[st]);
-    mbar_expect_tx(bar, (uint32_t)((KT + 1) * 512));
-    const double* src = a.band + (I * a.tpr + (DIR > 0 ? 0 : KT + 1)) * SPK_TILE_ELEMS;  // d=-KT..-1  or  d=1..KT
-    bulk_g2s(&S.stage[st][0][0], src, KT * 512, bar);
-    bulk_g2s(&S.stage[st][KT][0], a.dinv + I * SPK_TILE_ELEMS, 512, bar);
+    const bool rb = rhs_bulk_ok(I);
+    mbar_expect_tx(bar, (uint32_t)(NTILE * 512 + (rb ? 64 : 0)));
+    const double* src = a.band + (I * a.tpr + (DIR > 0 ? 0 : KT)) * SPK_TILE_ELEMS;  // d=-KT..-1  or  d=0..KT
+    bulk_g2s(&S.stage[st][0][0], src, NTILE * 512, bar);
+    if (rb) bulk_g2s(&S.stage[st][KT + 1][0], vin + I * 8, 64, bar);
   };
   if (threadIdx.x == 32) {
     for (int64_t it = 0; it < SW_NST && it < nrows; ++it) issue(it);
@@ -84,32 +94,30 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
       const int st = (int)((ib + it) % SW_NST);
       if (it == 0) mbar_wait(reinterpret_cast<uint64_t*>(&S.full[st]), (uint32_t)(((ib + it) / SW_NST) & 1));
       const int par = (int)(it & 1);
-      double cg = rhs(I, g) - (S.farpart[par][0][g] + S.farpart[par][1][g] + S.farpart[par][2][g]);
-      // adjacent tile: forward L(I,I-1) is stage tile KT-1 (d=-1); backward U(I,I+1) is stage tile 0 (d=+1)
+      double rhs;
+      if (rhs_bulk_ok(I)) rhs = S.stage[st][KT + 1][g];
+      else rhs = (I * 8 + g < nvalid) ? vin[I * 8 + g] : 0.0;
+      const double cg = rhs - (S.farpart[par][0][g] + S.farpart[par][1][g] + S.farpart[par][2][g]);
+      // adjacent tile: forward Lb(I,I-1) is stage tile KT-1 (d=-1); backward Ub(I,I+1) is stage tile 1 (d=+1)
       const int64_t Jn = I - DIR;
       double part = 0.0;
       if (Jn >= vlo && Jn < vhi && it > 0) {
-        const double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 0][2 * lane]);
+        const double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 1][2 * lane]);
         const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[yslot(Jn)][2 * tq]);
         part = fma(t.x, yp.x, t.y * yp.y);
       }
       part += __shfl_xor_sync(0xffffffffu, part, 1);
       part += __shfl_xor_sync(0xffffffffu, part, 2);
-      const double tg = cg - part;  // replicated in the 4 lanes of row g
-      // y_g = sum_c Dinv[g][c] t_c  (forward: unit lower, c<g plus t_g; backward: upper incl. diagonal, c>=g)
-      const double2 dv = *reinterpret_cast<const double2*>(&S.stage[st][KT][2 * lane]);
-      const int c0 = 2 * tq, c1 = 2 * tq + 1;
-      const double t0 = __shfl_sync(0xffffffffu, tg, 4 * c0);
-      const double t1 = __shfl_sync(0xffffffffu, tg, 4 * c1);
-      double yv;
-      if (DIR > 0) {
-        yv = ((c0 < g) ? dv.x * t0 : 0.0) + ((c1 < g) ? dv.y * t1 : 0.0);
-      } else {
-        yv = ((c0 >= g) ? dv.x * t0 : 0.0) + ((c1 >= g) ? dv.y * t1 : 0.0);
+      double yv = cg - part;  // replicated in the 4 lanes of row g
+      if (DIR < 0) {
+        // x_g = sum_c Dinv[g][c] t_c
+        const double2 dv = *reinterpret_cast<const double2*>(&S.stage[st][0][2 * lane]);
+        const double t0 = __shfl_sync(0xffffffffu, yv, 8 * tq);
+        const double t1 = __shfl_sync(0xffffffffu, yv, 8 * tq + 4);
+        yv = fma(dv.x, t0, dv.y * t1);
+        yv += __shfl_xor_sync(0xffffffffu, yv, 1);
+        yv += __shfl_xor_sync(0xffffffffu, yv, 2);
       }
-      yv += __shfl_xor_sync(0xffffffffu, yv, 1);
-      yv += __shfl_xor_sync(0xffffffffu, yv, 2);
-      if (DIR > 0) yv += tg;
       if (tq == 0) { S.ybuf[yslot(I)][g] = yv; sink(I, g, yv); }
     } else {
       // -------- far warps: partial sums for the NEXT tile row from blocks at distance >= 2
@@ -120,11 +128,11 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
         mbar_wait(reinterpret_cast<uint64_t*>(&S.full[stn]), (uint32_t)(((ib + itn) / SW_NST) & 1));
         const int fw = warp - 1;
         double acc = 0.0;
-        // forward: stage tile t <-> J = In-KT+t, t = 0..KT-2 ; backward: stage tile t <-> J = In+1+t, t = 1..KT-1
+        // forward: stage tile t <-> J = In-KT+t, t = 0..KT-2 ; backward: stage tile t <-> J = In+t, t = 2..KT
 #pragma unroll
         for (int t = fw; t < KT - 1; t += 3) {
-          const int tt = DIR > 0 ? t : t + 1;
-          const int64_t J = DIR > 0 ? In - KT + tt : In + 1 + tt;
+          const int tt = DIR > 0 ? t : t + 2;
+          const int64_t J = DIR > 0 ? In - KT + tt : In + tt;
           // only blocks already solved in THIS sweep contribute (others are outside the window / zero)
           const bool ok = (J >= vlo && J < vhi) && (DIR > 0 ? (J >= r0) : (J < r1));
           if (ok) {
@@ -159,17 +167,15 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(const SweepArgs a) {
   if (a.mode == SWEEP_MAIN) {
     const int p = blockIdx.x;
     const int64_t t0 = a.pstart[p], t1 = a.pstart[p + 1];
-    const double* in = a.in; double* x = a.x;
-    sweep_dir<KT, +1>(S, a, itbase, t0, t1, t0, t1,
-                      [&](int64_t I, int g) { return (I * 8 + g < n) ? in[I * 8 + g] : 0.0; },
-                      [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] = v; });
-    sweep_dir<KT, -1>(S, a, itbase, t0, t1, t0, t1,
-                      [&](int64_t I, int g) { return (I * 8 + g < n) ? x[I * 8 + g] : 0.0; },
-                      [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] = v; });
+    double* x = a.x;
+    auto store_x = [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] = v; };
+    sweep_dir<KT, +1>(S, a, itbase, t0, t1, t0, t1, a.in, n, store_x);
+    sweep_dir<KT, -1>(S, a, itbase, t0, t1, t0, t1, x, n, store_x);
     return;
   }
-  // ---- corrections: blockIdx = 2*p + side (0 top, 1 bottom); when the window covers the whole
-  //      partition both right-hand sides are folded into the side-0 job.
+  // ---- corrections: blockIdx = 2*p + side (0 top, 1 bottom); when the window covers more than half
+  //      of the partition both right-hand sides are folded into one full-partition job (side 0).
+  //      w = A_i^{-1} r is built in the scratch vector, then x -= w over the window.
   const int p = blockIdx.x >> 1, side = blockIdx.x & 1;
   const int64_t t0 = a.pstart[p], t1 = a.pstart[p + 1];
   const int64_t plen = t1 - t0;
@@ -178,50 +184,35 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(const SweepArgs a) {
   const bool full = 2 * (int64_t)a.tipT > plen;
   const int64_t W = full ? plen : a.tipT;
   double* x = a.x;
+  double* w = a.work;
   const double* rt = a.rtop + (size_t)p * kp;
   const double* rb = a.rbot + (size_t)p * kp;
+  const int64_t npad = a.pstart[a.P] * 8;
+  auto store_w = [&](int64_t I, int g, double v) { w[I * 8 + g] = v; };
+  int64_t lo, hi, flo;   // window [lo,hi) ; forward sweep starts at flo (zero right-hand side above it)
+  bool use_top, use_bot;
   if (full) {
     if (side == 1 || (!top_on && !bot_on)) return;
-    // scratch for y: reuse x? no -- keep the intermediate in the ring only is impossible for the
-    // backward pass, so the forward result is parked in x's shadow: we use the correction identity
-    // x <- x - A^{-1} r  with r sparse, computing w in place in a private global scratch is avoided by
-    // running the forward sweep into shared ybuf only for the rows that matter: rows below the top
-    // KT tile rows get y from the recurrence, which needs every row -> stream them through `work`.
-    double* w = const_cast<double*>(a.in);  // CORR full mode: a.in is a scratch vector (n_padded)
-    sweep_dir<KT, +1>(S, a, itbase, t0, t1, t0, t1,
-                      [&](int64_t I, int g) {
-                        double v = 0.0;
-                        if (top_on && I < t0 + KT) v += rt[(I - t0) * 8 + g];
-                        if (bot_on && I >= t1 - KT) v += rb[(I - (t1 - KT)) * 8 + g];
-                        return v;
-                      },
-                      [&](int64_t I, int g, double v) { w[I * 8 + g] = v; });
-    sweep_dir<KT, -1>(S, a, itbase, t0, t1, t0, t1,
-                      [&](int64_t I, int g) { return w[I * 8 + g]; },
-                      [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] -= v; });
-    return;
-  }
-  double* w = const_cast<double*>(a.in);
-  if (side == 0) {
+    lo = t0; hi = t1; use_top = top_on; use_bot = bot_on; flo = top_on ? t0 : t1 - KT;
+  } else if (side == 0) {
     if (!top_on) return;
-    const int64_t lo = t0, hi = t0 + W;
-    sweep_dir<KT, +1>(S, a, itbase, lo, hi, lo, hi,
-                      [&](int64_t I, int g) { return (I < t0 + KT) ? rt[(I - t0) * 8 + g] : 0.0; },
-                      [&](int64_t I, int g, double v) { w[I * 8 + g] = v; });
-    sweep_dir<KT, -1>(S, a, itbase, lo, hi, lo, hi,
-                      [&](int64_t I, int g) { return w[I * 8 + g]; },
-                      [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] -= v; });
+    lo = t0; hi = t0 + W; use_top = true; use_bot = false; flo = lo;
   } else {
     if (!bot_on) return;
-    const int64_t lo = t1 - W, hi = t1;
-    // forward: the right-hand side is zero above the last KT tile rows, so is y
-    sweep_dir<KT, +1>(S, a, itbase, t1 - KT, hi, t1 - KT, hi,
-                      [&](int64_t I, int g) { return rb[(I - (t1 - KT)) * 8 + g]; },
-                      [&](int64_t I, int g, double v) { w[I * 8 + g] = v; });
-    sweep_dir<KT, -1>(S, a, itbase, lo, hi, lo, hi,
-                      [&](int64_t I, int g) { return (I >= t1 - KT) ? w[I * 8 + g] : 0.0; },
-                      [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] -= v; });
+    lo = t1 - W; hi = t1; use_top = false; use_bot = true; flo = t1 - KT;
   }
+  for (int64_t e = lo * 8 + threadIdx.x; e < hi * 8; e += blockDim.x) {
+    const int64_t I = e >> 3;
+    double v = 0.0;
+    if (use_top && I < t0 + KT) v += rt[e - t0 * 8];
+    if (use_bot && I >= t1 - KT) v += rb[e - (t1 - KT) * 8];
+    w[e] = v;
+  }
+  sweep_dir<KT, +1>(S, a, itbase, flo, hi, lo, hi, w, npad, store_w);
+  sweep_dir<KT, -1>(S, a, itbase, lo, hi, lo, hi, w, npad, store_w);
+  __syncthreads();
+  for (int64_t e = lo * 8 + threadIdx.x; e < hi * 8; e += blockDim.x)
+    if (e < n) x[e] -= w[e];
 }
 
 template <int KT>
@@ -244,7 +235,7 @@ static int launch_sweep_any(spk_ctx* c, const SweepArgs& a, int grid) {
 int spk_launch_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld) {
   for (int r = 0; r < nrhs; ++r) {
     SweepArgs a{};
-    a.band = c->band; a.dinv = c->dinv; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.P = c->P;
+    a.band = c->band; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.P = c->P;
     a.mode = SWEEP_MAIN; a.in = b + (size_t)r * ld; a.x = x + (size_t)r * ld; a.tipT = c->tipT; a.n = c->L.n;
     const int rc = launch_sweep_any(c, a, c->P);
     if (rc) return rc;
@@ -255,8 +246,8 @@ int spk_launch_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t l
 int spk_launch_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld) {
   for (int r = 0; r < nrhs; ++r) {
     SweepArgs a{};
-    a.band = c->band; a.dinv = c->dinv; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.P = c->P;
-    a.mode = SWEEP_CORR; a.in = c->work; a.x = x + (size_t)r * ld; a.tipT = c->tipT; a.n = c->L.n;
+    a.band = c->band; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.P = c->P;
+    a.mode = SWEEP_CORR; a.work = c->work; a.x = x + (size_t)r * ld; a.tipT = c->tipT; a.n = c->L.n;
     a.rtop = c->gtip + (size_t)r * 2 * c->P * c->kp;
     a.rbot = a.rtop + (size_t)c->P * c->kp;
     a.has_left = (c->opts.rank > 0); a.has_right = (c->opts.rank + 1 < c->opts.nranks);

@@ -66,18 +66,25 @@ def test_matmult_vs_oracle(spk, oracle, n, k):
     S.close()
 
 
-# ------------------------------------------------------------------ factor: LU entries vs oracle
+# ------------------------------------------------------------------ factor: block-LU entries vs oracle
 @pytest.mark.parametrize("n,k", [(512, 10), (4096, 20), (3000, 50), (4096, 100), (2500, 128), (1001, 64)])
 def test_lu_factors_match_oracle_single_partition(spk, oracle, n, k):
+    """The kernel stores the block LU grouped by 8 pivots (Lb = A~ D^-1 below, A~ above, D^-1 on the
+    diagonal tiles); oracle.block_lu restates exactly that on the CPU, with the same Schur
+    complements, pivots and boosting rule as the scalar no-pivot LU (oracle.band_lu)."""
     a = oracle.gen_band(n, k, seed=n + k)
-    lu, nb = oracle.band_lu(a)
+    wide, nb, kw = oracle.block_lu(a)
     S = spk.Spike(partitions=1, tip_tiles=-1)
     S.set_band_dense(a, k)
     S.factor()
     f = S.get_band_rows()
-    scale = np.abs(lu).max()
-    assert np.abs(f - lu).max() <= 1e-12 * scale
-    assert S.view()["boosted_pivots"] == 0
+    ref = wide[:, kw - k:kw + k + 1]
+    assert np.abs(f - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    assert S.view()["boosted_pivots"] == 0 and nb == 0
+    # and the block factors solve like the scalar ones
+    lu, _ = oracle.band_lu(a)
+    b = oracle.band_mult(a, np.ones(n))
+    assert relerr(S.solve(b), oracle.band_solve(lu, b)) < RTOL
     S.close()
 
 

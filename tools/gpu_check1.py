@@ -16,7 +16,7 @@ def check(n,k,P,tip,delta=1.2):
     x=S.solve(b); print("  solve err vs u",np.abs(x-u).max()/1.0)
     lu,_=O.band_lu(a); xo=O.band_solve(lu,b); print("  vs oracle exact LU",np.abs(x-xo).max())
     if info['partitions']==1:
-        f=S.get_band_rows(); print("  factor entries maxdiff vs oracle LU",np.abs(f-lu).max())
+        wide,nb,kw=O.block_lu(a); f=S.get_band_rows(); print("  factor entries maxdiff vs oracle block LU",np.abs(f-wide[:,kw-k:kw+k+1]).max())
     return S
 check(4096,20,1,-1)
 check(4096,20,4,-1)
