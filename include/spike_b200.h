@@ -52,6 +52,10 @@ typedef struct spk_info {
   double  factor_ms, solve_ms;       /* device time of the last spk_factor / spk_solve (CUDA events)  */
   int64_t band_bytes;                /* bytes of the device band (tile-major, padded)                 */
   int     kernel_launches;           /* kernels launched by the last spk_factor + spk_solve           */
+  /* device time (ms, CUDA events on the context stream) of the kernels of the last factor / solve:
+     [0] bottom-up tip windows  [1] band LU  [2] spike tips + reduced factor
+     [3] partition sweeps       [4] reduced solve  [5] corrections   [6],[7] reserved */
+  double  stage_ms[8];
 } spk_info;
 
 void spk_default_opts(spk_opts *o);
@@ -115,18 +119,20 @@ int spk_tip_size(spk_ctx *ctx, int *kp);
 int spk_get_boundary(spk_ctx *ctx, int which, double *dev_buf);   /* see SPK_BND_* */
 int spk_set_boundary(spk_ctx *ctx, int which, const double *dev_buf);
 enum {
-  SPK_BND_WT_FIRST = 0,  /* out: W^(t) pre-image of my first partition (St and C block) -> left rank   */
-  SPK_BND_VB_LAST  = 1,  /* out: V^(b) of my last partition                                           */
-  SPK_BND_REMOTE_WT = 2, /* in : right neighbour's W^(t)                                              */
-  SPK_BND_G_TOP = 3,     /* out: g^(t) of my first partition (per solve)                              */
-  SPK_BND_REMOTE_G_TOP = 4, /* in: right neighbour's g^(t)                                            */
-  SPK_BND_X_BOT = 5,     /* out: x^(b) of my last partition (per solve) -> right rank                 */
-  SPK_BND_REMOTE_X_BOT = 6, /* in: left neighbour's x^(b)                                             */
-  SPK_BND_X_TOP_REMOTE = 7, /* out: x^(t) solved for the right neighbour's first partition            */
-  SPK_BND_X_TOP = 8      /* in : my first partition's x^(t) as solved by the left rank                */
+  SPK_BND_WT_FIRST = 0,     /* out: W^(t) of my first partition (kp*kp)            -> left rank, once  */
+  SPK_BND_REMOTE_WT = 2,    /* in : right neighbour's W^(t)                                           */
+  SPK_BND_G_TOP = 3,        /* out: g^(t), first kp entries of my D^-1 b (per solve) -> left rank     */
+  SPK_BND_REMOTE_G_TOP = 4, /* in : right neighbour's g^(t)                                           */
+  SPK_BND_X_BOT = 5,        /* out: x^(b) of the boundary interface (per solve)     -> right rank     */
+  SPK_BND_REMOTE_X_BOT = 6, /* in : left neighbour's x^(b)                                            */
+  SPK_BND_HALO_LEFT = 7,    /* in : last kp entries of the left neighbour's x  (sharded spk_mult)     */
+  SPK_BND_HALO_RIGHT = 8    /* in : first kp entries of the right neighbour's x (sharded spk_mult)    */
 };
-/* split-phase versions of factor/solve used when nranks > 1 (the host performs the exchanges
- * between phases); with nranks == 1 spk_factor/spk_solve run all phases back to back. */
+/* split-phase factor/solve for nranks > 1 (the host performs the NCCL exchanges between phases):
+ *   factor: phase 0 (tip windows + LU), phase 1 (local tips), [WT_FIRST -> left's REMOTE_WT], phase 2
+ *   solve : phase 0 (sweeps), [G_TOP -> left's REMOTE_G_TOP], phase 1 (reduced systems),
+ *           [X_BOT -> right's REMOTE_X_BOT], phase 2 (corrections).  Device vectors, nrhs = 1.
+ * With nranks == 1 spk_factor / spk_solve run all phases back to back. */
 int spk_factor_phase(spk_ctx *ctx, int phase);
 int spk_solve_phase(spk_ctx *ctx, int phase, const double *b, double *x, int nrhs);
 

@@ -8,6 +8,7 @@ anywhere, but every compute call raises unless libspike_b200.so is built and a B
 """
 from .capi import (Spike, SpikeError, lib, library_path, exported_symbols, GMRES, BCGS,  # noqa: F401
                    LAYOUT_ROWS, LAYOUT_DIAGS, MEM_HOST, MEM_DEVICE)
+from .sharded import ShardedSpike, shard_rows  # noqa: F401
 
 __all__ = ["Spike", "SpikeError", "lib", "library_path", "exported_symbols", "GMRES", "BCGS",
-           "LAYOUT_ROWS", "LAYOUT_DIAGS", "MEM_HOST", "MEM_DEVICE"]
+           "LAYOUT_ROWS", "LAYOUT_DIAGS", "MEM_HOST", "MEM_DEVICE", "ShardedSpike", "shard_rows"]

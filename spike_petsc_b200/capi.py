@@ -17,6 +17,7 @@ _LIB = None
 GMRES, BCGS = 0, 1
 LAYOUT_ROWS, LAYOUT_DIAGS = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
+BND_WT_FIRST, BND_REMOTE_WT, BND_G_TOP, BND_REMOTE_G_TOP, BND_X_BOT, BND_REMOTE_X_BOT, BND_HALO_LEFT, BND_HALO_RIGHT = 0, 2, 3, 4, 5, 6, 7, 8
 
 
 class SpikeError(RuntimeError):
@@ -33,7 +34,7 @@ class Info(C.Structure):
     _fields_ = [("n", C.c_int64), ("n_padded", C.c_int64), ("k", C.c_int), ("k_padded", C.c_int), ("kt", C.c_int),
                 ("partitions", C.c_int), ("tip_tiles", C.c_int), ("boosted_pivots", C.c_int64), ("factored", C.c_int),
                 ("frac", C.c_double), ("anorm_max", C.c_double), ("factor_ms", C.c_double), ("solve_ms", C.c_double),
-                ("band_bytes", C.c_int64), ("kernel_launches", C.c_int)]
+                ("band_bytes", C.c_int64), ("kernel_launches", C.c_int), ("stage_ms", C.c_double * 8)]
 
 
 def library_path() -> str:
@@ -218,7 +219,27 @@ class Spike:
                                   C.byref(rn), C.byref(conv)), "spk_krylov")
         return x, its.value, rn.value, bool(conv.value)
 
+    # ---- sharded (multi-GPU) split-phase interface; device memory only
+    def tip_size(self) -> int:
+        kp = C.c_int(0)
+        self._ck(lib().spk_tip_size(self._h, C.byref(kp)), "spk_tip_size")
+        return kp.value
+
+    def factor_phase(self, phase: int):
+        self._ck(lib().spk_factor_phase(self._h, phase), f"spk_factor_phase({phase})")
+
+    def solve_phase(self, phase: int, b=None, x=None):
+        self._ck(lib().spk_solve_phase(self._h, phase, _addr(b), _addr(x), 1), f"spk_solve_phase({phase})")
+
+    def get_boundary(self, which: int, buf):
+        self._ck(lib().spk_get_boundary(self._h, which, _addr(buf)), f"spk_get_boundary({which})")
+
+    def set_boundary(self, which: int, buf):
+        self._ck(lib().spk_set_boundary(self._h, which, _addr(buf)), f"spk_set_boundary({which})")
+
     def view(self) -> dict:
         info = Info()
         self._ck(lib().spk_view(self._h, C.byref(info)), "spk_view")
-        return {f[0]: getattr(info, f[0]) for f in Info._fields_}
+        d = {f[0]: getattr(info, f[0]) for f in Info._fields_}
+        d["stage_ms"] = list(info.stage_ms)
+        return d

@@ -12,6 +12,9 @@ int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, 
 
 static char g_err[512] = "";
 
+#define STAGE_BEGIN(c, i) cudaEventRecord((c)->evst[i][0], (c)->stream)
+#define STAGE_END(c, i) do { cudaEventRecord((c)->evst[i][1], (c)->stream); (c)->stage_timed[i] = 1; } while (0)
+
 extern "C" const char* spk_version(void) { return "spike_b200 0.1 (sm_100a, fp64 DMMA)"; }
 extern "C" const char* spk_last_error(const spk_ctx* ctx) { return ctx ? ctx->err : g_err; }
 
@@ -25,7 +28,7 @@ static void free_band(spk_ctx* c) {
   auto F = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
   F(c->band); F(c->orig); F(c->dinv); F(c->d_pstart); F(c->Sb); F(c->St); F(c->Vb); F(c->Wt); F(c->Red);
   F(c->RedPiv); F(c->work); F(c->gtip); F(c->xtip); F(c->xb); F(c->xt); F(c->corr);
-  F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->xtopRemote);
+  F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->xtopRemote); F(c->xbBoundary); F(c->haloL); F(c->haloR);
   F(c->opA.ia); F(c->opA.ja); F(c->opA.a);
   free(c->h_pstart); c->h_pstart = nullptr;
   c->have_band = c->factored = 0;
@@ -66,6 +69,7 @@ extern "C" int spk_create(spk_ctx** out, const spk_opts* opts) {
     free(c);
     return SPK_ERR_CUDA;
   }
+  for (int i = 0; i < 8; ++i) { cudaEventCreate(&c->evst[i][0]); cudaEventCreate(&c->evst[i][1]); }
   *out = c;
   return SPK_OK;
 }
@@ -78,6 +82,7 @@ extern "C" int spk_destroy(spk_ctx** pc) {
   free_band(c);
   cudaFree(c->d_boost); cudaFree(c->d_scalar);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evs0); cudaEventDestroy(c->evs1);
+  for (int i = 0; i < 8; ++i) { cudaEventDestroy(c->evst[i][0]); cudaEventDestroy(c->evst[i][1]); }
   free(c);
   *pc = nullptr;
   return SPK_OK;
@@ -133,6 +138,13 @@ static int plan(spk_ctx* c, int64_t n, int k) {
   SPK_CUDA(c, cudaMalloc(&c->gtip, sizeof(double) * 2 * (size_t)P * c->kp));
   SPK_CUDA(c, cudaMemsetAsync(c->gtip, 0, sizeof(double) * 2 * (size_t)P * c->kp, c->stream));
   SPK_CUDA(c, cudaMalloc(&c->remoteWt, sizeof(double) * kk));
+  SPK_CUDA(c, cudaMalloc(&c->remoteGtop, sizeof(double) * c->kp));
+  SPK_CUDA(c, cudaMalloc(&c->remoteXbot, sizeof(double) * c->kp));
+  SPK_CUDA(c, cudaMalloc(&c->xbBoundary, sizeof(double) * c->kp));
+  SPK_CUDA(c, cudaMalloc(&c->haloL, sizeof(double) * c->kp));
+  SPK_CUDA(c, cudaMalloc(&c->haloR, sizeof(double) * c->kp));
+  SPK_CUDA(c, cudaMemsetAsync(c->haloL, 0, sizeof(double) * c->kp, c->stream));
+  SPK_CUDA(c, cudaMemsetAsync(c->haloR, 0, sizeof(double) * c->kp, c->stream));
   c->work_elems = L.nt * 8;
   return SPK_OK;
 }
@@ -322,13 +334,22 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
     SPK_CUDA(c, cudaMemsetAsync(c->d_boost, 0, sizeof(int64_t), c->stream));
     SPK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     // W^(t) needs the unfactored top windows: UL pass first (read only), then the in-place LU
-    rc = spk_launch_ul_tips(c);
-    if (rc == SPK_OK) rc = spk_launch_lu(c);
+    STAGE_BEGIN(c, 0); rc = spk_launch_ul_tips(c); STAGE_END(c, 0);
+    if (rc == SPK_OK) { STAGE_BEGIN(c, 1); rc = spk_launch_lu(c); STAGE_END(c, 1); }
     if (rc) return rc;
     return SPK_OK;
   }
   if (phase == 1) {
-    rc = spk_launch_tips(c, 0, c->P - 1);
+    STAGE_BEGIN(c, 2); rc = spk_launch_tips(c, 0, 0); STAGE_END(c, 2);
+    if (rc) return rc;
+    if (c->opts.rank + 1 >= c->opts.nranks) {   // no right neighbour: done
+      SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+      c->factored = 1; c->timed_factor = 1;
+    }
+    return SPK_OK;
+  }
+  if (phase == 2) {  // after SPK_BND_REMOTE_WT has been set
+    rc = spk_launch_tips(c, 1, 0);
     if (rc) return rc;
     SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     c->factored = 1; c->timed_factor = 1;
@@ -339,6 +360,7 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
 }
 
 extern "C" int spk_factor(spk_ctx* c) {
+  if (c && c->opts.nranks > 1) { SPK_SET_ERR(c, "sharded context: drive spk_factor_phase 0,1,(exchange),2 from the host"); return SPK_ERR_STATE; }
   int rc = spk_factor_phase(c, 0);
   if (rc == SPK_OK) rc = spk_factor_phase(c, 1);
   return rc;
@@ -348,25 +370,61 @@ extern "C" int spk_factor(spk_ctx* c) {
 // solve (device pointers, one right-hand side)
 // ---------------------------------------------------------------------------------------------
 int spk_solve_dev(spk_ctx* c, const double* b, double* x) {
+  STAGE_BEGIN(c, 3);
   int rc = spk_launch_sweep(c, b, x, 1, c->L.n);
+  STAGE_END(c, 3);
   if (rc) return rc;
   if (c->P > 1) {
+    STAGE_BEGIN(c, 4);
     rc = spk_launch_reduced_solve(c, x, 1, c->L.n, 0, c->P - 1);
+    STAGE_END(c, 4);
     if (rc) return rc;
+    STAGE_BEGIN(c, 5);
     rc = spk_launch_corrections(c, x, 1, c->L.n);
+    STAGE_END(c, 5);
   }
   return rc;
 }
 
+// split-phase solve for a sharded context (device pointers, one right-hand side):
+//   phase 0: g = D^-1 b                      -> exchange SPK_BND_G_TOP (to the left rank)
+//   phase 1: reduced systems (incl. boundary) -> exchange SPK_BND_X_BOT (to the right rank)
+//   phase 2: coupling right-hand side of partition 0 + corrections
 extern "C" int spk_solve_phase(spk_ctx* c, int phase, const double* b, double* x, int nrhs) {
-  (void)phase; (void)b; (void)x; (void)nrhs;
-  SPK_SET_ERR(c, "split-phase solve is only needed for nranks > 1 and is not wired in this build");
-  return SPK_ERR_UNSUPPORTED;
+  if (!c || nrhs != 1) return SPK_ERR_ARG;
+  if (!c->factored) { SPK_SET_ERR(c, "spk_solve_phase before the factorisation is complete"); return SPK_ERR_STATE; }
+  if (c->opts.mem != SPK_MEM_DEVICE) { SPK_SET_ERR(c, "split-phase solve needs device vectors (opts.mem = SPK_MEM_DEVICE)"); return SPK_ERR_ARG; }
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  int rc = SPK_OK;
+  if (phase == 0) {
+    if (!b || !x) return SPK_ERR_ARG;
+    c->cur_x = x;
+    SPK_CUDA(c, cudaEventRecord(c->evs0, c->stream));
+    STAGE_BEGIN(c, 3); rc = spk_launch_sweep(c, b, x, 1, c->L.n); STAGE_END(c, 3);
+    return rc;
+  }
+  if (!c->cur_x) { SPK_SET_ERR(c, "solve phase %d without phase 0", phase); return SPK_ERR_STATE; }
+  if (phase == 1) {
+    STAGE_BEGIN(c, 4); rc = spk_launch_reduced_solve(c, c->cur_x, 1, c->L.n, 0, c->P - 1); STAGE_END(c, 4);
+    return rc;
+  }
+  if (phase == 2) {
+    STAGE_BEGIN(c, 5);
+    if (c->opts.rank > 0) rc = spk_launch_rtop_left(c);
+    if (rc == SPK_OK) rc = spk_launch_corrections(c, c->cur_x, 1, c->L.n);
+    STAGE_END(c, 5);
+    SPK_CUDA(c, cudaEventRecord(c->evs1, c->stream));
+    c->timed_solve = 1;
+    return rc;
+  }
+  SPK_SET_ERR(c, "bad solve phase %d", phase);
+  return SPK_ERR_ARG;
 }
 
 extern "C" int spk_solve(spk_ctx* c, const double* b, double* x, int nrhs) {
   if (!c || !b || !x || nrhs < 1) return SPK_ERR_ARG;
   if (!c->factored) { SPK_SET_ERR(c, "spk_solve before spk_factor"); return SPK_ERR_STATE; }
+  if (c->opts.nranks > 1) { SPK_SET_ERR(c, "sharded context: drive spk_solve_phase 0,1,2 with the boundary exchanges from the host"); return SPK_ERR_STATE; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   const int64_t n = c->L.n;
   const double* bd = b; double* xd = x;
@@ -474,18 +532,57 @@ extern "C" int spk_view(spk_ctx* c, spk_info* info) {
   info->kernel_launches = c->launches;
   if (c->timed_factor) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) info->factor_ms = ms; }
   if (c->timed_solve) { float ms = 0; if (cudaEventElapsedTime(&ms, c->evs0, c->evs1) == cudaSuccess) info->solve_ms = ms; }
+  for (int i = 0; i < 8; ++i) if (c->stage_timed[i]) { float ms = 0; if (cudaEventElapsedTime(&ms, c->evst[i][0], c->evst[i][1]) == cudaSuccess) info->stage_ms[i] = ms; }
   return SPK_OK;
 }
 
-// ---- multi-GPU boundary hooks (wired in a later milestone) -----------------------------------
+// ---- multi-GPU boundary hooks: buffers follow opts.mem (device pointers in sharded runs) --------
 extern "C" int spk_tip_size(spk_ctx* c, int* kp) { if (!c || !kp) return SPK_ERR_ARG; *kp = c->kp; return SPK_OK; }
-extern "C" int spk_get_boundary(spk_ctx* c, int which, double* dev_buf) {
-  (void)which; (void)dev_buf; SPK_SET_ERR(c, "boundary exchange not wired in this build"); return SPK_ERR_UNSUPPORTED;
+static int bnd_desc(spk_ctx* c, int which, double** ptr, size_t* count, int* is_out) {
+  const size_t kk = (size_t)c->kp * c->kp, k1 = (size_t)c->kp;
+  switch (which) {
+    case SPK_BND_WT_FIRST:     *ptr = c->Wt;          *count = kk; *is_out = 1; return 0;  // W^(t) of my partition 0
+    case SPK_BND_REMOTE_WT:    *ptr = c->remoteWt;    *count = kk; *is_out = 0; return 0;
+    case SPK_BND_G_TOP:        *ptr = c->cur_x;       *count = k1; *is_out = 1; return c->cur_x ? 0 : 1;
+    case SPK_BND_REMOTE_G_TOP: *ptr = c->remoteGtop;  *count = k1; *is_out = 0; return 0;
+    case SPK_BND_X_BOT:        *ptr = c->xbBoundary;  *count = k1; *is_out = 1; return 0;
+    case SPK_BND_REMOTE_X_BOT: *ptr = c->remoteXbot;  *count = k1; *is_out = 0; return 0;
+    case SPK_BND_HALO_LEFT:    *ptr = c->haloL;       *count = k1; *is_out = 0; return 0;
+    case SPK_BND_HALO_RIGHT:   *ptr = c->haloR;       *count = k1; *is_out = 0; return 0;
+    default: return 1;
+  }
 }
-extern "C" int spk_set_boundary(spk_ctx* c, int which, const double* dev_buf) {
-  (void)which; (void)dev_buf; SPK_SET_ERR(c, "boundary exchange not wired in this build"); return SPK_ERR_UNSUPPORTED;
+extern "C" int spk_get_boundary(spk_ctx* c, int which, double* buf) {
+  if (!c || !buf || !c->have_band) return SPK_ERR_ARG;
+  double* p; size_t n; int out;
+  if (bnd_desc(c, which, &p, &n, &out) || !out) { SPK_SET_ERR(c, "spk_get_boundary: bad or unavailable item %d", which); return SPK_ERR_ARG; }
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  SPK_CUDA(c, cudaMemcpyAsync(buf, p, sizeof(double) * n, c->opts.mem == SPK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  if (c->opts.mem != SPK_MEM_DEVICE) SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SPK_OK;
+}
+extern "C" int spk_set_boundary(spk_ctx* c, int which, const double* buf) {
+  if (!c || !buf || !c->have_band) return SPK_ERR_ARG;
+  double* p; size_t n; int out;
+  if (bnd_desc(c, which, &p, &n, &out) || out) { SPK_SET_ERR(c, "spk_set_boundary: bad item %d", which); return SPK_ERR_ARG; }
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  SPK_CUDA(c, cudaMemcpyAsync(p, buf, sizeof(double) * n, c->opts.mem == SPK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  if (c->opts.mem != SPK_MEM_DEVICE) SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SPK_OK;
 }
 
 // debug hook used by tools/lu_trace.py (not part of the public header): attach a device buffer of
 // 64*16 int64 that CTA 0 of the LU kernel fills with clock64 stamps for steps 100..163.
 extern "C" int spk_debug_set_lu_trace(spk_ctx* c, void* dev_buf) { if (!c) return SPK_ERR_ARG; c->lu_trace = dev_buf; return SPK_OK; }
+// bench.py hooks (not in the public header): address of the device band so a pristine copy can be
+// restored between timed steps, and a reset of the "factored" flag after such a restore.
+extern "C" void* spk_debug_band_ptr(spk_ctx* c) { return c ? (void*)c->band : nullptr; }
+extern "C" int spk_debug_reset_factored(spk_ctx* c) { if (!c) return SPK_ERR_ARG; c->factored = 0; c->launches = 0; return SPK_OK; }
+// restore the unfactored band from the copy kept by spk_keep_original(ctx,1) (device-to-device, async)
+extern "C" int spk_debug_restore_band(spk_ctx* c) {
+  if (!c || !c->orig) return SPK_ERR_STATE;
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  SPK_CUDA(c, cudaMemcpyAsync(c->band, c->orig, sizeof(double) * (size_t)c->L.elems(), cudaMemcpyDeviceToDevice, c->stream));
+  c->factored = 0; c->launches = 0;
+  return SPK_OK;
+}

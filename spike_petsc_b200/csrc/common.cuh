@@ -66,7 +66,9 @@ struct spk_ctx {
   double *corr;        // P * 2 * tipT*8
   int64_t work_elems;
   // remote (multi-GPU) boundary buffers
-  double *remoteWt, *remoteGtop, *remoteXbot, *xtopRemote;
+  double *remoteWt, *remoteGtop, *remoteXbot, *xtopRemote, *xbBoundary;
+  double *haloL, *haloR; // MatMult halos (8*kt entries of the neighbours' x)
+  double *cur_x;       // output vector of the solve in progress (split-phase)
   int have_remote_wt;
   // operator for Krylov
   CsrDev opA;
@@ -80,6 +82,8 @@ struct spk_ctx {
   cudaEvent_t ev0, ev1;     // factor start/stop
   cudaEvent_t evs0, evs1;   // solve start/stop
   int timed_factor, timed_solve;
+  cudaEvent_t evst[8][2];   // per-stage start/stop (see spk_info.stage_ms)
+  int stage_timed[8];
   void* lu_trace;           // debug: device buffer for clock64 stamps of the LU kernel (tools only)
   char err[512];
 };
@@ -147,7 +151,8 @@ int spk_launch_absmax(spk_ctx* c, const double* band, double* out_dev);
 int spk_launch_matmult(spk_ctx* c, const double* band, const double* x, double* y);
 int spk_launch_lu(spk_ctx* c);            // per-partition LU (+ S_b capture, dinv)
 int spk_launch_ul_tips(spk_ctx* c);       // UL window -> S_t
-int spk_launch_tips(spk_ctx* c, int iface_lo, int iface_hi);  // Vb, Wt, reduced LU for interfaces [lo,hi)
+int spk_launch_tips(spk_ctx* c, int what, int unused);  // 0: local tips + reduced blocks, 1: boundary reduced block
+int spk_launch_rtop_left(spk_ctx* c);
 int spk_launch_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld);   // g = D^-1 b
 int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int iface_lo, int iface_hi);
 int spk_launch_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld);

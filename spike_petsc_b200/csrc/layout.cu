@@ -156,7 +156,8 @@ int spk_launch_gather(spk_ctx* c, const int* idx_dev, int inverse, const double*
 // Algorithmic bytes: B + 2*8*N.
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_band_matmult(const double* __restrict__ band, BandLayout L,
-                                                      const double* __restrict__ x, double* __restrict__ y) {
+                                                      const double* __restrict__ x, double* __restrict__ y,
+                                                      const double* __restrict__ haloL, const double* __restrict__ haloR) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -169,11 +170,19 @@ __global__ void __launch_bounds__(256) k_band_matmult(const double* __restrict__
 #pragma unroll 4
     for (int t = 0; t < L.tpr; ++t) {
       const int64_t J = J0 + t;
-      if (J < 0 || J >= L.nt) continue;
-      const double2 a = *reinterpret_cast<const double2*>(row + (int64_t)t * SPK_TILE_ELEMS);
       const int64_t col = J * SPK_TILE + 2 * tq;
-      const double2 xv = (col + 1 < L.n) ? *reinterpret_cast<const double2*>(x + col)
-                                         : make_double2(col < L.n ? x[col] : 0.0, 0.0);
+      double2 xv;
+      if (J < 0) {          // rows owned by the left-neighbour rank: haloL holds its last 8*kt entries
+        if (!haloL) continue;
+        xv = *reinterpret_cast<const double2*>(haloL + (col + (int64_t)L.kt * SPK_TILE));
+      } else if (J >= L.nt) {  // right neighbour: haloR holds its first 8*kt entries
+        if (!haloR) continue;
+        xv = *reinterpret_cast<const double2*>(haloR + (col - L.nt * SPK_TILE));
+      } else {
+        xv = (col + 1 < L.n) ? *reinterpret_cast<const double2*>(x + col)
+                             : make_double2(col < L.n ? x[col] : 0.0, 0.0);
+      }
+      const double2 a = *reinterpret_cast<const double2*>(row + (int64_t)t * SPK_TILE_ELEMS);
       acc = fma(a.x, xv.x, acc);
       acc = fma(a.y, xv.y, acc);
     }
@@ -188,7 +197,9 @@ int spk_launch_matmult(spk_ctx* c, const double* band, const double* x, double* 
   int64_t blocks = (warps + 7) / 8;
   if (blocks > (int64_t)c->sm_count * 16) blocks = (int64_t)c->sm_count * 16;
   if (blocks < 1) blocks = 1;
-  k_band_matmult<<<(unsigned)blocks, 256, 0, c->stream>>>(band, c->L, x, y);
+  const bool has_left = c->opts.rank > 0, has_right = c->opts.rank + 1 < c->opts.nranks;
+  k_band_matmult<<<(unsigned)blocks, 256, 0, c->stream>>>(band, c->L, x, y, has_left ? c->haloL : nullptr,
+                                                          has_right ? c->haloR : nullptr);
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }

@@ -266,6 +266,9 @@ struct RedSolveArgs {
   const double* x;          // g (after the main sweep)
   double* rtop; double* rbot;  // P * kp each
   int first_iface;
+  int boundary_iface;          // interface index served with remote data (-1: none)
+  const double* remoteWt; const double* remoteGtop; double* xbBoundary;
+  int64_t n;
 };
 // y[r] = sum_c M[r*kp+c] v[c] for r = warp, warp+4, ... ; lanes stride the columns; shuffle reduction
 __device__ __forceinline__ double row_dot(const double* __restrict__ Mrow, const double* v, int kp, int lane) {
@@ -279,14 +282,15 @@ __global__ void __launch_bounds__(128) k_reduced_solve(const RedSolveArgs a) {
   const int kp = a.L.kt * 8, KT = a.L.kt;
   double* gb = sm; double* gt = gb + kp; double* tv = gt + kp; double* xt = tv + kp; double* xb = xt + kp;
   const int i = blockIdx.x + a.first_iface;
+  const bool bnd = (i == a.boundary_iface);
   const int64_t tb = a.pstart[i + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int e = threadIdx.x; e < kp; e += blockDim.x) {
     gb[e] = a.x[(tb - KT) * 8 + e];
-    gt[e] = (tb * 8 + e < a.L.n) ? a.x[tb * 8 + e] : 0.0;
+    gt[e] = bnd ? a.remoteGtop[e] : ((tb * 8 + e < a.n) ? a.x[tb * 8 + e] : 0.0);
   }
   __syncthreads();
-  const double* W = a.Wt + (size_t)(i + 1) * kp * kp;
+  const double* W = bnd ? a.remoteWt : a.Wt + (size_t)(i + 1) * kp * kp;
   const double* V = a.Vb + (size_t)i * kp * kp;
   const double* R = a.Rinv + (size_t)i * kp * kp;
   for (int r = warp; r < kp; r += 4) { const double s = row_dot(W + (size_t)r * kp, gb, kp, lane); if (lane == 0) tv[r] = gt[r] - s; }
@@ -299,15 +303,38 @@ __global__ void __launch_bounds__(128) k_reduced_solve(const RedSolveArgs a) {
   for (int r = warp; r < kp; r += 4) {
     double s1 = 0.0, s2 = 0.0;
     for (int c = lane; c < kp; c += 32) {
-      if ((c >> 3) >= (r >> 3)) s1 = fma(a.band[a.L.elem_off(tb * 8 + r, (tb - KT) * 8 + c)], xb[c], s1);
+      if (!bnd && (c >> 3) >= (r >> 3)) s1 = fma(a.band[a.L.elem_off(tb * 8 + r, (tb - KT) * 8 + c)], xb[c], s1);
       if ((c >> 3) <= (r >> 3)) s2 = fma(a.band[a.L.elem_off((tb - KT) * 8 + r, tb * 8 + c)], xt[c], s2);
     }
     for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-    if (lane == 0) { a.rtop[(size_t)(i + 1) * kp + r] = s1; a.rbot[(size_t)i * kp + r] = s2; }
+    if (lane == 0) {
+      if (!bnd) a.rtop[(size_t)(i + 1) * kp + r] = s1; else a.xbBoundary[r] = xb[r];
+      a.rbot[(size_t)i * kp + r] = s2;
+    }
   }
 }
 
+// r_top of partition 0 from the left neighbour's x_b:  r = C_0 x_b,  C_0(r,c) = A(r, c - kp)
+__global__ void __launch_bounds__(128) k_rtop_left(const double* __restrict__ band, BandLayout L, const double* __restrict__ xb, double* rtop) {
+  const int kp = L.kt * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < kp; r += 4) {
+    double s1 = 0.0;
+    for (int c = lane; c < kp; c += 32)
+      if ((c >> 3) >= (r >> 3)) s1 = fma(band[L.elem_off(r, (int64_t)c - kp)], xb[c], s1);
+    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    if (lane == 0) rtop[r] = s1;
+  }
+}
+int spk_launch_rtop_left(spk_ctx* c) {
+  k_rtop_left<<<1, 128, 0, c->stream>>>(c->band, c->L, c->remoteXbot, c->gtip);
+  SPK_KERNEL_CHECK(c);
+  return SPK_OK;
+}
+
 int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int iface_lo, int iface_hi) {
+  const bool has_right = c->opts.rank + 1 < c->opts.nranks;
+  if (has_right && iface_hi == c->P - 1) iface_hi = c->P;   // include the boundary interface
   const int n = iface_hi - iface_lo;
   if (n <= 0) return SPK_OK;
   for (int r = 0; r < nrhs; ++r) {
@@ -317,6 +344,8 @@ int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int if
     a.rtop = c->gtip + (size_t)r * 2 * c->P * c->kp;
     a.rbot = a.rtop + (size_t)c->P * c->kp;
     a.first_iface = iface_lo;
+    a.boundary_iface = has_right ? c->P - 1 : -1;
+    a.remoteWt = c->remoteWt; a.remoteGtop = c->remoteGtop; a.xbBoundary = c->xbBoundary; a.n = c->L.n;
     k_reduced_solve<<<n, 128, sizeof(double) * 5 * c->kp, c->stream>>>(a);
     SPK_KERNEL_CHECK(c);
   }

@@ -143,28 +143,46 @@ __global__ void __launch_bounds__(TIPS_THREADS) k_reduced_factor(const RedArgs a
 
 static size_t tips_smem(int kp) { return sizeof(double) * ((size_t)kp * (kp + 1) + 8) + sizeof(int) * (size_t)(kp + 2 + 8) + 64; }
 
-// interfaces [lo,hi): interface i couples partition i (bottom) with partition i+1 (top)
-int spk_launch_tips(spk_ctx* c, int iface_lo, int iface_hi) {
-  const int kp = c->kp;
+// Spike tips for this rank.  Interface i couples partition i (bottom) with partition i+1 (top);
+// interface P-1 is the boundary with the right-neighbour rank (its W^(t) arrives in c->remoteWt).
+//   what = 0: every local tip and local reduced block
+//   what = 1: only the boundary reduced block (after remoteWt has been set)
+int spk_launch_tips(spk_ctx* c, int what, int unused) {
+  (void)unused;
+  const int kp = c->kp, P = c->P;
   const size_t smem = tips_smem(kp);
   SPK_CUDA(c, cudaFuncSetAttribute(k_spike_tip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SPK_CUDA(c, cudaFuncSetAttribute(k_reduced_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int n = iface_hi - iface_lo;
-  if (n <= 0) return SPK_OK;
+  const bool has_left = c->opts.rank > 0, has_right = c->opts.rank + 1 < c->opts.nranks;
+  RedArgs r;
+  r.Vb = c->Vb; r.Wt = c->Wt; r.Rinv = c->Red; r.kp = kp; r.wt_part_offset = 1; r.remoteWt = c->remoteWt;
+  if (what == 1) {
+    if (!has_right) return SPK_OK;
+    r.first_iface = P - 1; r.remote_iface = P - 1;
+    k_reduced_factor<<<1, TIPS_THREADS, smem, c->stream>>>(r);
+    SPK_KERNEL_CHECK(c);
+    return SPK_OK;
+  }
   TipArgs t;
   t.band = c->band; t.L = c->L; t.pstart = c->d_pstart;
-  // V^(b) of partitions lo..hi-1
-  t.S = c->Sb; t.out = c->Vb; t.first_part = iface_lo; t.which = 0;
-  k_spike_tip<<<n, TIPS_THREADS, smem, c->stream>>>(t);
-  SPK_KERNEL_CHECK(c);
-  // W^(t) of partitions lo+1..hi
-  t.S = c->St; t.out = c->Wt; t.first_part = iface_lo + 1; t.which = 1;
-  k_spike_tip<<<n, TIPS_THREADS, smem, c->stream>>>(t);
-  SPK_KERNEL_CHECK(c);
-  RedArgs r;
-  r.Vb = c->Vb; r.Wt = c->Wt; r.Rinv = c->Red; r.kp = kp; r.first_iface = iface_lo; r.wt_part_offset = 1;
-  r.remoteWt = c->remoteWt; r.remote_iface = -1;
-  k_reduced_factor<<<n, TIPS_THREADS, smem, c->stream>>>(r);
-  SPK_KERNEL_CHECK(c);
+  // V^(b) of partitions 0..P-2 (+ P-1 when a right neighbour exists)
+  const int nvb = (P - 1) + (has_right ? 1 : 0);
+  if (nvb > 0) {
+    t.S = c->Sb; t.out = c->Vb; t.first_part = 0; t.which = 0;
+    k_spike_tip<<<nvb, TIPS_THREADS, smem, c->stream>>>(t);
+    SPK_KERNEL_CHECK(c);
+  }
+  // W^(t) of partitions 1..P-1 (+ 0 when a left neighbour exists)
+  const int wfirst = has_left ? 0 : 1;
+  if (P - wfirst > 0) {
+    t.S = c->St; t.out = c->Wt; t.first_part = wfirst; t.which = 1;
+    k_spike_tip<<<P - wfirst, TIPS_THREADS, smem, c->stream>>>(t);
+    SPK_KERNEL_CHECK(c);
+  }
+  if (P - 1 > 0) {
+    r.first_iface = 0; r.remote_iface = -1;
+    k_reduced_factor<<<P - 1, TIPS_THREADS, smem, c->stream>>>(r);
+    SPK_KERNEL_CHECK(c);
+  }
   return SPK_OK;
 }

@@ -1,0 +1,125 @@
+"""Row-block sharding of one banded system across the GPUs of a box (one process per GPU).
+
+SPIKE partitions shard naturally: rank r owns a contiguous block of rows (a multiple of 8) and runs
+the same factor / solve kernels on it.  Only the data of the partition interface that straddles two
+ranks crosses NVLink: one kp x kp spike tip W^(t) per boundary at factor time and two kp-vectors per
+boundary per solve (kp = 8*ceil(K/8)); this replaces the PETSc MPI scatter a distributed Mat/Vec
+would do on that path.  The exchanges are point-to-point `torch.distributed` operations, i.e.
+ncclSend / ncclRecv over NVLink 5 when the backend is NCCL.  The engine argument exists so the
+exchange protocol can be exercised on CPU (gloo) with a reference engine (tests/test_sharded_cpu.py).
+"""
+from __future__ import annotations
+
+from . import capi
+
+
+def shard_rows(n_global: int, world: int):
+    """Contiguous row blocks, every boundary a multiple of 8 rows (tile size)."""
+    tiles = (n_global + 7) // 8
+    bounds = [min(n_global, (tiles * r // world) * 8) for r in range(world + 1)]
+    bounds[-1] = n_global
+    return bounds
+
+
+class ShardedSpike:
+    def __init__(self, engine, rank: int, world: int, dist=None):
+        """engine: an object with the split-phase API of capi.Spike (factor_phase, solve_phase,
+        get_boundary, set_boundary, tip_size) created for this rank's row block."""
+        self.e, self.rank, self.world, self.dist = engine, rank, world, dist
+        self._bufs = None
+
+    # ---- neighbour exchange: send `out` to rank+dir_, receive the matching buffer from rank-dir_
+    def _shift(self, send_buf, recv_buf, direction: int):
+        """direction=-1: send to the left neighbour / receive from the right one; +1 the reverse."""
+        if self.world == 1:
+            return
+        import torch.distributed as td
+        ops = []
+        dst = self.rank + direction
+        src = self.rank - direction
+        if 0 <= dst < self.world:
+            ops.append(td.P2POp(td.isend, send_buf, dst))
+        if 0 <= src < self.world:
+            ops.append(td.P2POp(td.irecv, recv_buf, src))
+        if ops:
+            for req in td.batch_isend_irecv(ops):
+                req.wait()
+
+    def _alloc(self, like):
+        import torch
+        kp = self.e.tip_size()
+        mk = lambda m: torch.zeros(m, dtype=torch.float64, device=like.device)  # noqa: E731
+        self._bufs = {"wt_out": mk(kp * kp), "wt_in": mk(kp * kp), "v_out": mk(kp), "v_in": mk(kp)}
+        self.kp = kp
+
+    def _ptr(self, t):
+        return self.e.buffer_address(t) if hasattr(self.e, "buffer_address") else t.data_ptr()
+
+    def factor(self, like):
+        """like: any tensor on this rank's device (used to allocate the exchange buffers)."""
+        if self._bufs is None:
+            self._alloc(like)
+        b = self._bufs
+        has_left, has_right = self.rank > 0, self.rank + 1 < self.world
+        self.e.factor_phase(0)
+        self.e.factor_phase(1)
+        if self.world > 1:
+            if has_left:
+                self.e.get_boundary(capi.BND_WT_FIRST, self._ptr(b["wt_out"]))
+            self._sync(like)
+            self._shift(b["wt_out"], b["wt_in"], -1)
+            if has_right:
+                self.e.set_boundary(capi.BND_REMOTE_WT, self._ptr(b["wt_in"]))
+                self.e.factor_phase(2)
+
+    def solve(self, bvec, xvec):
+        """bvec, xvec: this rank's rows of b and x (tensors on the rank's device; may alias)."""
+        if self._bufs is None:
+            self._alloc(bvec)
+        b = self._bufs
+        has_left, has_right = self.rank > 0, self.rank + 1 < self.world
+        self.e.solve_phase(0, self._ptr(bvec), self._ptr(xvec))
+        if self.world > 1:
+            if has_left:
+                self.e.get_boundary(capi.BND_G_TOP, self._ptr(b["v_out"]))
+            self._sync(bvec)
+            self._shift(b["v_out"], b["v_in"], -1)
+            if has_right:
+                self.e.set_boundary(capi.BND_REMOTE_G_TOP, self._ptr(b["v_in"]))
+        self.e.solve_phase(1)
+        if self.world > 1:
+            if has_right:
+                self.e.get_boundary(capi.BND_X_BOT, self._ptr(b["v_out"]))
+            self._sync(bvec)
+            self._shift(b["v_out"], b["v_in"], +1)
+            if has_left:
+                self.e.set_boundary(capi.BND_REMOTE_X_BOT, self._ptr(b["v_in"]))
+        self.e.solve_phase(2)
+        return xvec
+
+    def mult(self, xvec, yvec):
+        """y = A x on this rank's rows with the kp-entry halos of both neighbours."""
+        if self._bufs is None:
+            self._alloc(xvec)
+        kp = self.kp
+        if self.world > 1:
+            import torch
+            lo = xvec[:kp].contiguous()
+            hi = xvec[-kp:].contiguous()
+            from_right = torch.zeros_like(lo)
+            from_left = torch.zeros_like(hi)
+            self._sync(xvec)
+            self._shift(lo, from_right, -1)   # my first entries go left; I receive the right rank's first entries
+            self._shift(hi, from_left, +1)    # my last entries go right; I receive the left rank's last entries
+            if self.rank + 1 < self.world:
+                self.e.set_boundary(capi.BND_HALO_RIGHT, self._ptr(from_right))
+            if self.rank > 0:
+                self.e.set_boundary(capi.BND_HALO_LEFT, self._ptr(from_left))
+        self.e.mult(self._ptr(xvec), self._ptr(yvec))
+        return yvec
+
+    def _sync(self, t):
+        # the engine enqueues on the legacy default stream; NCCL p2p runs on torch's streams
+        if getattr(t, "is_cuda", False):
+            import torch
+            torch.cuda.synchronize(t.device)

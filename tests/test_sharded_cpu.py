@@ -1,0 +1,140 @@
+"""N>1 host logic on CPU: world_size 2 (and 3) over gloo.  The neighbour-exchange protocol of
+spike_petsc_b200.sharded.ShardedSpike is driven with a dense numpy engine that implements the same
+split-phase interface as the CUDA context (one SPIKE partition per rank)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+class NumpyEngine:
+    """Reference engine with the split-phase API of capi.Spike; exchange buffers are CPU tensors."""
+
+    def __init__(self, A, lo, hi, k, rank, world):
+        self.k, self.rank, self.world = k, rank, world
+        n = A.shape[0]
+        self.Aloc = A[lo:hi, lo:hi].copy()
+        self.B = A[hi - k:hi, hi:hi + k].copy() if hi < n else None   # coupling to the right rank
+        self.C = A[lo:lo + k, lo - k:lo].copy() if lo > 0 else None   # coupling to the left rank
+        self.m = hi - lo
+        self.remote = {}
+
+    def buffer_address(self, t):
+        return t
+
+    def tip_size(self):
+        return self.k
+
+    def factor_phase(self, ph):
+        k, m = self.k, self.m
+        if ph == 1:
+            if self.B is not None:
+                rhs = np.zeros((m, k)); rhs[-k:] = self.B
+                self.Vb = np.linalg.solve(self.Aloc, rhs)[-k:]
+            if self.C is not None:
+                rhs = np.zeros((m, k)); rhs[:k] = self.C
+                self.Wt = np.linalg.solve(self.Aloc, rhs)[:k]
+        if ph == 2:
+            self.R = np.linalg.inv(np.eye(k) - self.remote["wt"] @ self.Vb)
+
+    def get_boundary(self, which, buf):
+        from spike_petsc_b200 import capi
+        src = {capi.BND_WT_FIRST: lambda: self.Wt.ravel(), capi.BND_G_TOP: lambda: self.g[:self.k],
+               capi.BND_X_BOT: lambda: self.xb}[which]()
+        buf.copy_(torch.from_numpy(np.ascontiguousarray(src)))
+
+    def set_boundary(self, which, buf):
+        from spike_petsc_b200 import capi
+        v = buf.numpy().copy()
+        if which == capi.BND_REMOTE_WT:
+            self.remote["wt"] = v.reshape(self.k, self.k)
+        elif which == capi.BND_REMOTE_G_TOP:
+            self.remote["gt"] = v
+        elif which == capi.BND_REMOTE_X_BOT:
+            self.remote["xb"] = v
+
+    def solve_phase(self, ph, b=None, x=None):
+        k = self.k
+        if ph == 0:
+            self.x = x
+            self.g = np.linalg.solve(self.Aloc, b.numpy())
+            self.rbot = None
+        elif ph == 1:
+            if self.B is not None:
+                gb = self.g[-k:]
+                t = self.remote["gt"] - self.remote["wt"] @ gb
+                xt = self.R @ t
+                self.xb = gb - self.Vb @ xt
+                self.rbot = self.B @ xt
+        elif ph == 2:
+            r = np.zeros(self.m)
+            if self.C is not None:
+                r[:k] += self.C @ self.remote["xb"]
+            if self.rbot is not None:
+                r[-k:] += self.rbot
+            self.x.copy_(torch.from_numpy(self.g - np.linalg.solve(self.Aloc, r)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, n, k, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle import oracle as O
+        from spike_petsc_b200.sharded import ShardedSpike, shard_rows
+        a = O.gen_band(n, k)
+        A = np.zeros((n, n))
+        for i in range(n):
+            for d in range(-k, k + 1):
+                if 0 <= i + d < n:
+                    A[i, i + d] = a[i, d + k]
+        u = O.gen_vec(n, 7)
+        bfull = A @ u
+        bounds = shard_rows(n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        eng = NumpyEngine(A, lo, hi, k, rank, world)
+        S = ShardedSpike(eng, rank, world)
+        b = torch.from_numpy(bfull[lo:hi].copy())
+        x = torch.zeros_like(b)
+        S.factor(b)
+        S.solve(b, x)
+        err = float(np.abs(x.numpy() - u[lo:hi]).max())
+        res = torch.tensor([err], dtype=torch.float64)
+        dist.all_reduce(res, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            out.put(res.item())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_exchange_protocol_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 480, 5, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) < 1e-11
+
+
+def test_shard_rows_are_tile_aligned():
+    from spike_petsc_b200.sharded import shard_rows
+    for n, w in [(10_000_000, 8), (1_000_003, 4), (100, 2), (64, 8)]:
+        b = shard_rows(n, w)
+        assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+        assert all(v % 8 == 0 for v in b[:-1])
