@@ -7,7 +7,9 @@ CSRC    := spike_petsc_b200/csrc
 LIBDIR  := spike_petsc_b200/lib
 OBJS    := $(LIBDIR)/layout.o $(LIBDIR)/lu.o $(LIBDIR)/tips.o $(LIBDIR)/solve.o $(LIBDIR)/krylov.o $(LIBDIR)/capi.o
 
-all: $(LIBDIR)/libspike_b200.so oracle
+HOST    := spike_petsc_b200/host
+
+all: $(LIBDIR)/libspike_b200.so $(LIBDIR)/libspike_petsc.so oracle
 
 $(LIBDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/spike_b200.h
 	@mkdir -p $(LIBDIR)
@@ -15,6 +17,10 @@ $(LIBDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/spike_b200.h
 
 $(LIBDIR)/libspike_b200.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+# PETSc-shaped host glue (C): PCBANDED / KSPREORDER / MatCreateSubMatrixBanded on the C ABI
+$(LIBDIR)/libspike_petsc.so: $(HOST)/pcbanded.c $(HOST)/kspreorder.c $(HOST)/petscshim.c $(HOST)/petscshim.h $(HOST)/spike_petsc.h $(LIBDIR)/libspike_b200.so
+	/usr/bin/gcc -O2 -fPIC -Wall -shared -o $@ $(HOST)/pcbanded.c $(HOST)/kspreorder.c $(HOST)/petscshim.c -L$(LIBDIR) -lspike_b200 -Wl,-rpath,'$$ORIGIN' -lm
 
 oracle:
 	$(MAKE) -C oracle

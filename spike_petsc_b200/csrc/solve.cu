@@ -48,62 +48,67 @@ struct SweepSmem {
 
 // One directional sweep over tile rows.  DIR=+1: forward with Lb (rows r0..r1-1 ascending, unit block
 // diagonal), DIR=-1: backward with Ub and the explicit D^-1 (rows r1-1..r0 descending).
-// Tile columns outside [vlo,vhi) are ignored.  vin[row] is the right-hand side (streamed through the
+// Only blocks solved earlier in the same sweep contribute (the sweep range is the solve window).
+// vin[row] is the right-hand side (streamed through the
 // bulk-copy ring together with the factor tiles), sink(I, g, value) consumes the result.
 template <int KT, int DIR, class Sink>
-__device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, int64_t& itbase, int64_t r0, int64_t r1,
-                                          int64_t vlo, int64_t vhi, const double* vin, int64_t nvalid, Sink sink) {
+__device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, unsigned& itbase, int64_t r0, int64_t r1,
+                                          const double* vin, int64_t nvalid, Sink sink) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
-  const int64_t nrows = r1 - r0;
+  const int nrows = (int)(r1 - r0);
   if (nrows <= 0) return;
-  auto row_of = [&](int64_t it) -> int64_t { return DIR > 0 ? r0 + it : r1 - 1 - it; };
-  // the ring's mbarriers keep counting across sweeps: global iteration index = itbase + it
-  const int64_t ib = itbase;
-  itbase += nrows;
+  constexpr int RING = KT + 1;
+  // the ring's mbarriers keep counting across sweeps: global iteration index = itbase + it (32-bit, wraps)
+  const unsigned ib = itbase;
+  itbase += (unsigned)nrows;
   const bool bulk_rhs = ((reinterpret_cast<uintptr_t>(vin) & 15) == 0);
   // earlier generic-proxy writes of this CTA (previous sweep's results) must be visible to the async proxy
   asm volatile("fence.proxy.async;" ::: "memory");
   __syncthreads();
-  for (int e = threadIdx.x; e < (KT + 1) * 8; e += blockDim.x) (&S.ybuf[0][0])[e] = 0.0;
+  for (int e = threadIdx.x; e < RING * 8; e += blockDim.x) (&S.ybuf[0][0])[e] = 0.0;
   for (int e = threadIdx.x; e < 2 * 3 * 8; e += blockDim.x) (&S.farpart[0][0][0])[e] = 0.0;
   __syncthreads();
   constexpr int NTILE = DIR > 0 ? KT : KT + 1;
-  auto rhs_bulk_ok = [&](int64_t I) -> bool { return bulk_rhs && (I * 8 + 8 <= nvalid); };
-  auto issue = [&](int64_t it) {  // executed by one thread
-    const int st = (int)((ib + it) % SW_NST);
-    const int64_t I = row_of(it);
+  const int64_t rstart = DIR > 0 ? r0 : r1 - 1;                 // tile row of iteration 0
+  const double* src0 = a.band + (rstart * a.tpr + (DIR > 0 ? 0 : KT)) * SPK_TILE_ELEMS;  // d=-KT..-1  or  d=0..KT
+  const int64_t src_step = (int64_t)DIR * a.tpr * SPK_TILE_ELEMS;
+  const double* rhs0 = vin + rstart * 8;
+  const int64_t rows_bulk = (nvalid / 8);                       // tile rows whose 8 entries all exist in vin
+  auto rhs_bulk_ok = [&](int it) -> bool { return bulk_rhs && (rstart + (int64_t)DIR * it) < rows_bulk; };
+  auto issue = [&](int it) {  // executed by one thread
+    const unsigned gi = ib + (unsigned)it;
+    const int st = (int)(gi % SW_NST);
     uint64_t* bar = reinterpret_cast<uint64_t*>(&S.full[st]);
-    const bool rb = rhs_bulk_ok(I);
+    const bool rb = rhs_bulk_ok(it);
     mbar_expect_tx(bar, (uint32_t)(NTILE * 512 + (rb ? 64 : 0)));
-    const double* src = a.band + (I * a.tpr + (DIR > 0 ? 0 : KT)) * SPK_TILE_ELEMS;  // d=-KT..-1  or  d=0..KT
-    bulk_g2s(&S.stage[st][0][0], src, NTILE * 512, bar);
-    if (rb) bulk_g2s(&S.stage[st][KT + 1][0], vin + I * 8, 64, bar);
+    bulk_g2s(&S.stage[st][0][0], src0 + (int64_t)it * src_step, NTILE * 512, bar);
+    if (rb) bulk_g2s(&S.stage[st][KT + 1][0], rhs0 + (int64_t)DIR * it * 8, 64, bar);
   };
   if (threadIdx.x == 32) {
-    for (int64_t it = 0; it < SW_NST && it < nrows; ++it) issue(it);
+    for (int it = 0; it < SW_NST && it < nrows; ++it) issue(it);
   }
-  // slot of tile row I in the y ring
-  auto yslot = [&](int64_t I) -> int { return (int)(((I % (KT + 1)) + (KT + 1)) % (KT + 1)); };
-
-  for (int64_t it = 0; it < nrows; ++it) {
-    const int64_t I = row_of(it);
+  // y ring: the block solved at iteration `it` lives in slot it % RING
+  int slot = 0;   // slot of the current iteration
+  for (int it = 0; it < nrows; ++it) {
+    const unsigned gi = ib + (unsigned)it;
     if (warp == 0) {
-      // -------- near warp: finish tile row I
-      // (the far warps already waited for this stage one iteration ago; only row 0 is unseen)
-      const int st = (int)((ib + it) % SW_NST);
-      if (it == 0) mbar_wait(reinterpret_cast<uint64_t*>(&S.full[st]), (uint32_t)(((ib + it) / SW_NST) & 1));
-      const int par = (int)(it & 1);
+      // -------- near warp: finish the tile row of this iteration
+      // (the far warps already waited for this stage one iteration ago; only iteration 0 is unseen)
+      const int st = (int)(gi % SW_NST);
+      if (it == 0) mbar_wait(reinterpret_cast<uint64_t*>(&S.full[st]), (gi / SW_NST) & 1u);
+      const int par = it & 1;
+      const int64_t I = rstart + (int64_t)DIR * it;
       double rhs;
-      if (rhs_bulk_ok(I)) rhs = S.stage[st][KT + 1][g];
+      if (rhs_bulk_ok(it)) rhs = S.stage[st][KT + 1][g];
       else rhs = (I * 8 + g < nvalid) ? vin[I * 8 + g] : 0.0;
       const double cg = rhs - (S.farpart[par][0][g] + S.farpart[par][1][g] + S.farpart[par][2][g]);
       // adjacent tile: forward Lb(I,I-1) is stage tile KT-1 (d=-1); backward Ub(I,I+1) is stage tile 1 (d=+1)
-      const int64_t Jn = I - DIR;
       double part = 0.0;
-      if (Jn >= vlo && Jn < vhi && it > 0) {
+      if (it > 0) {
+        const int ps = slot == 0 ? RING - 1 : slot - 1;
         const double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 1][2 * lane]);
-        const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[yslot(Jn)][2 * tq]);
+        const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[ps][2 * tq]);
         part = fma(t.x, yp.x, t.y * yp.y);
       }
       part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -118,42 +123,45 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
         yv += __shfl_xor_sync(0xffffffffu, yv, 1);
         yv += __shfl_xor_sync(0xffffffffu, yv, 2);
       }
-      if (tq == 0) { S.ybuf[yslot(I)][g] = yv; sink(I, g, yv); }
+      if (tq == 0) { S.ybuf[slot][g] = yv; sink(I, g, yv); }
     } else {
-      // -------- far warps: partial sums for the NEXT tile row from blocks at distance >= 2
-      const int64_t itn = it + 1;
+      // -------- far warps: partial sums for the NEXT iteration from blocks solved >= 2 iterations before it
+      const int itn = it + 1;
       if (itn < nrows) {
-        const int64_t In = row_of(itn);
-        const int stn = (int)((ib + itn) % SW_NST);
-        mbar_wait(reinterpret_cast<uint64_t*>(&S.full[stn]), (uint32_t)(((ib + itn) / SW_NST) & 1));
+        const unsigned gn = gi + 1u;
+        const int stn = (int)(gn % SW_NST);
+        mbar_wait(reinterpret_cast<uint64_t*>(&S.full[stn]), (gn / SW_NST) & 1u);
         const int fw = warp - 1;
+        const int sn = slot + 1 == RING ? 0 : slot + 1;   // slot of iteration itn
         double acc = 0.0;
-        // forward: stage tile t <-> J = In-KT+t, t = 0..KT-2 ; backward: stage tile t <-> J = In+t, t = 2..KT
+        // forward: stage tile tt (d = tt-KT) multiplies the block solved KT-tt iterations before itn;
+        // backward: stage tile tt (d = tt)  multiplies the block solved tt iterations before itn
 #pragma unroll
         for (int t = fw; t < KT - 1; t += 3) {
           const int tt = DIR > 0 ? t : t + 2;
-          const int64_t J = DIR > 0 ? In - KT + tt : In + tt;
-          // only blocks already solved in THIS sweep contribute (others are outside the window / zero)
-          const bool ok = (J >= vlo && J < vhi) && (DIR > 0 ? (J >= r0) : (J < r1));
-          if (ok) {
+          const int dist = DIR > 0 ? KT - tt : tt;
+          if (itn - dist >= 0) {
+            int ys = sn - dist;
+            if (ys < 0) ys += RING;
             const double2 tv = *reinterpret_cast<const double2*>(&S.stage[stn][tt][2 * lane]);
-            const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[yslot(J)][2 * tq]);
+            const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[ys][2 * tq]);
             acc = fma(tv.x, yp.x, acc);
             acc = fma(tv.y, yp.y, acc);
           }
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (tq == 0) S.farpart[(int)(itn & 1)][fw][g] = acc;
+        if (tq == 0) S.farpart[itn & 1][fw][g] = acc;
       }
     }
     __syncthreads();
     if (threadIdx.x == 32 && it + SW_NST < nrows) issue(it + SW_NST);
+    slot = slot + 1 == RING ? 0 : slot + 1;
   }
 }
 
 template <int KT>
-__global__ void __launch_bounds__(SW_THREADS) k_sweep(const SweepArgs a) {
+__global__ void __launch_bounds__(SW_THREADS, 3) k_sweep(const SweepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SweepSmem<KT>& S = *reinterpret_cast<SweepSmem<KT>*>(smem_raw);
   const int kp = KT * 8;
@@ -162,15 +170,15 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(const SweepArgs a) {
     fence_mbar_init();
   }
   __syncthreads();
-  int64_t itbase = 0;
+  unsigned itbase = 0;
   const int64_t n = a.n;
   if (a.mode == SWEEP_MAIN) {
     const int p = blockIdx.x;
     const int64_t t0 = a.pstart[p], t1 = a.pstart[p + 1];
     double* x = a.x;
     auto store_x = [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] = v; };
-    sweep_dir<KT, +1>(S, a, itbase, t0, t1, t0, t1, a.in, n, store_x);
-    sweep_dir<KT, -1>(S, a, itbase, t0, t1, t0, t1, x, n, store_x);
+    sweep_dir<KT, +1>(S, a, itbase, t0, t1, a.in, n, store_x);
+    sweep_dir<KT, -1>(S, a, itbase, t0, t1, x, n, store_x);
     return;
   }
   // ---- corrections: blockIdx = 2*p + side (0 top, 1 bottom); when the window covers more than half
@@ -208,8 +216,8 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(const SweepArgs a) {
     if (use_bot && I >= t1 - KT) v += rb[e - (t1 - KT) * 8];
     w[e] = v;
   }
-  sweep_dir<KT, +1>(S, a, itbase, flo, hi, lo, hi, w, npad, store_w);
-  sweep_dir<KT, -1>(S, a, itbase, lo, hi, lo, hi, w, npad, store_w);
+  sweep_dir<KT, +1>(S, a, itbase, flo, hi, w, npad, store_w);
+  sweep_dir<KT, -1>(S, a, itbase, lo, hi, w, npad, store_w);
   __syncthreads();
   for (int64_t e = lo * 8 + threadIdx.x; e < hi * 8; e += blockDim.x)
     if (e < n) x[e] -= w[e];

@@ -3,70 +3,88 @@
 //   W_i^(t)   = S_t(i)^-1 C_i        (S_t = leading Schur block left by the UL window of partition i)
 //   Rinv_i    = (I - W_{i+1}^(t) V_i^(b))^-1      (truncated SPIKE reduced block, explicit inverse)
 // [EXTERNAL algorithm: SPIKE (Polizzi/Sameh), SaP::GPU; the reference only names it, README.md:4.]
-// The dense solves use partial pivoting (matrix resident in shared memory); each thread then
-// carries one right-hand-side column through the row swaps and the two triangular sweeps.
+// The dense solves use partial pivoting with matrix AND right-hand sides resident in shared memory
+// (2 * kp*(kp+1) doubles: 175 KB at kp = 104, within the 227 KB a B200 CTA may opt into).
 #include "common.cuh"
 
 #define TIPS_THREADS 256
 
-// LU with partial pivoting of the kp x kp matrix M (shared memory, leading dimension ld).
-__device__ void dense_lu_smem(double* M, int ld, int kp, int* piv, double* red_val, int* red_idx) {
+// Solve M X = R for a kp x kp right-hand side, everything resident in shared memory:
+// Gaussian elimination with partial pivoting on the augmented [M | X], then right-looking back
+// substitution.  256 threads as a 16 x 16 grid over (rows, columns); no integer division in the loops.
+__device__ void dense_solve_smem(double* M, double* X, int ld, int kp, int ncols, int ldx, double* lcol, int* pivs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;
   for (int j = 0; j < kp; ++j) {
-    // pivot search over rows j..kp-1 of column j
-    double best = -1.0; int bi = j;
-    for (int r = j + tid; r < kp; r += blockDim.x) {
-      const double v = fabs(M[r * ld + j]);
-      if (v > best) { best = v; bi = r; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    if (lane == 0) { red_val[warp] = best; red_idx[warp] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      double b = red_val[0]; int p = red_idx[0];
-      for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-        if (red_val[w] > b || (red_val[w] == b && red_idx[w] < p)) { b = red_val[w]; p = red_idx[w]; }
-      piv[j] = p;
+    if (warp == 0) {  // pivot search in column j
+      double best = -1.0; int bi = j;
+      for (int r = j + lane; r < kp; r += 32) { const double v = fabs(M[r * ld + j]); if (v > best) { best = v; bi = r; } }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) pivs[0] = bi;
     }
     __syncthreads();
-    const int p = piv[j];
+    const int p = pivs[0];
     if (p != j) {
-      for (int c = tid; c < kp; c += blockDim.x) { const double t = M[j * ld + c]; M[j * ld + c] = M[p * ld + c]; M[p * ld + c] = t; }
+      for (int c = j + tid; c < kp; c += TIPS_THREADS) { const double t = M[j * ld + c]; M[j * ld + c] = M[p * ld + c]; M[p * ld + c] = t; }
+      for (int c = tid; c < ncols; c += TIPS_THREADS) { const double t = X[j * ldx + c]; X[j * ldx + c] = X[p * ldx + c]; X[p * ldx + c] = t; }
     }
     __syncthreads();
     const double d = M[j * ld + j];
     const double rd = (d != 0.0) ? 1.0 / d : 0.0;
-    for (int r = j + 1 + tid; r < kp; r += blockDim.x) M[r * ld + j] *= rd;
+    for (int r = j + 1 + tid; r < kp; r += TIPS_THREADS) lcol[r] = M[r * ld + j] * rd;
     __syncthreads();
-    const int m = kp - j - 1;
-    for (int e = tid; e < m * m; e += blockDim.x) {
-      const int r = j + 1 + e / m, c = j + 1 + e % m;
-      M[r * ld + c] = fma(-M[r * ld + j], M[j * ld + c], M[r * ld + c]);
+    {
+      // register-blocked rank-1 update: per row, load the thread's (<= 8) entries, FMA, store back
+      double pm[8], px[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int cm = j + 1 + tx + 16 * q, cx = tx + 16 * q;
+        pm[q] = (cm < kp) ? M[j * ld + cm] : 0.0;
+        px[q] = (cx < ncols) ? X[j * ldx + cx] : 0.0;
+      }
+      for (int r = j + 1 + ty; r < kp; r += 16) {
+        const double l = lcol[r];
+        double tm[8], tx8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int cm = j + 1 + tx + 16 * q, cx = tx + 16 * q;
+          tm[q] = (cm < kp) ? M[r * ld + cm] : 0.0;
+          tx8[q] = (cx < ncols) ? X[r * ldx + cx] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int cm = j + 1 + tx + 16 * q, cx = tx + 16 * q;
+          if (cm < kp) M[r * ld + cm] = fma(-l, pm[q], tm[q]);
+          if (cx < ncols) X[r * ldx + cx] = fma(-l, px[q], tx8[q]);
+        }
+      }
     }
     __syncthreads();
   }
-}
-// X (kp x kp, row-major in global memory, column t owned by thread t) <- M^-1 X
-__device__ void dense_solve_cols(const double* M, int ld, int kp, const int* piv, double* X) {
-  for (int t = threadIdx.x; t < kp; t += blockDim.x) {
-    for (int j = 0; j < kp; ++j) {
-      const int p = piv[j];
-      if (p != j) { const double v = X[(size_t)j * kp + t]; X[(size_t)j * kp + t] = X[(size_t)p * kp + t]; X[(size_t)p * kp + t] = v; }
+  for (int j = kp - 1; j >= 0; --j) {
+    const double d = M[j * ld + j];
+    const double rd = (d != 0.0) ? 1.0 / d : 0.0;
+    for (int c = tid; c < ncols; c += TIPS_THREADS) X[j * ldx + c] *= rd;
+    for (int r = tid; r < j; r += TIPS_THREADS) lcol[r] = M[r * ld + j];
+    __syncthreads();
+    {
+      double px[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const int cx = tx + 16 * q; px[q] = (cx < ncols) ? X[j * ldx + cx] : 0.0; }
+      for (int r = ty; r < j; r += 16) {
+        const double u = lcol[r];
+        double t8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int cx = tx + 16 * q; t8[q] = (cx < ncols) ? X[r * ldx + cx] : 0.0; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int cx = tx + 16 * q; if (cx < ncols) X[r * ldx + cx] = fma(-u, px[q], t8[q]); }
+      }
     }
-    for (int r = 1; r < kp; ++r) {
-      double s = X[(size_t)r * kp + t];
-      for (int j = 0; j < r; ++j) s = fma(-M[r * ld + j], X[(size_t)j * kp + t], s);
-      X[(size_t)r * kp + t] = s;
-    }
-    for (int r = kp - 1; r >= 0; --r) {
-      double s = X[(size_t)r * kp + t];
-      for (int j = r + 1; j < kp; ++j) s = fma(-M[r * ld + j], X[(size_t)j * kp + t], s);
-      X[(size_t)r * kp + t] = s / M[r * ld + r];
-    }
+    __syncthreads();
   }
 }
 
@@ -79,35 +97,49 @@ struct TipArgs {
   int which;            // 0: Vb (bottom, B block), 1: Wt (top, C block)
 };
 
+struct TipSmem { double* M; double* X; double* lcol; int* pivs; };
+// wide tips (kp > 112) do not fit M and all kp right-hand sides in 227 KB: they run two column passes
+__host__ __device__ __forceinline__ int tip_pass_cols(int kp) { return kp <= 112 ? kp : kp / 2; }
+__device__ __forceinline__ TipSmem tip_carve(double* sm, int kp) {
+  TipSmem t;
+  const int ld = kp + 1, ldx = tip_pass_cols(kp) + 1;
+  t.M = sm; t.X = sm + (size_t)kp * ld; t.lcol = t.X + (size_t)kp * ldx;
+  t.pivs = reinterpret_cast<int*>(t.lcol + kp);
+  return t;
+}
+
 // which==0: out[p] = Sb[p]^-1 B_p ; which==1: out[p] = St[p]^-1 C_p
 __global__ void __launch_bounds__(TIPS_THREADS) k_spike_tip(const TipArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int kp = a.L.kt * 8, ld = kp + 1, KT = a.L.kt;
-  double* M = sm;
-  int* piv = reinterpret_cast<int*>(M + (size_t)kp * ld);
-  double* red_val = reinterpret_cast<double*>(piv + kp + (kp & 1));
-  int* red_idx = reinterpret_cast<int*>(red_val + 8);
+  const TipSmem T = tip_carve(sm, kp);
   const int p = blockIdx.x + a.first_part;
   const double* S = a.S + (size_t)p * kp * kp;
-  double* X = a.out + (size_t)p * kp * kp;
-  for (int e = threadIdx.x; e < kp * kp; e += blockDim.x) M[(e / kp) * ld + (e % kp)] = S[e];
+  double* out = a.out + (size_t)p * kp * kp;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   // right-hand side block straight from the (never overwritten) coupling tiles of the band
   const int64_t tb = (a.which == 0) ? a.pstart[p + 1] : a.pstart[p];
-  for (int e = threadIdx.x; e < kp * kp; e += blockDim.x) {
-    const int r = e / kp, c = e % kp;
-    double v = 0.0;
-    if (a.which == 0) {  // B(r,c) = A(8(tb-KT)+r, 8tb+c), in band iff c/8 <= r/8
-      if ((c >> 3) <= (r >> 3)) v = a.band[a.L.elem_off((tb - KT) * 8 + r, tb * 8 + c)];
-    } else {             // C(r,c) = A(8tb+r, 8(tb-KT)+c), in band iff c/8 >= r/8
-      if ((c >> 3) >= (r >> 3)) v = a.band[a.L.elem_off(tb * 8 + r, (tb - KT) * 8 + c)];
+  const int nc = tip_pass_cols(kp), ldx = nc + 1;
+  for (int c0 = 0; c0 < kp; c0 += nc) {
+    for (int r = ty; r < kp; r += 16) {
+      for (int c = tx; c < kp; c += 16) T.M[r * ld + c] = S[(size_t)r * kp + c];
+      for (int cc = tx; cc < nc; cc += 16) {
+        const int c = c0 + cc;
+        double v = 0.0;
+        if (a.which == 0) {  // B(r,c) = A(8(tb-KT)+r, 8tb+c), in band iff c/8 <= r/8
+          if ((c >> 3) <= (r >> 3)) v = a.band[a.L.elem_off((tb - KT) * 8 + r, tb * 8 + c)];
+        } else {             // C(r,c) = A(8tb+r, 8(tb-KT)+c), in band iff c/8 >= r/8
+          if ((c >> 3) >= (r >> 3)) v = a.band[a.L.elem_off(tb * 8 + r, (tb - KT) * 8 + c)];
+        }
+        T.X[r * ldx + cc] = v;
+      }
     }
-    X[e] = v;
+    __syncthreads();
+    dense_solve_smem(T.M, T.X, ld, kp, nc, ldx, T.lcol, T.pivs);
+    for (int r = ty; r < kp; r += 16)
+      for (int cc = tx; cc < nc; cc += 16) out[(size_t)r * kp + c0 + cc] = T.X[r * ldx + cc];
+    __syncthreads();
   }
-  __syncthreads();
-  dense_lu_smem(M, ld, kp, piv, red_val, red_idx);
-  __threadfence_block();
-  __syncthreads();
-  dense_solve_cols(M, ld, kp, piv, X);
 }
 
 struct RedArgs {
@@ -119,29 +151,35 @@ struct RedArgs {
 __global__ void __launch_bounds__(TIPS_THREADS) k_reduced_factor(const RedArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int kp = a.kp, ld = kp + 1;
-  double* M = sm;
-  int* piv = reinterpret_cast<int*>(M + (size_t)kp * ld);
-  double* red_val = reinterpret_cast<double*>(piv + kp + (kp & 1));
-  int* red_idx = reinterpret_cast<int*>(red_val + 8);
+  const TipSmem T = tip_carve(sm, kp);
   const int i = blockIdx.x + a.first_iface;
   const double* V = a.Vb + (size_t)i * kp * kp;
   const double* W = (i == a.remote_iface) ? a.remoteWt : a.Wt + (size_t)(i + a.wt_part_offset) * kp * kp;
-  double* X = a.Rinv + (size_t)i * kp * kp;
-  for (int e = threadIdx.x; e < kp * kp; e += blockDim.x) {
-    const int r = e / kp, c = e % kp;
-    double s = (r == c) ? 1.0 : 0.0;
-    for (int q = 0; q < kp; ++q) s = fma(-W[(size_t)r * kp + q], V[(size_t)q * kp + c], s);
-    M[r * ld + c] = s;
-    X[e] = (r == c) ? 1.0 : 0.0;
+  double* out = a.Rinv + (size_t)i * kp * kp;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int nc = tip_pass_cols(kp), ldx = nc + 1;
+  for (int c0 = 0; c0 < kp; c0 += nc) {
+    // M = I - W V (W, V stream from L2; kp^3 flops per pass are negligible next to the elimination)
+    for (int r = ty; r < kp; r += 16) {
+      const double* wr = W + (size_t)r * kp;
+      for (int c = tx; c < kp; c += 16) {
+        double s0 = (r == c) ? 1.0 : 0.0, s1 = 0.0;
+        int q = 0;
+        for (; q + 1 < kp; q += 2) { s0 = fma(-wr[q], V[(size_t)q * kp + c], s0); s1 = fma(-wr[q + 1], V[(size_t)(q + 1) * kp + c], s1); }
+        for (; q < kp; ++q) s0 = fma(-wr[q], V[(size_t)q * kp + c], s0);
+        T.M[r * ld + c] = s0 + s1;
+      }
+      for (int cc = tx; cc < nc; cc += 16) T.X[r * ldx + cc] = (r == c0 + cc) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    dense_solve_smem(T.M, T.X, ld, kp, nc, ldx, T.lcol, T.pivs);
+    for (int r = ty; r < kp; r += 16)
+      for (int cc = tx; cc < nc; cc += 16) out[(size_t)r * kp + c0 + cc] = T.X[r * ldx + cc];
+    __syncthreads();
   }
-  __syncthreads();
-  dense_lu_smem(M, ld, kp, piv, red_val, red_idx);
-  __threadfence_block();
-  __syncthreads();
-  dense_solve_cols(M, ld, kp, piv, X);
 }
 
-static size_t tips_smem(int kp) { return sizeof(double) * ((size_t)kp * (kp + 1) + 8) + sizeof(int) * (size_t)(kp + 2 + 8) + 64; }
+static size_t tips_smem(int kp) { return sizeof(double) * ((size_t)kp * (kp + 1) + (size_t)kp * (tip_pass_cols(kp) + 1) + kp) + sizeof(int) * 4 + 64; }
 
 // Spike tips for this rank.  Interface i couples partition i (bottom) with partition i+1 (top);
 // interface P-1 is the boundary with the right-neighbour rank (its W^(t) arrives in c->remoteWt).

@@ -1,0 +1,28 @@
+/*
+ * spike_petsc.h -- host-side mirror of the reference's plugin surface, implemented on the C ABI of
+ * include/spike_b200.h.  Same names, argument meaning and error behaviour as the reference:
+ *   MatCreateSubMatrixBanded   /root/reference/src/matbanded.h:5, src/matbanded.c:22-107
+ *   PCCreate_Banded ("banded") /root/reference/src/matbanded.c:251-283 (+ ops :120-233, setters :305-343)
+ *   KSPCreate_Reorder ("reorder") /root/reference/src/kspreorder.c:197-223 (+ ops :11-28,113-185)
+ * Registration is by name exactly as src/testbed2.c:66-71 does it.
+ */
+#ifndef SPK_SPIKE_PETSC_H
+#define SPK_SPIKE_PETSC_H
+#ifdef HAVE_PETSC
+#include <petscksp.h>
+#else
+#include "petscshim.h"
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+PetscErrorCode MatCreateSubMatrixBanded(Mat A, PetscInt *kmax, PetscReal *frac, Mat *B);
+PetscErrorCode PCCreate_Banded(PC pc);
+PetscErrorCode PCBandedSetMaxHalfBandwith(PC pc, PetscInt kmax);   /* (sic) reference spelling, src/matbanded.c:305 */
+PetscErrorCode PCBandedSetNormFraction(PC pc, PetscReal frac);
+PetscErrorCode PCBandedGetInfo(PC pc, PetscInt *k, PetscReal *f, PetscInt *partitions, long long *boosted);
+PetscErrorCode KSPCreate_Reorder(KSP ksp);
+#ifdef __cplusplus
+}
+#endif
+#endif

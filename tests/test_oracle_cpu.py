@@ -270,3 +270,13 @@ def test_cabi_fails_loudly_without_gpu():
     import spike_petsc_b200 as spk
     with pytest.raises(spk.SpikeError, match="no CPU fallback|CUDA"):
         spk.Spike()
+
+
+def test_petsc_glue_library_exports_plugin_surface():
+    """libspike_petsc.so (C host glue) loads and exports the reference's plugin entry points."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spike_petsc_b200", "lib", "libspike_petsc.so")
+    assert os.path.exists(path), "libspike_petsc.so missing: run `make`"
+    L = ctypes.CDLL(path)
+    for name in ("PCCreate_Banded", "KSPCreate_Reorder", "MatCreateSubMatrixBanded", "PCBandedSetMaxHalfBandwith",
+                 "PCBandedSetNormFraction", "MatOrderingRegister", "KSPSolve", "PCApply"):
+        assert hasattr(L, name)
