@@ -45,7 +45,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -192,12 +192,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.1)
     step_ms, lu_ms, stage = [], [], None
     for it in range(args.warmup + args.steps):
         restore()
         barrier()
-        if it == args.warmup and rank == 0:
-            sampler.start()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
