@@ -166,7 +166,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     bounds = sp.shard_rows(N_ROWS, world)
     n_loc = bounds[rank + 1] - bounds[rank]
-    parts = args.partitions if args.partitions > 0 else max(2, 296 // world)
+    parts = args.partitions if args.partitions > 0 else 296   # 2 CTAs/SM per GPU (the LU kernel interleaves two partitions per SM)
     eng = sp.Spike(device=local, partitions=parts, tip_tiles=args.tip_tiles, mem=sp.MEM_DEVICE, rank=rank, nranks=world,
                    row_offset=bounds[rank], n_global=N_ROWS)
     eng.keep_original(True)                        # pristine copy: the factorisation is in place

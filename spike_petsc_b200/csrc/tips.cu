@@ -3,85 +3,119 @@
 //   W_i^(t)   = S_t(i)^-1 C_i        (S_t = leading Schur block left by the UL window of partition i)
 //   Rinv_i    = (I - W_{i+1}^(t) V_i^(b))^-1      (truncated SPIKE reduced block, explicit inverse)
 // [EXTERNAL algorithm: SPIKE (Polizzi/Sameh), SaP::GPU; the reference only names it, README.md:4.]
-// The dense solves use partial pivoting with matrix AND right-hand sides resident in shared memory
-// (2 * kp*(kp+1) doubles: 175 KB at kp = 104, within the 227 KB a B200 CTA may opt into).
+// The dense solves are blocked Gauss-Jordan eliminations with matrix AND right-hand sides resident in
+// shared memory (2 * kp*(kp+1) doubles: 175 KB at kp = 104, within the 227 KB a B200 CTA may opt into).
 #include "common.cuh"
 
 #define TIPS_THREADS 256
 
-// Solve M X = R for a kp x kp right-hand side, everything resident in shared memory:
-// Gaussian elimination with partial pivoting on the augmented [M | X], then right-looking back
-// substitution.  256 threads as a 16 x 16 grid over (rows, columns); no integer division in the loops.
-__device__ void dense_solve_smem(double* M, double* X, int ld, int kp, int ncols, int ldx, double* lcol, int* pivs) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int j = 0; j < kp; ++j) {
-    if (warp == 0) {  // pivot search in column j
-      double best = -1.0; int bi = j;
-      for (int r = j + lane; r < kp; r += 32) { const double v = fabs(M[r * ld + j]); if (v > best) { best = v; bi = r; } }
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (lane == 0) pivs[0] = bi;
-    }
-    __syncthreads();
-    const int p = pivs[0];
-    if (p != j) {
-      for (int c = j + tid; c < kp; c += TIPS_THREADS) { const double t = M[j * ld + c]; M[j * ld + c] = M[p * ld + c]; M[p * ld + c] = t; }
-      for (int c = tid; c < ncols; c += TIPS_THREADS) { const double t = X[j * ldx + c]; X[j * ldx + c] = X[p * ldx + c]; X[p * ldx + c] = t; }
-    }
-    __syncthreads();
-    const double d = M[j * ld + j];
-    const double rd = (d != 0.0) ? 1.0 / d : 0.0;
-    for (int r = j + 1 + tid; r < kp; r += TIPS_THREADS) lcol[r] = M[r * ld + j] * rd;
-    __syncthreads();
-    {
-      // register-blocked rank-1 update: per row, load the thread's (<= 8) entries, FMA, store back
-      double pm[8], px[8];
+// Solve M X = R (kp x kp matrix, ncols right-hand sides), everything resident in shared memory, by
+// BLOCKED Gauss-Jordan: kp/8 steps, each inverting an 8x8 pivot block (one warp, same in-register
+// Gauss-Jordan + boosting rule as the band LU), scaling the pivot block row and eliminating the block
+// column from all other rows with a register-blocked rank-8 update.  No pivoting across blocks --
+// these matrices are the Schur blocks the no-pivot band LU itself would go on to factor, and
+// I - W V of decaying spikes.  256 threads as a 16 x 16 grid over (rows, columns).
+__device__ __forceinline__ void gj8_inverse_warp(const double* D, int ld, double* Dv, double thr) {
+  // lanes 0..7 hold rows; result Dv[8][8] row-major
+  const int lane = threadIdx.x & 31, r8 = lane & 7;
+  double row[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int cm = j + 1 + tx + 16 * q, cx = tx + 16 * q;
-        pm[q] = (cm < kp) ? M[j * ld + cm] : 0.0;
-        px[q] = (cx < ncols) ? X[j * ldx + cx] : 0.0;
-      }
-      for (int r = j + 1 + ty; r < kp; r += 16) {
-        const double l = lcol[r];
-        double tm[8], tx8[8];
+  for (int c = 0; c < 8; ++c) row[c] = D[r8 * ld + c];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int cm = j + 1 + tx + 16 * q, cx = tx + 16 * q;
-          tm[q] = (cm < kp) ? M[r * ld + cm] : 0.0;
-          tx8[q] = (cx < ncols) ? X[r * ldx + cx] : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int cm = j + 1 + tx + 16 * q, cx = tx + 16 * q;
-          if (cm < kp) M[r * ld + cm] = fma(-l, pm[q], tm[q]);
-          if (cx < ncols) X[r * ldx + cx] = fma(-l, px[q], tx8[q]);
-        }
-      }
+  for (int k = 0; k < 8; ++k) {
+    const double piv = __shfl_sync(0xffffffffu, row[k], k);
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(piv));
+    const bool isp = (r8 == k);
+    const double q = isp ? 0.0 : row[k] * r0;
+    const double e = fma(-piv, r0, 1.0);
+    const double t = fma(e, e, e);
+    double f = fma(q, t, q);
+    double rc = fma(r0, t, r0);
+    if (fabs(piv) < thr) {
+      rc = (piv < 0.0) ? -1.0 / thr : 1.0 / thr;
+      f = isp ? 0.0 : row[k] * rc;
     }
-    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c == k) continue;
+      const double u = __shfl_sync(0xffffffffu, row[c], k);
+      row[c] = isp ? u * rc : fma(-f, u, row[c]);
+    }
+    row[k] = isp ? rc : -f;
   }
-  for (int j = kp - 1; j >= 0; --j) {
-    const double d = M[j * ld + j];
-    const double rd = (d != 0.0) ? 1.0 / d : 0.0;
-    for (int c = tid; c < ncols; c += TIPS_THREADS) X[j * ldx + c] *= rd;
-    for (int r = tid; r < j; r += TIPS_THREADS) lcol[r] = M[r * ld + j];
+  if (lane < 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) Dv[lane * 8 + c] = row[c];
+  }
+}
+
+__device__ void dense_solve_smem(double* M, double* X, int ld, int kp, int ncols, int ldx, double* Dv, double thr) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int c0 = 0; c0 < kp; c0 += 8) {
+    // (1) inverse of the pivot block
+    if (warp == 0) gj8_inverse_warp(M + c0 * ld + c0, ld, Dv, thr);
     __syncthreads();
-    {
-      double px[8];
+    // (2) pivot block row <- Dinv * (pivot block row), one thread per column (M columns right of the block, all X columns)
+    const int nm = kp - (c0 + 8);
+    for (int cc = tid; cc < nm + ncols; cc += TIPS_THREADS) {
+      double* col = (cc < nm) ? (M + c0 * ld + (c0 + 8 + cc)) : (X + c0 * ldx + (cc - nm));
+      const int st = (cc < nm) ? ld : ldx;
+      double v[8], o[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { const int cx = tx + 16 * q; px[q] = (cx < ncols) ? X[j * ldx + cx] : 0.0; }
-      for (int r = ty; r < j; r += 16) {
-        const double u = lcol[r];
-        double t8[8];
+      for (int k = 0; k < 8; ++k) v[k] = col[k * st];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { const int cx = tx + 16 * q; t8[q] = (cx < ncols) ? X[r * ldx + cx] : 0.0; }
+      for (int r = 0; r < 8; ++r) {
+        double acc = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { const int cx = tx + 16 * q; if (cx < ncols) X[r * ldx + cx] = fma(-u, px[q], t8[q]); }
+        for (int k = 0; k < 8; ++k) acc = fma(Dv[r * 8 + k], v[k], acc);
+        o[r] = acc;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) col[r * st] = o[r];
+    }
+    __syncthreads();
+    // (3) eliminate the block column from every other row: rank-8 update, thread = rows {ty+16m} x cols {tx+16q}
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      double* T = pass == 0 ? M : X;
+      const int tld = pass == 0 ? ld : ldx;
+      const int cbeg = pass == 0 ? c0 + 8 : 0;
+      const int cend = pass == 0 ? kp : ncols;
+      if (cbeg + tx >= cend) continue;
+      for (int rbase = ty; rbase < kp; rbase += 16 * 4) {      // 4 rows per register block
+        double acc[4][8];
+        int rr[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          rr[m] = rbase + 16 * m;
+          const bool live = rr[m] < kp && (rr[m] < c0 || rr[m] >= c0 + 8);
+          if (!live) rr[m] = -1;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int c = cbeg + tx + 16 * q;
+            acc[m][q] = (live && c < cend) ? T[rr[m] * tld + c] : 0.0;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          double pk[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { const int c = cbeg + tx + 16 * q; pk[q] = (c < cend) ? T[(c0 + k) * tld + c] : 0.0; }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const double l = (rr[m] >= 0) ? M[rr[m] * ld + c0 + k] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[m][q] = fma(-l, pk[q], acc[m][q]);
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (rr[m] < 0) continue;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { const int c = cbeg + tx + 16 * q; if (c < cend) T[rr[m] * tld + c] = acc[m][q]; }
+        }
       }
     }
     __syncthreads();
@@ -95,16 +129,16 @@ struct TipArgs {
   double* out;          // Vb or Wt, indexed by partition
   int first_part;       // partition handled by blockIdx 0
   int which;            // 0: Vb (bottom, B block), 1: Wt (top, C block)
+  double thr;           // pivot boosting threshold (same rule as the band LU)
 };
 
-struct TipSmem { double* M; double* X; double* lcol; int* pivs; };
+struct TipSmem { double* M; double* X; double* Dv; };
 // wide tips (kp > 112) do not fit M and all kp right-hand sides in 227 KB: they run two column passes
 __host__ __device__ __forceinline__ int tip_pass_cols(int kp) { return kp <= 112 ? kp : kp / 2; }
 __device__ __forceinline__ TipSmem tip_carve(double* sm, int kp) {
   TipSmem t;
   const int ld = kp + 1, ldx = tip_pass_cols(kp) + 1;
-  t.M = sm; t.X = sm + (size_t)kp * ld; t.lcol = t.X + (size_t)kp * ldx;
-  t.pivs = reinterpret_cast<int*>(t.lcol + kp);
+  t.M = sm; t.X = sm + (size_t)kp * ld; t.Dv = t.X + (size_t)kp * ldx;
   return t;
 }
 
@@ -135,7 +169,7 @@ __global__ void __launch_bounds__(TIPS_THREADS) k_spike_tip(const TipArgs a) {
       }
     }
     __syncthreads();
-    dense_solve_smem(T.M, T.X, ld, kp, nc, ldx, T.lcol, T.pivs);
+    dense_solve_smem(T.M, T.X, ld, kp, nc, ldx, T.Dv, a.thr);
     for (int r = ty; r < kp; r += 16)
       for (int cc = tx; cc < nc; cc += 16) out[(size_t)r * kp + c0 + cc] = T.X[r * ldx + cc];
     __syncthreads();
@@ -146,6 +180,7 @@ struct RedArgs {
   const double* Vb; const double* Wt; double* Rinv;
   int kp; int first_iface; int wt_part_offset;  // interface i uses Vb[i], Wt[i + wt_part_offset]
   const double* remoteWt; int remote_iface;     // interface == remote_iface uses remoteWt instead
+  double thr;
 };
 // Rinv[i] = (I - Wt[i+1] Vb[i])^-1
 __global__ void __launch_bounds__(TIPS_THREADS) k_reduced_factor(const RedArgs a) {
@@ -172,14 +207,14 @@ __global__ void __launch_bounds__(TIPS_THREADS) k_reduced_factor(const RedArgs a
       for (int cc = tx; cc < nc; cc += 16) T.X[r * ldx + cc] = (r == c0 + cc) ? 1.0 : 0.0;
     }
     __syncthreads();
-    dense_solve_smem(T.M, T.X, ld, kp, nc, ldx, T.lcol, T.pivs);
+    dense_solve_smem(T.M, T.X, ld, kp, nc, ldx, T.Dv, a.thr);
     for (int r = ty; r < kp; r += 16)
       for (int cc = tx; cc < nc; cc += 16) out[(size_t)r * kp + c0 + cc] = T.X[r * ldx + cc];
     __syncthreads();
   }
 }
 
-static size_t tips_smem(int kp) { return sizeof(double) * ((size_t)kp * (kp + 1) + (size_t)kp * (tip_pass_cols(kp) + 1) + kp) + sizeof(int) * 4 + 64; }
+static size_t tips_smem(int kp) { return sizeof(double) * ((size_t)kp * (kp + 1) + (size_t)kp * (tip_pass_cols(kp) + 1) + 64) + 64; }
 
 // Spike tips for this rank.  Interface i couples partition i (bottom) with partition i+1 (top);
 // interface P-1 is the boundary with the right-neighbour rank (its W^(t) arrives in c->remoteWt).
@@ -194,6 +229,7 @@ int spk_launch_tips(spk_ctx* c, int what, int unused) {
   const bool has_left = c->opts.rank > 0, has_right = c->opts.rank + 1 < c->opts.nranks;
   RedArgs r;
   r.Vb = c->Vb; r.Wt = c->Wt; r.Rinv = c->Red; r.kp = kp; r.wt_part_offset = 1; r.remoteWt = c->remoteWt;
+  r.thr = 1e-13;
   if (what == 1) {
     if (!has_right) return SPK_OK;
     r.first_iface = P - 1; r.remote_iface = P - 1;
@@ -202,7 +238,7 @@ int spk_launch_tips(spk_ctx* c, int what, int unused) {
     return SPK_OK;
   }
   TipArgs t;
-  t.band = c->band; t.L = c->L; t.pstart = c->d_pstart;
+  t.band = c->band; t.L = c->L; t.pstart = c->d_pstart; t.thr = c->opts.boost_rel * c->anorm_max;
   // V^(b) of partitions 0..P-2 (+ P-1 when a right neighbour exists)
   const int nvb = (P - 1) + (has_right ? 1 : 0);
   if (nvb > 0) {
