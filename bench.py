@@ -292,7 +292,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--partitions", type=int, default=0)
-    ap.add_argument("--tip-tiles", type=int, default=104)
+    ap.add_argument("--tip-tiles", type=int, default=78)   # 6 bandwidths: 1e-13 (profiles/r01_truncation_window.md)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -278,14 +278,41 @@ struct RedSolveArgs {
   const double* remoteWt; const double* remoteGtop; double* xbBoundary;
   int64_t n;
 };
-// y[r] = sum_c M[r*kp+c] v[c] for r = warp, warp+4, ... ; lanes stride the columns; shuffle reduction
-__device__ __forceinline__ double row_dot(const double* __restrict__ Mrow, const double* v, int kp, int lane) {
-  double s = 0.0;
-  for (int c = lane; c < kp; c += 32) s = fma(Mrow[c], v[c], s);
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  return s;
+// out[r] = base[r] - sum_c M[r*kp+c] v[c] (or just the product when base == nullptr).  8 warps; each warp
+// takes 4 rows per pass and issues all their loads before the shuffle reductions (memory-level
+// parallelism: the matrices stream from L2/HBM once per solve).
+__device__ __forceinline__ void block_matvec(const double* __restrict__ M, const double* v, const double* base, double* out,
+                                             int kp, bool negate) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r0 = warp * 4; r0 < kp; r0 += nw * 4) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    double mv[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int c = lane + 32 * q, r = r0 + m; mv[m][q] = (r < kp && c < kp) ? M[(size_t)r * kp + c] : 0.0; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lane + 32 * q;
+      const double vc = (c < kp) ? v[c] : 0.0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) s[m] = fma(mv[m][q], vc, s[m]);
+    }
+    for (int c = lane + 128; c < kp; c += 32) {   // kp > 128 never happens (kt <= 16), kept for safety
+#pragma unroll
+      for (int m = 0; m < 4; ++m) if (r0 + m < kp) s[m] = fma(M[(size_t)(r0 + m) * kp + c], v[c], s[m]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) s[m] += __shfl_xor_sync(0xffffffffu, s[m], o);
+    }
+    if (lane < 4 && r0 + lane < kp) {
+      const double sv = lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3];
+      out[r0 + lane] = negate ? (base ? base[r0 + lane] : 0.0) - sv : sv;
+    }
+  }
 }
-__global__ void __launch_bounds__(128) k_reduced_solve(const RedSolveArgs a) {
+__global__ void __launch_bounds__(256) k_reduced_solve(const RedSolveArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int kp = a.L.kt * 8, KT = a.L.kt;
   double* gb = sm; double* gt = gb + kp; double* tv = gt + kp; double* xt = tv + kp; double* xb = xt + kp;
@@ -301,14 +328,14 @@ __global__ void __launch_bounds__(128) k_reduced_solve(const RedSolveArgs a) {
   const double* W = bnd ? a.remoteWt : a.Wt + (size_t)(i + 1) * kp * kp;
   const double* V = a.Vb + (size_t)i * kp * kp;
   const double* R = a.Rinv + (size_t)i * kp * kp;
-  for (int r = warp; r < kp; r += 4) { const double s = row_dot(W + (size_t)r * kp, gb, kp, lane); if (lane == 0) tv[r] = gt[r] - s; }
+  block_matvec(W, gb, gt, tv, kp, true);      // t  = g_t - W g_b
   __syncthreads();
-  for (int r = warp; r < kp; r += 4) { const double s = row_dot(R + (size_t)r * kp, tv, kp, lane); if (lane == 0) xt[r] = s; }
+  block_matvec(R, tv, nullptr, xt, kp, false); // x_t = R t
   __syncthreads();
-  for (int r = warp; r < kp; r += 4) { const double s = row_dot(V + (size_t)r * kp, xt, kp, lane); if (lane == 0) xb[r] = gb[r] - s; }
+  block_matvec(V, xt, gb, xb, kp, true);      // x_b = g_b - V x_t
   __syncthreads();
   // r_top of partition i+1: C_{i+1} x_b ;  r_bot of partition i: B_i x_t
-  for (int r = warp; r < kp; r += 4) {
+  for (int r = warp; r < kp; r += 8) {
     double s1 = 0.0, s2 = 0.0;
     for (int c = lane; c < kp; c += 32) {
       if (!bnd && (c >> 3) >= (r >> 3)) s1 = fma(a.band[a.L.elem_off(tb * 8 + r, (tb - KT) * 8 + c)], xb[c], s1);
@@ -354,7 +381,7 @@ int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int if
     a.first_iface = iface_lo;
     a.boundary_iface = has_right ? c->P - 1 : -1;
     a.remoteWt = c->remoteWt; a.remoteGtop = c->remoteGtop; a.xbBoundary = c->xbBoundary; a.n = c->L.n;
-    k_reduced_solve<<<n, 128, sizeof(double) * 5 * c->kp, c->stream>>>(a);
+    k_reduced_solve<<<n, 256, sizeof(double) * 5 * c->kp, c->stream>>>(a);
     SPK_KERNEL_CHECK(c);
   }
   return SPK_OK;

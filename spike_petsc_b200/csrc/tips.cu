@@ -194,17 +194,49 @@ __global__ void __launch_bounds__(TIPS_THREADS) k_reduced_factor(const RedArgs a
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const int nc = tip_pass_cols(kp), ldx = nc + 1;
   for (int c0 = 0; c0 < kp; c0 += nc) {
-    // M = I - W V (W, V stream from L2; kp^3 flops per pass are negligible next to the elimination)
-    for (int r = ty; r < kp; r += 16) {
-      const double* wr = W + (size_t)r * kp;
-      for (int c = tx; c < kp; c += 16) {
-        double s0 = (r == c) ? 1.0 : 0.0, s1 = 0.0;
-        int q = 0;
-        for (; q + 1 < kp; q += 2) { s0 = fma(-wr[q], V[(size_t)q * kp + c], s0); s1 = fma(-wr[q + 1], V[(size_t)(q + 1) * kp + c], s1); }
-        for (; q < kp; ++q) s0 = fma(-wr[q], V[(size_t)q * kp + c], s0);
-        T.M[r * ld + c] = s0 + s1;
+    // M = I - W V: stage W in M's space and V in X's space (coalesced), accumulate each thread's
+    // (<= 8 x 8) output patch in registers, then overwrite.  (Wide tips: V does not fit next to M in one
+    // pass; they take the slower global-memory product below.)
+    if (nc == kp) {
+      for (int r = ty; r < kp; r += 16)
+        for (int c = tx; c < kp; c += 16) { T.M[r * ld + c] = W[(size_t)r * kp + c]; T.X[r * ldx + c] = V[(size_t)r * kp + c]; }
+      __syncthreads();
+      double acc[8][8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[m][q] = 0.0;
+      for (int k = 0; k < kp; ++k) {
+        double wv[8], vv[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) { const int r = ty + 16 * m; wv[m] = (r < kp) ? T.M[r * ld + k] : 0.0; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int c = tx + 16 * q; vv[q] = (c < kp) ? T.X[k * ldx + c] : 0.0; }
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[m][q] = fma(wv[m], vv[q], acc[m][q]);
       }
-      for (int cc = tx; cc < nc; cc += 16) T.X[r * ldx + cc] = (r == c0 + cc) ? 1.0 : 0.0;
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int r = ty + 16 * m, c = tx + 16 * q;
+          if (r < kp && c < kp) { T.M[r * ld + c] = ((r == c) ? 1.0 : 0.0) - acc[m][q]; T.X[r * ldx + c] = (r == c) ? 1.0 : 0.0; }
+        }
+    } else {
+      for (int r = ty; r < kp; r += 16) {
+        const double* wr = W + (size_t)r * kp;
+        for (int c = tx; c < kp; c += 16) {
+          double s0 = (r == c) ? 1.0 : 0.0, s1 = 0.0;
+          int q = 0;
+          for (; q + 1 < kp; q += 2) { s0 = fma(-wr[q], V[(size_t)q * kp + c], s0); s1 = fma(-wr[q + 1], V[(size_t)(q + 1) * kp + c], s1); }
+          for (; q < kp; ++q) s0 = fma(-wr[q], V[(size_t)q * kp + c], s0);
+          T.M[r * ld + c] = s0 + s1;
+        }
+        for (int cc = tx; cc < nc; cc += 16) T.X[r * ldx + cc] = (r == c0 + cc) ? 1.0 : 0.0;
+      }
     }
     __syncthreads();
     dense_solve_smem(T.M, T.X, ld, kp, nc, ldx, T.Dv, a.thr);

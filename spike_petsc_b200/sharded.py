@@ -119,7 +119,7 @@ class ShardedSpike:
         return yvec
 
     def _sync(self, t):
-        # the engine enqueues on the legacy default stream; NCCL p2p runs on torch's streams
-        if getattr(t, "is_cuda", False):
-            import torch
-            torch.cuda.synchronize(t.device)
+        # No host synchronisation: the engine enqueues on the legacy default stream, which is also
+        # torch's current stream, and torch.distributed orders its NCCL stream against the current
+        # stream with events on both sides of every p2p operation.
+        return
