@@ -328,7 +328,7 @@ def _gj_inverse_nopivot(D: np.ndarray, boost: float):
 
 def block_lu(a: np.ndarray, tile: int = 8, boost: float = 0.0):
     """Block LU of the band (rows layout) grouped by `tile` pivots, the factorisation the GPU kernel
-    stores: Lb(I,J) = A~(I,J) D_J^-1 below the diagonal, A~(I,J) above it, D_I^-1 in the diagonal tile.
+    stores: A~(I,J) below the diagonal, Ub(I,J) = D_I^-1 A~(I,J) above it, D_I^-1 in the diagonal tile.
     Same Schur complements / pivots / boosting as the scalar no-pivot LU (band_lu).  Returns the
     factors in a rows layout widened to the tile band (half-width kw = tile*ceil(k/tile) + tile-1)."""
     n, bw = a.shape
@@ -352,9 +352,9 @@ def block_lu(a: np.ndarray, tile: int = 8, boost: float = 0.0):
         m = r1 - r0
         Dinv, nb = _gj_inverse_nopivot(Wd[:m, :m], boost)
         nboost += nb
-        L = Wd[m:, :m] @ Dinv
-        Wd[m:, m:] -= L @ Wd[:m, m:]
-        Wd[m:, :m] = L
+        Ub = Dinv @ Wd[:m, m:]
+        Wd[m:, m:] -= Wd[m:, :m] @ Ub
+        Wd[:m, m:] = Ub
         Wd[:m, :m] = Dinv
         wide[ii[ok], dd[ok]] = Wd[ok]
     return wide, nboost, kw

@@ -3,25 +3,32 @@
 // Replaces PCSetUp(inner) = PETSc sparse LU of the AIJ band (/root/reference/src/matbanded.c:178).
 //
 // Factorisation computed (8x8 tiles, tile row/col indices I,J):   A = Lb * Ub  with
-//     Lb(I,I) = I,  Lb(I,J) = A~(I,J) * D_J^-1  (J < I),      Ub(I,J) = A~(I,J)  (J >= I),  D_I = A~(I,I)
-// where A~ is the Schur-updated matrix.  The band keeps Lb tiles below the diagonal, Ub tiles above
-// it and the EXPLICIT INVERSE D_I^-1 in the diagonal tile slot (that is what both this kernel and
-// the triangular sweeps need; a scalar LU of D_I never has to be applied).  Mathematically this is
-// the same elimination as the scalar no-pivot LU (same Schur complements, same pivots, same
+//     Lb(I,J) = A~(I,J)  (J <= I, D_I = A~(I,I)),      Ub(I,I) = I,  Ub(I,J) = D_I^-1 A~(I,J)  (J > I)
+// where A~ is the Schur-updated matrix.  The band keeps the A~ tiles below the diagonal, the scaled
+// Ub tiles above it and the EXPLICIT INVERSE D_I^-1 in the diagonal tile slot (that is what both this
+// kernel and the triangular sweeps need; a scalar LU of D_I never has to be applied).  Mathematically
+// this is the same elimination as the scalar no-pivot LU (same Schur complements, same pivots, same
 // boosting rule), grouped by 8 pivots.
 //
-// One CTA per SPIKE partition, KT+1 warps (KT = ceil(K/8)):
+// One CTA per SPIKE partition, KT+1 warps (KT = ceil(K/8)), no CTA-wide barrier in the main loop:
 //   * warp w < KT owns tile COLUMN J == w (mod KT) of the sliding KT x KT-tile trailing window; its
 //     KT tiles live in registers as DMMA m8n8k4 accumulator fragments (2 doubles/lane/tile), so the
-//     whole K x K window is register resident and every band entry is read and written once.
-//   * per 8-pivot step s: warp w forms Lb(s+1+w, s) = A~(s+1+w, s) D_s^-1 (2 DMMAs, fragments
-//     published to shared memory), then every warp updates its column: A~(I,J) -= Lb(I,s) A~(s,J)
-//     (2 DMMAs per tile, one 16 B LDS per lane for the A fragment; the B fragment is the raw pivot-row
-//     tile its owner published at the end of the previous step).
-//   * the service warp inverts the NEXT diagonal tile by in-register Gauss-Jordan (lane r = row r,
-//     pivot row broadcast by shuffles) as soon as its owner has updated it, i.e. concurrently with
-//     the current trailing update; it also keeps a 4-deep ring of cp.async.bulk (TMA) copies filled
-//     with the 2KT+1 tiles that enter the window two steps ahead.
+//     whole K x K window is register resident and every band entry is read and written once.  Tiles
+//     entering the window are loaded straight into the fragments (one coalesced 16 B load per lane
+//     and tile, issued a step ahead, L2-prefetched two steps ahead).
+//   * per 8-pivot step s a column warp scales ITS OWN pivot-row tile, Ub(s,J) = D_s^-1 A~(s,J)
+//     (2 DMMAs, operand layout changes by register shuffles), then updates its column
+//     A~(I,J) -= A~(I,s) Ub(s,J) (2 DMMAs per tile; the left operands come from the step PACKAGE: the
+//     pivot-column tiles -A~(s+1.., s) in A-fragment order, written to shared memory by the column's
+//     owner when it finished update(s-1)).  Packages live in a 4-deep ring guarded by full/empty
+//     mbarriers, so warps drift apart by up to a step instead of meeting at barriers.
+//   * the LOOKAHEAD warp (warp KT) runs the only truly sequential part of the factorisation, the chain
+//     D_t^-1 -> D_t+1 -> D_t+1^-1, privately and one step ahead of the column warps: as soon as the
+//     three tiles A~(t,t-1), A~(t-1,t), A~(t,t) are final after update(t-2) (they are the first tiles
+//     their owners update, and are handed over through shared memory at once) it recomputes
+//     D_t = A~(t,t) - A~(t,t-1) (D_t-1^-1 A~(t-1,t)) with the same DMMA sequence the column warps use
+//     (bit-identical), inverts it in registers and publishes D_t^-1 in A-fragment order (the second
+//     arrival on the package's `full` barrier).  The column warps never wait for a pivot-block inverse.
 //   * REV=true runs the same elimination on the row/column-reversed matrix (= bottom-up elimination
 //     of the partition's first tipT tile rows) without storing factors: it only yields the top
 //     Schur block S_t needed for the W^(t) spike tip.
@@ -29,40 +36,26 @@
 // boosted-pivot count.
 #include "common.cuh"
 
-#define LU_NSTAGE 4
+#define LU_R 4            // ring depth of the step packages
 #define LU_TRACE_STEPS 64
-// optional clock64 trace of CTA 0 (tools/lu_trace.py): [step-100][16]; 0..7 column warp 0, 8..15 service
-// LU_TRB: stamp after a barrier -- BAR.SYNC is deferred-blocking, so first consume a shared-memory word
-#define LU_TRB(slot, ptr) do { if (a.trace && blockIdx.x == 0 && s >= 100 && s < 100 + LU_TRACE_STEPS) { double d_ = *(volatile double*)(ptr); double e_; asm volatile("add.f64 %0, %1, %1;" : "=d"(e_) : "d"(d_)); if (lane == 0) a.trace[(s - 100) * 16 + (slot)] = clock64() + (e_ == 1.2345e300 ? 1 : 0); } } while (0)
-#define LU_TR(slot) do { if (a.trace && blockIdx.x == 0 && lane == 0 && s >= 100 && s < 100 + LU_TRACE_STEPS) a.trace[(s - 100) * 16 + (slot)] = clock64(); } while (0)
+// optional clock64 trace of CTA 0 (tools/lu_trace.py): [step-100][16]; 0..7 column warp 0, 8..15 lookahead warp
+// LU_TRV: stamp once a register value has been produced
+#define LU_TRV(slot, val) do { if (TRACE && blockIdx.x == 0 && s >= 100 && s < 100 + LU_TRACE_STEPS) { double e_; asm volatile("add.f64 %0, %1, %1;" : "=d"(e_) : "d"(val)); if (lane == 0) a.trace[(s - 100) * 16 + (slot)] = clock64() + (e_ == 1.2345e300 ? 1 : 0); } } while (0)
+#define LU_TR(slot) do { if (TRACE && blockIdx.x == 0 && lane == 0 && s >= 100 && s < 100 + LU_TRACE_STEPS) a.trace[(s - 100) * 16 + (slot)] = clock64(); } while (0)
 
-// Warp placement.  FP64 instructions of a warp queue IN ORDER behind every DMMA already issued on the
-// same SM sub-partition (hardware warp id % 4): with the column warps streaming 2*KT DMMAs each, an
-// FP64 op of the service warp would wait for the whole queue (>1000 cycles, tools/lu_trace.py) and
-// the Gauss-Jordan chain could never overlap the trailing update.  With LU_DEDICATED the service warp
-// is hardware warp 3 and every other warp id == 3 (mod 4) is parked, so sub-partition 3 carries no
-// DMMA stream.
-#ifndef LU_DEDICATED
-#define LU_DEDICATED 0
-#endif
-template <int KT>
-constexpr int lu_total_warps() {
-  if (!LU_DEDICATED) return KT + 1;
-  int W = 4;
-  while (W - W / 4 < KT) ++W;
-  return W;
-}
+// named barriers 4,5: "the three tiles of update(u) are in shared memory", u even/odd
+// (two producer warps arrive, the lookahead warp syncs)
+#define LU_BAR_TILES 4
 
 template <int KT>
 struct LuSmem {
-  double Lfrag[KT][64];      // -Lb(s+1+i, s), A-fragment order interleaved: [lane*2 + h] = -L[lane/4][4h + lane%4]
-  double Ufrag[2][KT][64];   //  A~(s, s+1+j), B-fragment order interleaved: [lane*2 + h] =  U[4h + lane%4][lane/4]
-  double Praw[KT][64];       // raw pivot-column tiles A~(s+1+i, s), row-major
-  double Dtile[64];          // diagonal tile handed to the service warp (row-major)
-  double Dinv[64];           // its inverse, row-major (goes to the band's diagonal slot)
-  double DinvF[64];          // its inverse in B-fragment order
-  double stage[LU_NSTAGE][2 * KT + 1][64];
-  unsigned long long full[LU_NSTAGE];
+  double PK[LU_R][KT][64];   // package of step s (slot s % LU_R): -A~(s+1+i, s), i = 0..KT-1, A-fragment order
+  double XA[LU_R][64];       // D_s^-1 in A-fragment order: [2*lane + h] = X[lane/4][4h + lane%4]
+  double tP[2][64];          // handed over during update(u), buffer u & 1, row-major: A~(u+2, u+1)
+  double tU[2][64];          //                                                        A~(u+1, u+2)
+  double tA[2][64];          //                                                        A~(u+2, u+2)
+  unsigned long long full[LU_R];    // 2 arrivals: the column's owner (package) + the lookahead warp (inverse)
+  unsigned long long empty[LU_R];   // KT arrivals: every column warp is done with the slot
 };
 
 struct LuArgs {
@@ -77,16 +70,62 @@ struct LuArgs {
   long long* trace;       // optional debug stamps; nullptr in production
 };
 
-template <int KT, bool REV>
-__global__ void __launch_bounds__(lu_total_warps<KT>() * 32, (LU_DEDICATED ? 1 : (KT >= 12 ? 2 : (KT >= 8 ? 3 : 4)))) k_band_lu(const LuArgs a) {
+// ---- register-level fragment conversions of an 8x8 tile (lane = 4g + tq) -------------------------
+// C fragment: lane holds M[g][2tq], M[g][2tq+1]   (= row-major doubles 2*lane, 2*lane+1)
+// A fragment: lane holds M[g][tq], M[g][4+tq]     (the two k-chunks of a left operand)
+// B fragment: lane holds M[tq][g], M[4+tq][g]     (the two k-chunks of a right operand)
+__device__ __forceinline__ void cfrag_to_afrag(const double2& c, int g, int tq, double& a0, double& a1) {
+  const int src0 = 4 * g + (tq >> 1), src1 = src0 + 2;
+  const double sx0 = __shfl_sync(0xffffffffu, c.x, src0), sy0 = __shfl_sync(0xffffffffu, c.y, src0);
+  const double sx1 = __shfl_sync(0xffffffffu, c.x, src1), sy1 = __shfl_sync(0xffffffffu, c.y, src1);
+  a0 = (tq & 1) ? sy0 : sx0;
+  a1 = (tq & 1) ? sy1 : sx1;
+}
+__device__ __forceinline__ void cfrag_to_bfrag(const double2& c, int g, int tq, double& b0, double& b1) {
+  const int src0 = 4 * tq + (g >> 1), src1 = src0 + 16;
+  const double sx0 = __shfl_sync(0xffffffffu, c.x, src0), sy0 = __shfl_sync(0xffffffffu, c.y, src0);
+  const double sx1 = __shfl_sync(0xffffffffu, c.x, src1), sy1 = __shfl_sync(0xffffffffu, c.y, src1);
+  b0 = (g & 1) ? sy0 : sx0;
+  b1 = (g & 1) ? sy1 : sx1;
+}
+
+// In-register Gauss-Jordan inverse of an 8x8 block held as a C fragment, no pivoting, diagonal boosting
+// (|pivot| < thr -> +-thr, SpikeGPU style).  Per pivot: 4 fp64 shuffles (pivot, this row's multiplier, the
+// two pivot-row entries of this lane's columns), reciprocal (hardware seed + one Halley step, relative
+// error e^3), 2 FMAs.  Branch-free.
+__device__ __forceinline__ double2 gj8_cfrag(double2 v, int g, int tq, double thr, double rthr, int& nboost) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double mine = (k & 1) ? v.y : v.x;
+    const double piv = __shfl_sync(0xffffffffu, mine, 4 * k + (k >> 1));    // D[k][k]
+    const double colk = __shfl_sync(0xffffffffu, mine, 4 * g + (k >> 1));   // D[g][k]
+    const double rx = __shfl_sync(0xffffffffu, v.x, 4 * k + tq);            // D[k][2tq]
+    const double ry = __shfl_sync(0xffffffffu, v.y, 4 * k + tq);            // D[k][2tq+1]
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(piv));
+    const double e = fma(-piv, r0, 1.0);
+    const double t = fma(e, e, e);
+    double rc = fma(r0, t, r0);                                             // 1/piv to fp64 accuracy
+    const bool boost = fabs(piv) < thr;                                     // warp-uniform, rare
+    rc = boost ? (piv < 0.0 ? -rthr : rthr) : rc;
+    nboost += boost ? 1 : 0;
+    const bool isp = (g == k);
+    const double f = isp ? 0.0 : colk * rc;   // multiplier of the pivot row for this lane's row
+    const double ck = isp ? rc : -f;          // column k of the inverse-in-progress
+    double nx = isp ? rx * rc : fma(-f, rx, v.x);
+    double ny = isp ? ry * rc : fma(-f, ry, v.y);
+    if (tq == (k >> 1)) { if (k & 1) ny = ck; else nx = ck; }
+    v.x = nx; v.y = ny;
+  }
+  return v;
+}
+
+template <int KT, bool REV, bool TRACE>
+__global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 : (KT >= 8 ? 3 : 4)))) k_band_lu(const LuArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LuSmem<KT>& S = *reinterpret_cast<LuSmem<KT>*>(smem_raw);
-  constexpr int NT = (KT + 1) * 32;
-  constexpr int NCOL = KT * 32;
-  const int hw = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool is_service = LU_DEDICATED ? (hw == 3) : (hw == KT);
-  const int warp = LU_DEDICATED ? hw - ((hw + 1) >> 2) : hw;  // column index of a column warp
-  const bool parked = LU_DEDICATED && !is_service && (((hw & 3) == 3) || warp >= KT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_lookahead = (warp == KT);
   const int g = lane >> 2, tq = lane & 3;
   const int part = blockIdx.x + (REV ? a.first_part : 0);
   const int64_t t0 = a.pstart[part];
@@ -107,240 +146,209 @@ __global__ void __launch_bounds__(lu_total_warps<KT>() * 32, (LU_DEDICATED ? 1 :
     const double2 v = *reinterpret_cast<const double2*>(tile + 62 - 2 * lane);
     return make_double2(v.y, v.x);
   };
-  auto stage_valid = [&](int s) -> bool { return s + KT < T; };
-  auto stage_wait = [&](int s) {
-    if (stage_valid(s)) mbar_wait(reinterpret_cast<uint64_t*>(&S.full[s % LU_NSTAGE]), (uint32_t)((s / LU_NSTAGE) & 1));
+  // tile (I,J) of the partition's diagonal block, zero outside it
+  auto ld_tile = [&](int I, int J) -> double2 {
+    return (I < T && J < T) ? ld_pair(tptr(I, J)) : make_double2(0.0, 0.0);
   };
-  // staged tile of the row chunk (s+KT, s+j), j = 0..KT   /   of the column (s+i, s+KT), i = 0..KT-1
-  auto stage_row = [&](int s, int j) -> const double* { return S.stage[s % LU_NSTAGE][REV ? KT - j : j]; };
-  auto stage_col = [&](int s, int i) -> const double* { return S.stage[s % LU_NSTAGE][KT + 1 + i]; };
+  auto full_bar = [&](int s) -> uint64_t* { return reinterpret_cast<uint64_t*>(&S.full[s % LU_R]); };
+  auto empty_bar = [&](int s) -> uint64_t* { return reinterpret_cast<uint64_t*>(&S.empty[s % LU_R]); };
+  // slot of step s is free again once every column warp has finished update(s - LU_R)
+  auto wait_slot_free = [&](int s) {
+    if (s >= LU_R) mbar_wait(empty_bar(s), (uint32_t)((s / LU_R - 1) & 1));
+  };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < LU_NSTAGE; ++i) mbar_init(reinterpret_cast<uint64_t*>(&S.full[i]), 1);
+    for (int i = 0; i < LU_R; ++i) {
+      mbar_init(reinterpret_cast<uint64_t*>(&S.full[i]), 2);
+      mbar_init(reinterpret_cast<uint64_t*>(&S.empty[i]), KT);
+    }
     fence_mbar_init();
   }
   __syncthreads();
-  if (parked) return;
 
-  if (is_service) {
-    // =========================== service warp ===========================================
-    // Staging of step s: the service warp arms the mbarrier (expect_tx for all 2KT+1 tiles) and copies
-    // the contiguous row chunk; the KT single-tile column copies are issued one per column warp
-    // (a per-lane UBLKCP would be serialised through the uniform datapath, ~80 cycles each).
-    auto issue_stage = [&](int s, bool with_columns) {
-      if (!stage_valid(s)) return;
-      uint64_t* bar = reinterpret_cast<uint64_t*>(&S.full[s % LU_NSTAGE]);
-      if (lane == 0) {
-        mbar_expect_tx(bar, (uint32_t)((2 * KT + 1) * 512));
-        // row chunk: logical tiles (s+KT, s .. s+KT) are contiguous in memory
-        const double* src = REV ? tptr(s + KT, s + KT) : tptr(s + KT, s);
-        bulk_g2s(S.stage[s % LU_NSTAGE][0], src, (KT + 1) * 512, bar);
-      }
-      if (with_columns) {
-        __syncwarp();
-        if (lane >= 1 && lane <= KT) bulk_g2s(S.stage[s % LU_NSTAGE][KT + lane], tptr(s + lane - 1, s + KT), 512, bar);
-      }
-    };
-    // prologue: steps 0 and 1 completely; steps 2,3 get their column tiles from the column warps
-    for (int s = 0; s < LU_NSTAGE && s < T; ++s) issue_stage(s, s < 2);
-    const int r8 = lane & 7;
-    int nboost_total = 0;
-
+  if (is_lookahead) {
+    // =========================== lookahead warp ===========================================
+    const double thr = a.boost_thr, rthr = 1.0 / a.boost_thr;
+    int nboost = 0;
+    double xa0 = 0.0, xa1 = 0.0;   // D_{s-1}^-1 as an A fragment
+    // step 1 works on raw tiles: fetch them before anybody can overwrite them with factors
+    double2 pc1 = ld_tile(1, 0), uc1 = ld_tile(0, 1), d1 = ld_tile(1, 1);
     for (int s = 0; s < T; ++s) {
       LU_TR(8);
-      named_bar_sync(2, 64);  // diagonal tile of step s is in S.Dtile
-      LU_TRB(9, &S.Dtile[0]);
-      // ---- in-place Gauss-Jordan inverse of the 8x8 pivot block, no pivoting, boosting.
-      //      Lane r (mod 8) holds row r.  Per pivot the dependent chain is
-      //      shuffle(pivot) -> reciprocal -> multiplier -> one FMA (the next pivot element).
-      double row[8];
-      {
-        const double2* dt = reinterpret_cast<const double2*>(&S.Dtile[r8 * 8]);
-        const double2 q0 = dt[0], q1 = dt[1], q2 = dt[2], q3 = dt[3];
-        row[0] = q0.x; row[1] = q0.y; row[2] = q1.x; row[3] = q1.y;
-        row[4] = q2.x; row[5] = q2.y; row[6] = q3.x; row[7] = q3.y;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const double piv = __shfl_sync(0xffffffffu, row[k], k);
-        // reciprocal: hardware seed r0 (~2^-20) + one Halley step, 1/piv = r0 (1 + e + e^2), e = 1 - piv r0,
-        // relative error e^3.  The multiplier is formed from q = a*r0 in parallel: f = q + q (e + e^2).
-        double r0;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(piv));
-        const bool isp = (r8 == k);
-        const double q = isp ? 0.0 : row[k] * r0;
-        const double e = fma(-piv, r0, 1.0);
-        const double t = fma(e, e, e);
-        double f = fma(q, t, q);             // multiplier of the pivot row for this lane's row (0 for the pivot row)
-        double rc = fma(r0, t, r0);          // 1/piv to fp64 accuracy
-        if (fabs(piv) < a.boost_thr) {       // warp-uniform, rare: boosted pivot (SpikeGPU-style)
-          rc = (piv < 0.0) ? -1.0 / a.boost_thr : 1.0 / a.boost_thr;
-          f = isp ? 0.0 : row[k] * rc;
-          ++nboost_total;
+      double2 d;
+      if (s == 0) {
+        d = ld_pair(tptr(0, 0));
+      } else {
+        double2 pc, uc;
+        if (s == 1) {
+          pc = pc1; uc = uc1; d = d1;
+        } else {        // final after update(s-2): handed over by their owners early in that update
+          named_bar_sync(LU_BAR_TILES + (s & 1), 96);
+          pc = *reinterpret_cast<const double2*>(&S.tP[s & 1][2 * lane]);
+          uc = *reinterpret_cast<const double2*>(&S.tU[s & 1][2 * lane]);
+          d = *reinterpret_cast<const double2*>(&S.tA[s & 1][2 * lane]);
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          if (c == k) continue;
-          const double u = __shfl_sync(0xffffffffu, row[c], k);   // unscaled pivot-row entry
-          row[c] = isp ? u * rc : fma(-f, u, row[c]);
-        }
-        row[k] = isp ? rc : -f;              // column k of the inverse-in-progress
+        LU_TRV(9, d.x);
+        // the column warps' sequence, bit for bit:  Ub = X U ;  D = A + (-P) Ub
+        double u0, u1, b0, b1, n0, n1;
+        double2 ut = make_double2(0.0, 0.0);
+        cfrag_to_bfrag(uc, g, tq, u0, u1);
+        dmma884(ut.x, ut.y, xa0, u0);
+        dmma884(ut.x, ut.y, xa1, u1);
+        cfrag_to_afrag(make_double2(-pc.x, -pc.y), g, tq, n0, n1);
+        cfrag_to_bfrag(ut, g, tq, b0, b1);
+        dmma884(d.x, d.y, n0, b0);
+        dmma884(d.x, d.y, n1, b1);
       }
-      if (lane < 8) {
-        double2* dl = reinterpret_cast<double2*>(&S.Dinv[lane * 8]);
-        dl[0] = make_double2(row[0], row[1]); dl[1] = make_double2(row[2], row[3]);
-        dl[2] = make_double2(row[4], row[5]); dl[3] = make_double2(row[6], row[7]);
-        // B-fragment order: element Dinv[k=r][c] -> [2*(4c + (r&3)) + (r>>2)]
-        double* f0 = &S.DinvF[2 * (lane & 3) + (lane >> 2)];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) f0[8 * c] = row[c];
-      }
+      LU_TRV(10, d.x);
+      const double2 x = gj8_cfrag(d, g, tq, thr, rthr, nboost);
+      LU_TRV(13, x.x);
+      cfrag_to_afrag(x, g, tq, xa0, xa1);
+      wait_slot_free(s);
+      *reinterpret_cast<double2*>(&S.XA[s % LU_R][2 * lane]) = make_double2(xa0, xa1);
+      LU_TRV(11, xa0);
       __syncwarp();
-      LU_TR(11);
-      named_bar_arrive(1, NT);  // D_s^-1 is published
+      if (lane == 0) mbar_arrive(full_bar(s));   // D_s^-1 is published
+      if (!REV) *reinterpret_cast<double2*>(tptr(s, s) + 2 * lane) = x;  // factor output
       LU_TR(12);
-      if (!REV) {  // factor output, off the critical path
-        double* dst = tptr(s, s);
-        *reinterpret_cast<double2*>(dst + 2 * lane) = *reinterpret_cast<const double2*>(&S.Dinv[2 * lane]);
-      }
-      if (s >= 2) issue_stage(s + 2, false);
     }
-    if (lane == 0 && nboost_total) atomicAdd((unsigned long long*)a.boost_count, (unsigned long long)nboost_total);
+    if (lane == 0 && nboost) atomicAdd((unsigned long long*)a.boost_count, (unsigned long long)nboost);
     return;
   }
 
   // =========================== column warps ================================================
+  // acc[i] = A~(s+i, c), i = 0..KT-1, of the warp's current column c = s + cj  (cj = jrel, or KT for
+  // the warp whose column retired at this step and that has taken over the entering column s+KT)
   double2 acc[KT];
-  // initial window: rows 0..KT-1 of column `warp`
 #pragma unroll
-  for (int i = 0; i < KT; ++i) {
-    acc[i] = (i < T && warp < T) ? ld_pair(tptr(i, warp)) : make_double2(0.0, 0.0);
-  }
-  int jrel = warp;  // (column owned) - s
+  for (int i = 0; i < KT; ++i) acc[i] = ld_tile(i, warp);
+  int jrel = warp;  // (column owned) - s, taken mod KT
 
-  // B-fragment publication of a C-fragment tile: element (k=g, c=2tq+e) -> [2*(4c + (g&3)) + (g>>2)]
-  auto publish_u = [&](double* uf, const double2& v) {
-    uf[2 * (8 * tq + (g & 3)) + (g >> 2)] = v.x;
-    uf[2 * (8 * tq + 4 + (g & 3)) + (g >> 2)] = v.y;
-  };
-  // Work done by a warp when step sn is about to start and its column is (sn + jr):
-  //   jr == 0 : its column is the pivot column -> publish the raw panel tiles (diag handed separately)
-  //             and the band-edge row tile A(sn, sn+KT) as the last U fragment
-  //   jr >= 1 : its slot-0 tile is the pivot-row tile A~(sn, sn+jr): it is final -> store it as the
-  //             Ub factor and publish it as a B fragment
-  auto publish_for_step = [&](int sn, int jr) {
-    double* ub = &S.Ufrag[sn & 1][0][0];
-    if (jr == 0) {
+  // the owner of pivot column sn (registers: acc[i] = A~(sn+i, sn)) publishes the step package
+  auto publish_package = [&](int sn) {
+    wait_slot_free(sn);
+    double* pk = &S.PK[sn % LU_R][0][0];
+    const int idx = 2 * (4 * g + 2 * (tq & 1)) + (tq >> 1);
+    const double2 e = ld_tile(sn + KT, sn);   // band-edge tile of the pivot column (never updated before)
 #pragma unroll
-      for (int i = 1; i < KT; ++i) *reinterpret_cast<double2*>(&S.Praw[i - 1][2 * lane]) = acc[i];
-      stage_wait(sn);
-      const bool v = stage_valid(sn);
-      const double2 e = v ? ld_pair(stage_row(sn, 0)) : make_double2(0.0, 0.0);
-      *reinterpret_cast<double2*>(&S.Praw[KT - 1][2 * lane]) = e;
-      const double2 ue = v ? ld_pair(stage_col(sn, 0)) : make_double2(0.0, 0.0);
-      publish_u(ub + (KT - 1) * 64, ue);
-    } else {
-      publish_u(ub + (jr - 1) * 64, acc[0]);
-      if (!REV && sn + jr < T) *reinterpret_cast<double2*>(tptr(sn, sn + jr) + 2 * lane) = acc[0];
+    for (int i = 1; i < KT; ++i) {
+      pk[(i - 1) * 64 + idx] = -acc[i].x;
+      pk[(i - 1) * 64 + idx + 2] = -acc[i].y;
+      if (!REV && sn + i < T) *reinterpret_cast<double2*>(tptr(sn + i, sn) + 2 * lane) = acc[i];
+    }
+    pk[(KT - 1) * 64 + idx] = -e.x;
+    pk[(KT - 1) * 64 + idx + 2] = -e.y;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full_bar(sn));
+  };
+  // fresh tiles of the entering column sn+KT (rows sn .. sn+KT-1) for the warp whose column just retired
+  auto load_entering_column = [&](int sn) {
+#pragma unroll
+    for (int i = 0; i < KT; ++i) acc[i] = ld_tile(sn + i, sn + KT);
+  };
+  // L2 prefetch of the tiles (I0+i, J), i = 0..cnt-1 (4 lines of 128 B each)
+  auto prefetch_col = [&](int I0, int J, int cnt) {
+    if (J >= T) return;
+    for (int l = lane; l < 4 * cnt; l += 32) {
+      const int i = l >> 2;
+      if (I0 + i < T) {
+        const double* p = tptr(I0 + i, J) + (l & 3) * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      }
     }
   };
-  auto hand_diag = [&](const double2& d) {
-    *reinterpret_cast<double2*>(&S.Dtile[2 * lane]) = d;
-    __syncwarp();
-    named_bar_arrive(2, 64);  // barrier arrival orders the shared-memory writes for the waiting service warp
-  };
 
-  if (jrel == 0) hand_diag(acc[0]);
-  publish_for_step(0, jrel);
-
+  // when step T-KT is about to start the registers hold the trailing Schur complement of the partition
+  // (rows/cols T-KT..T-1); called before the pivot column's owner recycles its registers
   const int kp = KT * 8;
-  for (int s = 0; s < T; ++s) {
-    if (s == T - KT) {
-      // registers hold the trailing Schur complement of the partition (rows/cols s..s+KT-1)
-      double* out = a.schur + (int64_t)part * kp * kp;
+  auto schur_out = [&]() {
+    double* out = a.schur + (int64_t)part * kp * kp;
 #pragma unroll
-      for (int i = 0; i < KT; ++i) {
-        const int r = 8 * i + g, cc = 8 * jrel + 2 * tq;
-        if (!REV) {
-          *reinterpret_cast<double2*>(out + (int64_t)r * kp + cc) = acc[i];
-        } else {
-          out[(int64_t)(kp - 1 - r) * kp + (kp - 1 - cc)] = acc[i].x;
-          out[(int64_t)(kp - 1 - r) * kp + (kp - 2 - cc)] = acc[i].y;
+    for (int i = 0; i < KT; ++i) {
+      const int r = 8 * i + g, cc = 8 * jrel + 2 * tq;
+      if (!REV) {
+        *reinterpret_cast<double2*>(out + (int64_t)r * kp + cc) = acc[i];
+      } else {
+        out[(int64_t)(kp - 1 - r) * kp + (kp - 1 - cc)] = acc[i].x;
+        out[(int64_t)(kp - 1 - r) * kp + (kp - 2 - cc)] = acc[i].y;
+      }
+    }
+  };
+  if (T == KT) schur_out();
+  if (jrel == 0) { publish_package(0); load_entering_column(0); }
+
+  for (int s = 0; s < T; ++s) {
+    const int cj = (jrel == 0) ? KT : jrel;
+    // ---- independent of the package: operand layout of the pivot-row tile, the entering row tile
+    double u0, u1;
+    cfrag_to_bfrag(acc[0], g, tq, u0, u1);
+    double2 f = ld_tile(s + KT, s + cj);
+    // two steps ahead: this column's entering row tile; the entering column of step s+2
+    if (cj >= 2) prefetch_col(s + 2 + KT, s + cj, 1);
+    if (jrel == (KT > 2 ? 2 : KT - 1)) prefetch_col(s + 2, s + 2 + KT, KT + 1);
+    if (warp == 0) LU_TR(0);
+    mbar_wait(full_bar(s), (uint32_t)((s / LU_R) & 1));   // package(s) and D_s^-1 are in shared memory
+    if (warp == 0) LU_TR(1);
+    // ---------------- Ub(s, c) = D_s^-1 A~(s, c) ----------------
+    double b0, b1;
+    {
+      const double2 xa = *reinterpret_cast<const double2*>(&S.XA[s % LU_R][2 * lane]);
+      double2 ut = make_double2(0.0, 0.0);
+      dmma884(ut.x, ut.y, xa.x, u0);
+      dmma884(ut.x, ut.y, xa.y, u1);
+      if (!REV && s + cj < T) *reinterpret_cast<double2*>(tptr(s, s + cj) + 2 * lane) = ut;
+      cfrag_to_bfrag(ut, g, tq, b0, b1);
+    }
+    if (warp == 0) LU_TR(2);
+    // ---------------- trailing update of the column + window slide ----------------
+    const double* pk = &S.PK[s % LU_R][0][0];
+    const bool give = (s + 2 < T);
+#pragma unroll
+    for (int i = 1; i < KT; ++i) {
+      const double2 af = *reinterpret_cast<const double2*>(pk + (i - 1) * 64 + 2 * lane);
+      dmma884(acc[i].x, acc[i].y, af.x, b0);
+      dmma884(acc[i].x, acc[i].y, af.y, b1);
+      if (KT > 2 && i == 2 && give) {   // hand the lookahead warp its tiles the moment they are final
+        if (jrel == 1) {
+          *reinterpret_cast<double2*>(&S.tP[s & 1][2 * lane]) = acc[2];
+          named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
+        } else if (jrel == 2) {
+          *reinterpret_cast<double2*>(&S.tU[s & 1][2 * lane]) = acc[1];
+          *reinterpret_cast<double2*>(&S.tA[s & 1][2 * lane]) = acc[2];
+          named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
         }
       }
     }
-    if (warp == 0) LU_TR(0);
-    named_bar_sync(1, NT);  // S1: D_s^-1 ready, Praw/Ufrag(s) published, update(s-1) complete
-    if (warp == 0) LU_TRB(1, &S.DinvF[0]);
-    // ---------------- phase A: Lb(s+1+warp, s) = A~(s+1+warp, s) * D_s^-1 ----------------
     {
-      const double* pr = S.Praw[warp];
-      const double a0 = pr[g * 8 + tq], a1 = pr[g * 8 + 4 + tq];
-      const double2 ub = *reinterpret_cast<const double2*>(&S.DinvF[2 * lane]);
-      double x0 = 0.0, x1 = 0.0;
-      dmma884(x0, x1, a0, ub.x);
-      dmma884(x0, x1, a1, ub.y);
-      if (!REV && s + 1 + warp < T) *reinterpret_cast<double2*>(tptr(s + 1 + warp, s) + 2 * lane) = make_double2(x0, x1);
-      const int idx = 2 * (4 * g + 2 * (tq & 1)) + (tq >> 1);
-      S.Lfrag[warp][idx] = -x0;
-      S.Lfrag[warp][idx + 2] = -x1;
+      const double2 af = *reinterpret_cast<const double2*>(pk + (KT - 1) * 64 + 2 * lane);
+      dmma884(f.x, f.y, af.x, b0);
+      dmma884(f.x, f.y, af.y, b1);
     }
-    if (warp == 0) LU_TR(2);
-    named_bar_sync(3, NCOL);  // S2: Lfrag(s) complete
-    if (warp == 0) LU_TRB(3, &S.Lfrag[0][0]);
-    // column tile `warp` of step s+2 (its ring slot was last read in update(s-2), which is complete)
-    if (lane == 0 && stage_valid(s + 2)) {
-      const int sn = s + 2;
-      bulk_g2s(S.stage[sn % LU_NSTAGE][KT + 1 + warp], tptr(sn + warp, sn + KT), 512,
-               reinterpret_cast<uint64_t*>(&S.full[sn % LU_NSTAGE]));
+    if (KT == 2 && give) {
+      if (jrel == 1) {
+        *reinterpret_cast<double2*>(&S.tP[s & 1][2 * lane]) = f;
+        named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
+      } else {
+        *reinterpret_cast<double2*>(&S.tU[s & 1][2 * lane]) = acc[1];
+        *reinterpret_cast<double2*>(&S.tA[s & 1][2 * lane]) = f;
+        named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
+      }
     }
-    // ---------------- phase B: trailing update + window slide ----------------
-    const double* ufs = &S.Ufrag[s & 1][0][0];
-    if (jrel != 0) {
-      const double2 bf = *reinterpret_cast<const double2*>(ufs + (jrel - 1) * 64 + 2 * lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar(s));   // this warp no longer reads the slot of step s
 #pragma unroll
-      for (int i = 1; i < KT; ++i) {
-        const double2 af = *reinterpret_cast<const double2*>(&S.Lfrag[i - 1][2 * lane]);
-        dmma884(acc[i].x, acc[i].y, af.x, bf.x);
-        dmma884(acc[i].x, acc[i].y, af.y, bf.y);
-        if (i == 1 && jrel == 1 && s + 1 < T) hand_diag(acc[1]);  // next diagonal tile: to the service warp now
-      }
-      stage_wait(s);
-      double2 f = stage_valid(s) ? ld_pair(stage_row(s, jrel)) : make_double2(0.0, 0.0);
-      {
-        const double2 af = *reinterpret_cast<const double2*>(&S.Lfrag[KT - 1][2 * lane]);
-        dmma884(f.x, f.y, af.x, bf.x);
-        dmma884(f.x, f.y, af.y, bf.y);
-      }
-#pragma unroll
-      for (int i = 1; i < KT; ++i) acc[i - 1] = acc[i];
-      acc[KT - 1] = f;
-      --jrel;
-    } else {
-      // pivot warp: its column is retired; take over the entering column s+KT (all tiles fresh)
-      const double2 bf = *reinterpret_cast<const double2*>(ufs + (KT - 1) * 64 + 2 * lane);
-      stage_wait(s);
-      const bool sv = stage_valid(s);
-#pragma unroll
-      for (int i = 0; i < KT; ++i) {
-        double2 f;
-        if (i < KT - 1) f = sv ? ld_pair(stage_col(s, i + 1)) : make_double2(0.0, 0.0);
-        else            f = sv ? ld_pair(stage_row(s, KT)) : make_double2(0.0, 0.0);
-        const double2 af = *reinterpret_cast<const double2*>(&S.Lfrag[i][2 * lane]);
-        dmma884(f.x, f.y, af.x, bf.x);
-        dmma884(f.x, f.y, af.y, bf.y);
-        acc[i] = f;
-      }
-      jrel = KT - 1;
-    }
+    for (int i = 1; i < KT; ++i) acc[i - 1] = acc[i];
+    acc[KT - 1] = f;
+    jrel = (jrel == 0) ? KT - 1 : jrel - 1;
     if (warp == 0) LU_TR(4);
-    if (s + 1 < T) publish_for_step(s + 1, jrel);
+    if (s + 1 == T - KT) schur_out();
+    if (jrel == 0 && s + 1 < T) { publish_package(s + 1); load_entering_column(s + 1); }
     if (warp == 0) LU_TR(5);
   }
 }
 
 // --------------------------------------------------------------------------------------------
-template <int KT, bool REV>
+template <int KT, bool REV, bool TRACE>
 static int launch_lu_kt(spk_ctx* c, int grid, int first_part) {
   LuArgs a;
   a.band = c->band; a.schur = REV ? c->St : c->Sb; a.pstart = c->d_pstart;
@@ -348,16 +356,17 @@ static int launch_lu_kt(spk_ctx* c, int grid, int first_part) {
   a.boost_thr = c->opts.boost_rel * c->anorm_max;
   a.trace = (long long*)c->lu_trace;
   const size_t smem = sizeof(LuSmem<KT>);
-  SPK_CUDA(c, cudaFuncSetAttribute(k_band_lu<KT, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_band_lu<KT, REV><<<grid, lu_total_warps<KT>() * 32, smem, c->stream>>>(a);
+  SPK_CUDA(c, cudaFuncSetAttribute(k_band_lu<KT, REV, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_band_lu<KT, REV, TRACE><<<grid, (KT + 1) * 32, smem, c->stream>>>(a);
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }
 
 template <bool REV>
 static int launch_lu(spk_ctx* c, int grid, int first_part) {
+  if (!REV && c->lu_trace && c->L.kt == 13) return launch_lu_kt<13, false, true>(c, grid, first_part);  // tools/lu_trace.py
   switch (c->L.kt) {
-#define CASE(K_) case K_: return launch_lu_kt<K_, REV>(c, grid, first_part);
+#define CASE(K_) case K_: return launch_lu_kt<K_, REV, false>(c, grid, first_part);
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
 #undef CASE
     default:

@@ -10,7 +10,7 @@
 //                       tipT = whole partition reproduces the classical second full sweep.
 //
 // Sweep kernel anatomy (one CTA per partition / correction job, 4 warps):
-//   warp 0 ("near")  carries the sequential recurrence  y_I = Linv_I (c_I - L(I,I-1) y_{I-1})
+//   warp 0 ("near")  carries the sequential recurrence  y_I = D_I^-1 (c_I - Lb(I,I-1) y_{I-1})
 //                    with 8x8 tiles spread over the lanes and warp-shuffle reductions;
 //   warps 1-3 ("far") accumulate the part of the dot products that only needs y_{<=I-2} for the
 //                    NEXT tile row (warp-shuffle reductions over the 4 lanes of a row);
@@ -38,16 +38,16 @@ struct SweepArgs {
 
 template <int KT>
 struct SweepSmem {
-  // forward : [0..KT-1] = Lb tiles d=-KT..-1,                      [KT+1] = right-hand-side block (8 doubles)
-  // backward: [0] = D^-1 (diagonal slot), [1..KT] = Ub tiles d=1..KT, [KT+1] = right-hand-side block
+  // forward : [0..KT-1] = Lb tiles d=-KT..-1, [KT] = D^-1 (diagonal slot), [KT+1] = right-hand-side block (8 doubles)
+  // backward: [0..KT-1] = Ub tiles d=1..KT (unit block diagonal),         [KT+1] = right-hand-side block
   double stage[SW_NST][KT + 2][64];
   double ybuf[KT + 1][8];            // ring of the last KT+1 solved tile-row blocks
   double farpart[2][3][8];
   unsigned long long full[SW_NST];
 };
 
-// One directional sweep over tile rows.  DIR=+1: forward with Lb (rows r0..r1-1 ascending, unit block
-// diagonal), DIR=-1: backward with Ub and the explicit D^-1 (rows r1-1..r0 descending).
+// One directional sweep over tile rows.  DIR=+1: forward with Lb and the explicit D^-1 (rows r0..r1-1
+// ascending), DIR=-1: backward with Ub, unit block diagonal (rows r1-1..r0 descending).
 // Only blocks solved earlier in the same sweep contribute (the sweep range is the solve window).
 // vin[row] is the right-hand side (streamed through the
 // bulk-copy ring together with the factor tiles), sink(I, g, value) consumes the result.
@@ -69,9 +69,9 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
   for (int e = threadIdx.x; e < RING * 8; e += blockDim.x) (&S.ybuf[0][0])[e] = 0.0;
   for (int e = threadIdx.x; e < 2 * 3 * 8; e += blockDim.x) (&S.farpart[0][0][0])[e] = 0.0;
   __syncthreads();
-  constexpr int NTILE = DIR > 0 ? KT : KT + 1;
+  constexpr int NTILE = DIR > 0 ? KT + 1 : KT;
   const int64_t rstart = DIR > 0 ? r0 : r1 - 1;                 // tile row of iteration 0
-  const double* src0 = a.band + (rstart * a.tpr + (DIR > 0 ? 0 : KT)) * SPK_TILE_ELEMS;  // d=-KT..-1  or  d=0..KT
+  const double* src0 = a.band + (rstart * a.tpr + (DIR > 0 ? 0 : KT + 1)) * SPK_TILE_ELEMS;  // d=-KT..0  or  d=1..KT
   const int64_t src_step = (int64_t)DIR * a.tpr * SPK_TILE_ELEMS;
   const double* rhs0 = vin + rstart * 8;
   const int64_t rows_bulk = (nvalid / 8);                       // tile rows whose 8 entries all exist in vin
@@ -103,20 +103,20 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
       if (rhs_bulk_ok(it)) rhs = S.stage[st][KT + 1][g];
       else rhs = (I * 8 + g < nvalid) ? vin[I * 8 + g] : 0.0;
       const double cg = rhs - (S.farpart[par][0][g] + S.farpart[par][1][g] + S.farpart[par][2][g]);
-      // adjacent tile: forward Lb(I,I-1) is stage tile KT-1 (d=-1); backward Ub(I,I+1) is stage tile 1 (d=+1)
+      // adjacent tile: forward Lb(I,I-1) is stage tile KT-1 (d=-1); backward Ub(I,I+1) is stage tile 0 (d=+1)
       double part = 0.0;
       if (it > 0) {
         const int ps = slot == 0 ? RING - 1 : slot - 1;
-        const double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 1][2 * lane]);
+        const double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 0][2 * lane]);
         const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[ps][2 * tq]);
         part = fma(t.x, yp.x, t.y * yp.y);
       }
       part += __shfl_xor_sync(0xffffffffu, part, 1);
       part += __shfl_xor_sync(0xffffffffu, part, 2);
       double yv = cg - part;  // replicated in the 4 lanes of row g
-      if (DIR < 0) {
-        // x_g = sum_c Dinv[g][c] t_c
-        const double2 dv = *reinterpret_cast<const double2*>(&S.stage[st][0][2 * lane]);
+      if (DIR > 0) {
+        // y_g = sum_c Dinv[g][c] t_c
+        const double2 dv = *reinterpret_cast<const double2*>(&S.stage[st][KT][2 * lane]);
         const double t0 = __shfl_sync(0xffffffffu, yv, 8 * tq);
         const double t1 = __shfl_sync(0xffffffffu, yv, 8 * tq + 4);
         yv = fma(dv.x, t0, dv.y * t1);
@@ -135,11 +135,11 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
         const int sn = slot + 1 == RING ? 0 : slot + 1;   // slot of iteration itn
         double acc = 0.0;
         // forward: stage tile tt (d = tt-KT) multiplies the block solved KT-tt iterations before itn;
-        // backward: stage tile tt (d = tt)  multiplies the block solved tt iterations before itn
+        // backward: stage tile tt (d = tt+1) multiplies the block solved tt+1 iterations before itn
 #pragma unroll
         for (int t = fw; t < KT - 1; t += 3) {
-          const int tt = DIR > 0 ? t : t + 2;
-          const int dist = DIR > 0 ? KT - tt : tt;
+          const int tt = DIR > 0 ? t : t + 1;
+          const int dist = DIR > 0 ? KT - tt : tt + 1;
           if (itn - dist >= 0) {
             int ys = sn - dist;
             if (ys < 0) ys += RING;

@@ -69,7 +69,7 @@ def test_matmult_vs_oracle(spk, oracle, n, k):
 # ------------------------------------------------------------------ factor: block-LU entries vs oracle
 @pytest.mark.parametrize("n,k", [(512, 10), (4096, 20), (3000, 50), (4096, 100), (2500, 128), (1001, 64)])
 def test_lu_factors_match_oracle_single_partition(spk, oracle, n, k):
-    """The kernel stores the block LU grouped by 8 pivots (Lb = A~ D^-1 below, A~ above, D^-1 on the
+    """The kernel stores the block LU grouped by 8 pivots (A~ below, Ub = D^-1 A~ above, D^-1 on the
     diagonal tiles); oracle.block_lu restates exactly that on the CPU, with the same Schur
     complements, pivots and boosting rule as the scalar no-pivot LU (oracle.band_lu)."""
     a = oracle.gen_band(n, k, seed=n + k)
