@@ -17,11 +17,17 @@
 //     entering the window are loaded straight into the fragments (one coalesced 16 B load per lane
 //     and tile, issued a step ahead, L2-prefetched two steps ahead).
 //   * per 8-pivot step s a column warp scales ITS OWN pivot-row tile, Ub(s,J) = D_s^-1 A~(s,J)
-//     (2 DMMAs, operand layout changes by register shuffles), then updates its column
-//     A~(I,J) -= A~(I,s) Ub(s,J) (2 DMMAs per tile; the left operands come from the step PACKAGE: the
-//     pivot-column tiles -A~(s+1.., s) in A-fragment order, written to shared memory by the column's
-//     owner when it finished update(s-1)).  Packages live in a 4-deep ring guarded by full/empty
-//     mbarriers, so warps drift apart by up to a step instead of meeting at barriers.
+//     (2 DMMAs), then updates its column A~(I,J) -= A~(I,s) Ub(s,J) (2 DMMAs per tile; the left
+//     operands come from the step PACKAGE: the pivot-column tiles -A~(s+1.., s), written to shared
+//     memory by the column's owner when it finished update(s-1)).  Packages live in a 4-deep ring
+//     guarded by full/empty mbarriers, so warps drift apart by up to a step instead of meeting at
+//     barriers.
+//   * operand layouts: a DMMA contracts over k, so the SAME permutation of k may be applied to both
+//     operands.  With k = 2*(lane%4)+h for k-chunk h, the left operand of M1*M2 is the accumulator
+//     ("C") fragment of M1 itself and the right operand is the C fragment of M2^T.  Every product in
+//     this kernel is arranged so that its operands are C fragments somebody already holds (tiles are
+//     row-major = C-fragment order in memory, shared memory and registers); the only layout change
+//     left is one register transposition of the pivot-row tile per column warp and step.
 //   * the LOOKAHEAD warp (warp KT) runs the only truly sequential part of the factorisation, the chain
 //     D_t^-1 -> D_t+1 -> D_t+1^-1, privately and one step ahead of the column warps: as soon as the
 //     three tiles A~(t,t-1), A~(t-1,t), A~(t,t) are final after update(t-2) (they are the first tiles
@@ -49,11 +55,13 @@
 
 template <int KT>
 struct LuSmem {
-  double PK[LU_R][KT][64];   // package of step s (slot s % LU_R): -A~(s+1+i, s), i = 0..KT-1, A-fragment order
-  double XA[LU_R][64];       // D_s^-1 in A-fragment order: [2*lane + h] = X[lane/4][4h + lane%4]
+  double PK[LU_R][KT][64];   // package of step s (slot s % LU_R): -A~(s+1+i, s), i = 0..KT-1, row-major
+  double XC[LU_R][64];       // D_s^-1, row-major
+  double FT[KT][64];         // per column warp: landing slot of its entering row tile (cp.async)
   double tP[2][64];          // handed over during update(u), buffer u & 1, row-major: A~(u+2, u+1)
-  double tU[2][64];          //                                                        A~(u+1, u+2)
+  double tUt[2][64];         //                                                        A~(u+1, u+2)^T
   double tA[2][64];          //                                                        A~(u+2, u+2)
+  double tAt[2][64];         //                                                        A~(u+2, u+2)^T
   unsigned long long full[LU_R];    // 2 arrivals: the column's owner (package) + the lookahead warp (inverse)
   unsigned long long empty[LU_R];   // KT arrivals: every column warp is done with the slot
 };
@@ -70,23 +78,34 @@ struct LuArgs {
   long long* trace;       // optional debug stamps; nullptr in production
 };
 
-// ---- register-level fragment conversions of an 8x8 tile (lane = 4g + tq) -------------------------
-// C fragment: lane holds M[g][2tq], M[g][2tq+1]   (= row-major doubles 2*lane, 2*lane+1)
-// A fragment: lane holds M[g][tq], M[g][4+tq]     (the two k-chunks of a left operand)
-// B fragment: lane holds M[tq][g], M[4+tq][g]     (the two k-chunks of a right operand)
-__device__ __forceinline__ void cfrag_to_afrag(const double2& c, int g, int tq, double& a0, double& a1) {
-  const int src0 = 4 * g + (tq >> 1), src1 = src0 + 2;
-  const double sx0 = __shfl_sync(0xffffffffu, c.x, src0), sy0 = __shfl_sync(0xffffffffu, c.y, src0);
-  const double sx1 = __shfl_sync(0xffffffffu, c.x, src1), sy1 = __shfl_sync(0xffffffffu, c.y, src1);
-  a0 = (tq & 1) ? sy0 : sx0;
-  a1 = (tq & 1) ? sy1 : sx1;
+// ---- 8x8 tiles in registers (lane = 4g + tq) -----------------------------------------------------
+// C fragment of M: lane holds M[g][2tq], M[g][2tq+1]   (= row-major doubles 2*lane, 2*lane+1).
+// dmma_cc: acc += M1 * M2 with  m1 = C fragment of M1,  m2t = C fragment of M2^T.
+__device__ __forceinline__ void dmma_cc(double2& acc, const double2& m1, const double2& m2t) {
+  dmma884(acc.x, acc.y, m1.x, m2t.x);
+  dmma884(acc.x, acc.y, m1.y, m2t.y);
 }
-__device__ __forceinline__ void cfrag_to_bfrag(const double2& c, int g, int tq, double& b0, double& b1) {
-  const int src0 = 4 * tq + (g >> 1), src1 = src0 + 16;
-  const double sx0 = __shfl_sync(0xffffffffu, c.x, src0), sy0 = __shfl_sync(0xffffffffu, c.y, src0);
-  const double sx1 = __shfl_sync(0xffffffffu, c.x, src1), sy1 = __shfl_sync(0xffffffffu, c.y, src1);
-  b0 = (g & 1) ? sy0 : sx0;
-  b1 = (g & 1) ? sy1 : sx1;
+__device__ __forceinline__ double neg_bits(double x) {   // -x on the integer pipe
+  return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+__device__ __forceinline__ double2 neg2(const double2& v) { return make_double2(neg_bits(v.x), neg_bits(v.y)); }
+// C fragment of M^T from the C fragment of M: lane wants M[2tq][g], M[2tq+1][g]
+__device__ __forceinline__ double2 cfrag_transpose(const double2& c, int g, int tq) {
+  const int s0 = 8 * tq + (g >> 1), s1 = s0 + 4;
+  const double x0 = __shfl_sync(0xffffffffu, c.x, s0), y0 = __shfl_sync(0xffffffffu, c.y, s0);
+  const double x1 = __shfl_sync(0xffffffffu, c.x, s1), y1 = __shfl_sync(0xffffffffu, c.y, s1);
+  return make_double2((g & 1) ? y0 : x0, (g & 1) ? y1 : x1);
+}
+__device__ __forceinline__ float2 cfrag_transpose_f(const float2& c, int g, int tq) {
+  const int s0 = 8 * tq + (g >> 1), s1 = s0 + 4;
+  const float x0 = __shfl_sync(0xffffffffu, c.x, s0), y0 = __shfl_sync(0xffffffffu, c.y, s0);
+  const float x1 = __shfl_sync(0xffffffffu, c.x, s1), y1 = __shfl_sync(0xffffffffu, c.y, s1);
+  return make_float2((g & 1) ? y0 : x0, (g & 1) ? y1 : x1);
+}
+// store a C fragment so that the 64 doubles at `dst` hold M^T row-major
+__device__ __forceinline__ void store_transposed(double* dst, const double2& c, int g, int tq) {
+  dst[(2 * tq) * 8 + g] = c.x;
+  dst[(2 * tq + 1) * 8 + g] = c.y;
 }
 
 // In-register Gauss-Jordan inverse of an 8x8 block held as a C fragment, no pivoting, diagonal boosting
@@ -120,6 +139,80 @@ __device__ __forceinline__ double2 gj8_cfrag(double2 v, int g, int tq, double th
   return v;
 }
 
+// fp64 <-> fp32 by bit manipulation on the integer pipe (the F2F conversions would queue behind the column
+// warps' DMMAs on the FP64 pipe).  Truncating; out-of-range magnitudes become 0 / inf and simply make the
+// fp32 attempt below fail its residual test.
+__device__ __forceinline__ float d2f_bits(double d) {
+  const unsigned hi = (unsigned)__double2hiint(d), lo = (unsigned)__double2loint(d);
+  const int e = (int)((hi >> 20) & 0x7ffu) - 896;
+  unsigned b = (hi & 0x80000000u);
+  if (e >= 255) b |= 0x7f800000u;
+  else if (e > 0) b |= ((unsigned)e << 23) | ((hi & 0xfffffu) << 3) | (lo >> 29);
+  return __uint_as_float(b);
+}
+__device__ __forceinline__ double f2d_bits(float f) {
+  const unsigned b = __float_as_uint(f);
+  const unsigned ex = (b >> 23) & 0xffu;
+  const unsigned hi = (b & 0x80000000u) | ((ex + 896u) << 20) | ((b & 0x7fffffu) >> 3);
+  return (ex == 0u) ? 0.0 : __hiloint2double((int)(ex == 255u ? (hi | 0x7ff00000u) : hi), (int)(b << 29));
+}
+// |x| >= 2^e2 (or NaN/inf), decided on the exponent field with integer instructions
+__device__ __forceinline__ bool mag_ge_pow2(double x, int e2) {
+  return (int)(((unsigned)__double2hiint(x) >> 20) & 0x7ffu) >= 1023 + e2;
+}
+
+// Inverse of an 8x8 pivot block held as a C fragment.
+// Fast path (well-conditioned blocks, i.e. practically always): Gauss-Jordan without pivoting in FP32 on the
+// FP32 pipe -- which the DMMA streams of the column warps do not load -- followed by Newton-Schulz
+// iterations X <- X + (I - X D) X on the tensor cores (4 DMMAs each; the residual norm squares per step and
+// the iteration stops once the next update is below fp64 round-off), so the result is D^-1 to fp64 accuracy.
+// Blocks whose fp32 attempt does not contract (tiny / boostable pivots, huge dynamic range) take the exact
+// FP64 Gauss-Jordan with the boosting rule.
+__device__ __forceinline__ float2 gj8_f32_cfrag(const double2& d, int g, int tq) {
+  float vx = d2f_bits(d.x), vy = d2f_bits(d.y);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float mine = (k & 1) ? vy : vx;
+    const float piv = __shfl_sync(0xffffffffu, mine, 4 * k + (k >> 1));
+    const float colk = __shfl_sync(0xffffffffu, mine, 4 * g + (k >> 1));
+    const float rx = __shfl_sync(0xffffffffu, vx, 4 * k + tq);
+    const float ry = __shfl_sync(0xffffffffu, vy, 4 * k + tq);
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(piv));
+    const bool isp = (g == k);
+    const float f = isp ? 0.0f : colk * rc;
+    const float ck = isp ? rc : -f;
+    float nx = isp ? rx * rc : fmaf(-f, rx, vx);
+    float ny = isp ? ry * rc : fmaf(-f, ry, vy);
+    if (tq == (k >> 1)) { if (k & 1) ny = ck; else nx = ck; }
+    vx = nx; vy = ny;
+  }
+  return make_float2(vx, vy);
+}
+// Newton-Schulz refinement X <- X + (I - X D) X of an approximate inverse, carried for X and X^T at once so
+// that every operand is a C fragment already in registers (x, xt: X, X^T; d, dt: D, D^T).  The residual norm
+// squares per step; stops once the next update is below fp64 round-off.  false: the iteration does not contract.
+__device__ __forceinline__ bool ns_refine8(const double2& d, const double2& dt, double2& x, double2& xt, int g, int tq) {
+  const double2 eye = make_double2(g == 2 * tq ? 1.0 : 0.0, g == 2 * tq + 1 ? 1.0 : 0.0);
+  const double2 ndt = neg2(dt);
+#pragma unroll 1
+  for (int it = 0; it < 6; ++it) {
+    double2 r = eye, rt = eye;
+    dmma_cc(r, neg2(x), dt);                          // R   = I - X D
+    dmma_cc(rt, ndt, x);                              // R^T = I - D^T X^T
+    // residual entries: all < 2^-28 -> this update is the last one; any >= 2^-4 at the start -> not contracting
+    const bool big = mag_ge_pow2(r.x, -28) || mag_ge_pow2(r.y, -28);
+    const bool huge = mag_ge_pow2(r.x, -4) || mag_ge_pow2(r.y, -4);
+    const unsigned mbig = __ballot_sync(0xffffffffu, big), mhuge = __ballot_sync(0xffffffffu, huge);
+    if (mhuge != 0u && (it == 0 || it == 5)) return false;
+    const double2 xto = xt;
+    dmma_cc(x, r, xto);                               // X   += R X
+    dmma_cc(xt, xto, r);                              // X^T += X^T R^T
+    if (mbig == 0u) return true;
+  }
+  return false;
+}
+
 template <int KT, bool REV, bool TRACE>
 __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 : (KT >= 8 ? 3 : 4)))) k_band_lu(const LuArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -146,6 +239,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     const double2 v = *reinterpret_cast<const double2*>(tile + 62 - 2 * lane);
     return make_double2(v.y, v.x);
   };
+  auto ld_pair_s = [&](const double* tile) -> double2 { return ld_pair(tile); };
   // tile (I,J) of the partition's diagonal block, zero outside it
   auto ld_tile = [&](int I, int J) -> double2 {
     return (I < T && J < T) ? ld_pair(tptr(I, J)) : make_double2(0.0, 0.0);
@@ -170,43 +264,46 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     // =========================== lookahead warp ===========================================
     const double thr = a.boost_thr, rthr = 1.0 / a.boost_thr;
     int nboost = 0;
-    double xa0 = 0.0, xa1 = 0.0;   // D_{s-1}^-1 as an A fragment
+    double2 x = make_double2(0.0, 0.0);   // D_{s-1}^-1
     // step 1 works on raw tiles: fetch them before anybody can overwrite them with factors
-    double2 pc1 = ld_tile(1, 0), uc1 = ld_tile(0, 1), d1 = ld_tile(1, 1);
+    const double2 p1 = ld_tile(1, 0), a1 = ld_tile(1, 1);
+    const double2 ut1 = cfrag_transpose(ld_tile(0, 1), g, tq), at1 = cfrag_transpose(a1, g, tq);
     for (int s = 0; s < T; ++s) {
       LU_TR(8);
-      double2 d;
+      double2 d, dt;
       if (s == 0) {
         d = ld_pair(tptr(0, 0));
+        dt = cfrag_transpose(d, g, tq);
       } else {
-        double2 pc, uc;
+        double2 pc, uct;
         if (s == 1) {
-          pc = pc1; uc = uc1; d = d1;
+          pc = p1; uct = ut1; d = a1; dt = at1;
         } else {        // final after update(s-2): handed over by their owners early in that update
           named_bar_sync(LU_BAR_TILES + (s & 1), 96);
           pc = *reinterpret_cast<const double2*>(&S.tP[s & 1][2 * lane]);
-          uc = *reinterpret_cast<const double2*>(&S.tU[s & 1][2 * lane]);
+          uct = *reinterpret_cast<const double2*>(&S.tUt[s & 1][2 * lane]);
           d = *reinterpret_cast<const double2*>(&S.tA[s & 1][2 * lane]);
+          dt = *reinterpret_cast<const double2*>(&S.tAt[s & 1][2 * lane]);
         }
         LU_TRV(9, d.x);
-        // the column warps' sequence, bit for bit:  Ub = X U ;  D = A + (-P) Ub
-        double u0, u1, b0, b1, n0, n1;
-        double2 ut = make_double2(0.0, 0.0);
-        cfrag_to_bfrag(uc, g, tq, u0, u1);
-        dmma884(ut.x, ut.y, xa0, u0);
-        dmma884(ut.x, ut.y, xa1, u1);
-        cfrag_to_afrag(make_double2(-pc.x, -pc.y), g, tq, n0, n1);
-        cfrag_to_bfrag(ut, g, tq, b0, b1);
-        dmma884(d.x, d.y, n0, b0);
-        dmma884(d.x, d.y, n1, b1);
+        // Ub^T = U^T X^T ;  D = A - P Ub ;  D^T = A^T - Ub^T P^T     (X = D_{s-1}^-1)
+        double2 ubt = make_double2(0.0, 0.0);
+        dmma_cc(ubt, uct, x);
+        dmma_cc(d, neg2(pc), ubt);
+        dmma_cc(dt, neg2(ubt), pc);
       }
       LU_TRV(10, d.x);
-      const double2 x = gj8_cfrag(d, g, tq, thr, rthr, nboost);
+      // approximate inverse in FP32 on the FP32 pipe, then Newton-Schulz on the tensor cores
+      const float2 xf = gj8_f32_cfrag(d, g, tq);
+      const float2 xft = cfrag_transpose_f(xf, g, tq);
+      x = make_double2(f2d_bits(xf.x), f2d_bits(xf.y));
+      double2 xt = make_double2(f2d_bits(xft.x), f2d_bits(xft.y));
+      LU_TRV(14, x.x);
+      if (!ns_refine8(d, dt, x, xt, g, tq)) x = gj8_cfrag(d, g, tq, thr, rthr, nboost);   // exact FP64 path, boosting
       LU_TRV(13, x.x);
-      cfrag_to_afrag(x, g, tq, xa0, xa1);
       wait_slot_free(s);
-      *reinterpret_cast<double2*>(&S.XA[s % LU_R][2 * lane]) = make_double2(xa0, xa1);
-      LU_TRV(11, xa0);
+      *reinterpret_cast<double2*>(&S.XC[s % LU_R][2 * lane]) = x;
+      LU_TRV(11, x.x);
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(s));   // D_s^-1 is published
       if (!REV) *reinterpret_cast<double2*>(tptr(s, s) + 2 * lane) = x;  // factor output
@@ -228,16 +325,13 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
   auto publish_package = [&](int sn) {
     wait_slot_free(sn);
     double* pk = &S.PK[sn % LU_R][0][0];
-    const int idx = 2 * (4 * g + 2 * (tq & 1)) + (tq >> 1);
     const double2 e = ld_tile(sn + KT, sn);   // band-edge tile of the pivot column (never updated before)
 #pragma unroll
     for (int i = 1; i < KT; ++i) {
-      pk[(i - 1) * 64 + idx] = -acc[i].x;
-      pk[(i - 1) * 64 + idx + 2] = -acc[i].y;
+      *reinterpret_cast<double2*>(pk + (i - 1) * 64 + 2 * lane) = neg2(acc[i]);
       if (!REV && sn + i < T) *reinterpret_cast<double2*>(tptr(sn + i, sn) + 2 * lane) = acc[i];
     }
-    pk[(KT - 1) * 64 + idx] = -e.x;
-    pk[(KT - 1) * 64 + idx + 2] = -e.y;
+    *reinterpret_cast<double2*>(pk + (KT - 1) * 64 + 2 * lane) = neg2(e);
     __syncwarp();
     if (lane == 0) mbar_arrive(full_bar(sn));
   };
@@ -279,25 +373,26 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
 
   for (int s = 0; s < T; ++s) {
     const int cj = (jrel == 0) ? KT : jrel;
-    // ---- independent of the package: operand layout of the pivot-row tile, the entering row tile
-    double u0, u1;
-    cfrag_to_bfrag(acc[0], g, tq, u0, u1);
-    double2 f = ld_tile(s + KT, s + cj);
+    // ---- independent of the package: transposed pivot-row tile; the entering row tile lands in shared memory
+    const double2 ut = cfrag_transpose(acc[0], g, tq);
+    const bool fvalid = (s + KT < T);   // (all columns of the window are inside the partition then)
+    if (fvalid) {
+      const double* src = tptr(s + KT, s + cj) + 2 * lane;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&S.FT[warp][2 * lane])), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // two steps ahead: this column's entering row tile; the entering column of step s+2
     if (cj >= 2) prefetch_col(s + 2 + KT, s + cj, 1);
     if (jrel == (KT > 2 ? 2 : KT - 1)) prefetch_col(s + 2, s + 2 + KT, KT + 1);
     if (warp == 0) LU_TR(0);
     mbar_wait(full_bar(s), (uint32_t)((s / LU_R) & 1));   // package(s) and D_s^-1 are in shared memory
     if (warp == 0) LU_TR(1);
-    // ---------------- Ub(s, c) = D_s^-1 A~(s, c) ----------------
-    double b0, b1;
+    // ---------------- Ub(s, c) = D_s^-1 A~(s, c), held as the C fragment of Ub^T = U^T X^T ----------------
+    double2 w = make_double2(0.0, 0.0);
     {
-      const double2 xa = *reinterpret_cast<const double2*>(&S.XA[s % LU_R][2 * lane]);
-      double2 ut = make_double2(0.0, 0.0);
-      dmma884(ut.x, ut.y, xa.x, u0);
-      dmma884(ut.x, ut.y, xa.y, u1);
-      if (!REV && s + cj < T) *reinterpret_cast<double2*>(tptr(s, s + cj) + 2 * lane) = ut;
-      cfrag_to_bfrag(ut, g, tq, b0, b1);
+      const double2 xc = *reinterpret_cast<const double2*>(&S.XC[s % LU_R][2 * lane]);
+      dmma_cc(w, ut, xc);
+      if (!REV && s + cj < T) store_transposed(tptr(s, s + cj), w, g, tq);
     }
     if (warp == 0) LU_TR(2);
     // ---------------- trailing update of the column + window slide ----------------
@@ -306,31 +401,34 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
 #pragma unroll
     for (int i = 1; i < KT; ++i) {
       const double2 af = *reinterpret_cast<const double2*>(pk + (i - 1) * 64 + 2 * lane);
-      dmma884(acc[i].x, acc[i].y, af.x, b0);
-      dmma884(acc[i].x, acc[i].y, af.y, b1);
+      dmma_cc(acc[i], af, w);
       if (KT > 2 && i == 2 && give) {   // hand the lookahead warp its tiles the moment they are final
         if (jrel == 1) {
           *reinterpret_cast<double2*>(&S.tP[s & 1][2 * lane]) = acc[2];
           named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
         } else if (jrel == 2) {
-          *reinterpret_cast<double2*>(&S.tU[s & 1][2 * lane]) = acc[1];
+          store_transposed(S.tUt[s & 1], acc[1], g, tq);
           *reinterpret_cast<double2*>(&S.tA[s & 1][2 * lane]) = acc[2];
+          store_transposed(S.tAt[s & 1], acc[2], g, tq);
           named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
         }
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (REV) __syncwarp();
+    double2 f = fvalid ? ld_pair_s(S.FT[warp]) : make_double2(0.0, 0.0);
     {
       const double2 af = *reinterpret_cast<const double2*>(pk + (KT - 1) * 64 + 2 * lane);
-      dmma884(f.x, f.y, af.x, b0);
-      dmma884(f.x, f.y, af.y, b1);
+      dmma_cc(f, af, w);
     }
     if (KT == 2 && give) {
       if (jrel == 1) {
         *reinterpret_cast<double2*>(&S.tP[s & 1][2 * lane]) = f;
         named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
       } else {
-        *reinterpret_cast<double2*>(&S.tU[s & 1][2 * lane]) = acc[1];
+        store_transposed(S.tUt[s & 1], acc[1], g, tq);
         *reinterpret_cast<double2*>(&S.tA[s & 1][2 * lane]) = f;
+        store_transposed(S.tAt[s & 1], f, g, tq);
         named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
       }
     }

@@ -14,8 +14,16 @@ t = tr.cpu().numpy().reshape(64, 16)
 step = np.diff(t[:, 0]).astype(float)
 print("cycles/step (col warp 0 S1-enter to S1-enter): mean %.0f min %.0f max %.0f" % (step.mean(), step.min(), step.max()))
 def seg(a, b): return (t[:, b] - t[:, a]).astype(float)
-print("col warp0:  wait S1 %.0f | phase A %.0f | wait S2 %.0f | update %.0f | publish %.0f" % (
-    seg(0, 1).mean(), seg(1, 2).mean(), seg(2, 3).mean(), seg(3, 4).mean(), seg(4, 5).mean()))
+print("col warp0:  wait full %.0f | Ub = X U %.0f | update %.0f | publish/load (1 step in KT) %.0f | loop top %.0f" % (
+    seg(0, 1).mean(), seg(1, 2).mean(), seg(2, 4).mean(), seg(4, 5).mean(), (t[1:, 0] - t[:-1, 5]).astype(float).mean()))
+print("lookahead:  fp32 GJ %.0f | Newton-Schulz %.0f" % (seg(10, 14).mean(), seg(14, 13).mean()))
 print("lookahead:  wait tiles %.0f | D_s = A - (P X) U %.0f | Gauss-Jordan %.0f | to B fragment + publish %.0f | arrive+store+stage %.0f | iteration %.0f" % (
     seg(8, 9).mean(), seg(9, 10).mean(), seg(10, 13).mean(), seg(13, 11).mean(), seg(11, 12).mean(), np.diff(t[:, 8]).astype(float).mean()))
 print("lookahead lead: D_s^-1 published %.0f cycles before the column warps enter S1(s)" % ((t[:, 0] - t[:, 11]).astype(float).mean()))
+if len(sys.argv) > 4:
+    print("step | col warp0: S0 wait  Ub  update  pub  top || lookahead: wait D gj32 ns pub rest")
+    for i in range(0, 40):
+        r = t[i]
+        nxt = t[i + 1]
+        print("%3d | %5d %5d %5d %5d %5d || %5d %5d %5d %5d %5d %5d" % (i, r[1] - r[0], r[2] - r[1], r[4] - r[2], r[5] - r[4], nxt[0] - r[5],
+              r[9] - r[8], r[10] - r[9], r[14] - r[10], r[13] - r[14], r[11] - r[13], nxt[8] - r[11]))
