@@ -58,6 +58,7 @@ struct LuSmem {
   double PK[LU_R][KT][64];   // package of step s (slot s % LU_R): -A~(s+1+i, s), i = 0..KT-1, row-major
   double XC[LU_R][64];       // D_s^-1, row-major
   double FT[KT][64];         // per column warp: landing slot of its entering row tile (cp.async)
+  double LT[KT][2][64];      // per column warp: the newest row(s) of its column (transposed C-fragment order)
   double tP[2][64];          // handed over during update(u), buffer u & 1, row-major: A~(u+2, u+1)
   double tUt[2][64];         //                                                        A~(u+1, u+2)^T
   double tA[2][64];          //                                                        A~(u+2, u+2)
@@ -84,6 +85,11 @@ struct LuArgs {
 __device__ __forceinline__ void dmma_cc(double2& acc, const double2& m1, const double2& m2t) {
   dmma884(acc.x, acc.y, m1.x, m2t.x);
   dmma884(acc.x, acc.y, m1.y, m2t.y);
+}
+__device__ __forceinline__ double2 lds_v2(uint32_t addr) {   // volatile 16 B shared-memory load
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ double neg_bits(double x) {   // -x on the integer pipe
   return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
@@ -196,7 +202,7 @@ __device__ __forceinline__ bool ns_refine8(const double2& d, const double2& dt, 
   const double2 eye = make_double2(g == 2 * tq ? 1.0 : 0.0, g == 2 * tq + 1 ? 1.0 : 0.0);
   const double2 ndt = neg2(dt);
 #pragma unroll 1
-  for (int it = 0; it < 6; ++it) {
+  for (int it = 0; it < 7; ++it) {
     double2 r = eye, rt = eye;
     dmma_cc(r, neg2(x), dt);                          // R   = I - X D
     dmma_cc(rt, ndt, x);                              // R^T = I - D^T X^T
@@ -204,7 +210,7 @@ __device__ __forceinline__ bool ns_refine8(const double2& d, const double2& dt, 
     const bool big = mag_ge_pow2(r.x, -28) || mag_ge_pow2(r.y, -28);
     const bool huge = mag_ge_pow2(r.x, -4) || mag_ge_pow2(r.y, -4);
     const unsigned mbig = __ballot_sync(0xffffffffu, big), mhuge = __ballot_sync(0xffffffffu, huge);
-    if (mhuge != 0u && (it == 0 || it == 5)) return false;
+    if (mhuge != 0u && (it == 0 || it == 6)) return false;
     const double2 xto = xt;
     dmma_cc(x, r, xto);                               // X   += R X
     dmma_cc(xt, xto, r);                              // X^T += X^T R^T
@@ -212,12 +218,31 @@ __device__ __forceinline__ bool ns_refine8(const double2& d, const double2& dt, 
   }
   return false;
 }
+// Starting guess for diagonally dominant pivot blocks, no elimination at all: the first Newton-Schulz iterate
+// from the Jacobi guess diag(D)^-1, which can be written entry-wise,  X = (2I - Dg^-1 D) Dg^-1  (one round of
+// shuffles for the diagonal entries, hardware reciprocal seeds).  I - X D = (I - Dg^-1 D)^2.
+__device__ __forceinline__ void jacobi_start8(const double2& d, const double2& dt, double2& x, double2& xt, int g, int tq) {
+  const int sr = 4 * g + (g >> 1);
+  const double drx = __shfl_sync(0xffffffffu, d.x, sr), dry = __shfl_sync(0xffffffffu, d.y, sr);
+  const double dc0 = __shfl_sync(0xffffffffu, d.x, 9 * tq);        // D[2tq][2tq]
+  const double dc1 = __shfl_sync(0xffffffffu, d.y, 9 * tq + 4);    // D[2tq+1][2tq+1]
+  const double dr = (g & 1) ? dry : drx;                           // D[g][g]
+  double rr, rc0, rc1;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(dr));
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc0) : "d"(dc0));
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc1) : "d"(dc1));
+  const double e0 = (g == 2 * tq) ? 2.0 : 0.0, e1 = (g == 2 * tq + 1) ? 2.0 : 0.0;
+  x = make_double2(fma(-d.x, rr, e0) * rc0, fma(-d.y, rr, e1) * rc1);
+  xt = make_double2(fma(-dt.x, rc0, e0) * rr, fma(-dt.y, rc1, e1) * rr);
+}
 
 template <int KT, bool REV, bool TRACE>
 __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 : (KT >= 8 ? 3 : 4)))) k_band_lu(const LuArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LuSmem<KT>& S = *reinterpret_cast<LuSmem<KT>*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived
+  // from it (column bookkeeping, running pointers, ring slots) in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const bool is_lookahead = (warp == KT);
   const int g = lane >> 2, tq = lane & 3;
   const int part = blockIdx.x + (REV ? a.first_part : 0);
@@ -239,7 +264,6 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     const double2 v = *reinterpret_cast<const double2*>(tile + 62 - 2 * lane);
     return make_double2(v.y, v.x);
   };
-  auto ld_pair_s = [&](const double* tile) -> double2 { return ld_pair(tile); };
   // tile (I,J) of the partition's diagonal block, zero outside it
   auto ld_tile = [&](int I, int J) -> double2 {
     return (I < T && J < T) ? ld_pair(tptr(I, J)) : make_double2(0.0, 0.0);
@@ -293,13 +317,19 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
         dmma_cc(dt, neg2(ubt), pc);
       }
       LU_TRV(10, d.x);
-      // approximate inverse in FP32 on the FP32 pipe, then Newton-Schulz on the tensor cores
-      const float2 xf = gj8_f32_cfrag(d, g, tq);
-      const float2 xft = cfrag_transpose_f(xf, g, tq);
-      x = make_double2(f2d_bits(xf.x), f2d_bits(xf.y));
-      double2 xt = make_double2(f2d_bits(xft.x), f2d_bits(xft.y));
+      // pivot-block inverse on the tensor cores: Newton-Schulz from (1) the entry-wise Jacobi iterate (diagonally
+      // dominant blocks: no elimination at all), else from (2) an FP32 Gauss-Jordan without pivoting on the
+      // FP32 pipe, else (3) the exact FP64 Gauss-Jordan with the boosting rule
+      double2 xt;
+      jacobi_start8(d, dt, x, xt, g, tq);
       LU_TRV(14, x.x);
-      if (!ns_refine8(d, dt, x, xt, g, tq)) x = gj8_cfrag(d, g, tq, thr, rthr, nboost);   // exact FP64 path, boosting
+      if (!ns_refine8(d, dt, x, xt, g, tq)) {
+        const float2 xf = gj8_f32_cfrag(d, g, tq);
+        const float2 xft = cfrag_transpose_f(xf, g, tq);
+        x = make_double2(f2d_bits(xf.x), f2d_bits(xf.y));
+        xt = make_double2(f2d_bits(xft.x), f2d_bits(xft.y));
+        if (!ns_refine8(d, dt, x, xt, g, tq)) x = gj8_cfrag(d, g, tq, thr, rthr, nboost);
+      }
       LU_TRV(13, x.x);
       wait_slot_free(s);
       *reinterpret_cast<double2*>(&S.XC[s % LU_R][2 * lane]) = x;
@@ -314,133 +344,195 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
   }
 
   // =========================== column warps ================================================
-  // acc[i] = A~(s+i, c), i = 0..KT-1, of the warp's current column c = s + cj  (cj = jrel, or KT for
-  // the warp whose column retired at this step and that has taken over the entering column s+KT)
-  double2 acc[KT];
-#pragma unroll
-  for (int i = 0; i < KT; ++i) acc[i] = ld_tile(i, warp);
-  int jrel = warp;  // (column owned) - s, taken mod KT
+  // The window tiles are held TRANSPOSED: accT[i] = C fragment of A~(s+i, c)^T, i = 0..KT-1, for the warp's
+  // current column c = s + cj (cj = jrel, or KT for the warp whose column retired at this step and that
+  // has taken over the entering column s+KT).  Then  Ub^T = U^T X^T  and  A~^T -= Ub^T P^T  take their
+  // operands as they are: accT[0], the inverse and the package tiles (row-major) -- no layout change at all.
+  constexpr int SGN = REV ? -1 : 1;
+  const int RS = SGN * (tpr - 1) * SPK_TILE_ELEMS;   // one tile row down, same column (doubles)
+  constexpr int CS = SGN * SPK_TILE_ELEMS;           // one tile column to the right
+  // per-lane element offsets of the transposed fragment inside a stored tile (logical (2tq+e, g))
+  const int o0 = REV ? 63 - (16 * tq + g) : 16 * tq + g;
+  const int o1 = REV ? o0 - 8 : o0 + 8;
+  const int l0 = 16 * tq + g;                        // same, logical orientation (shared memory)
+  auto ldT = [&](const double* tile) -> double2 { return make_double2(tile[o0], tile[o1]); };
+  auto stT = [&](double* tile, const double2& v) { tile[o0] = v.x; tile[o1] = v.y; };
+  auto stT_s = [&](double* tile, const double2& v) { tile[l0] = v.x; tile[l0 + 8] = v.y; };
 
-  // the owner of pivot column sn (registers: acc[i] = A~(sn+i, sn)) publishes the step package
-  auto publish_package = [&](int sn) {
-    wait_slot_free(sn);
-    double* pk = &S.PK[sn % LU_R][0][0];
-    const double2 e = ld_tile(sn + KT, sn);   // band-edge tile of the pivot column (never updated before)
+  // rows 0..NR-1 of the column live in registers, the NSM newest rows in the warp's shared-memory slots
+  // (C-fragment order: every lane reads back its own 16 B).  KT = 13 would need 52 accumulator registers;
+  // with the 72 that two CTAs per SM leave, the compiler then spills accumulators and cannot keep a
+  // package tile in flight ahead of the tensor pipe.
+  constexpr int NSM = (KT >= 12) ? 2 : 1;
+  constexpr int NR = KT - NSM;
+  double2 accT[NR];
+  double* const lt = &S.LT[warp][0][2 * lane];   // slot j at lt + j*64
+  auto col_tile = [&](int i, int J) -> double2 { return (i < T && J < T) ? ldT(tptr(i, J)) : make_double2(0.0, 0.0); };
 #pragma unroll
-    for (int i = 1; i < KT; ++i) {
-      *reinterpret_cast<double2*>(pk + (i - 1) * 64 + 2 * lane) = neg2(acc[i]);
-      if (!REV && sn + i < T) *reinterpret_cast<double2*>(tptr(sn + i, sn) + 2 * lane) = acc[i];
-    }
-    *reinterpret_cast<double2*>(pk + (KT - 1) * 64 + 2 * lane) = neg2(e);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(full_bar(sn));
-  };
-  // fresh tiles of the entering column sn+KT (rows sn .. sn+KT-1) for the warp whose column just retired
-  auto load_entering_column = [&](int sn) {
+  for (int i = 0; i < NR; ++i) accT[i] = col_tile(i, warp);
 #pragma unroll
-    for (int i = 0; i < KT; ++i) acc[i] = ld_tile(sn + i, sn + KT);
+  for (int j = 0; j < NSM; ++j) *reinterpret_cast<double2*>(lt + j * 64) = col_tile(NR + j, warp);
+  int jrel = warp;                   // (column owned) - s, taken mod KT
+  double* pf = tptr(KT, warp);       // running pointer: tile (s+KT, c)
+  double* const ft = &S.FT[warp][0];
+
+  // Package of pivot column sn: tiles 0..KT-2 = -A~(sn+1+j, sn) (logical row-major), tile KT-1 = the band-edge
+  // tile (sn+KT, sn), which no update ever touched: a RAW copy (stored orientation, not negated) made by cp.async.
+  auto stage_edge = [&](int sn, const double* src) {
+    double* dst = &S.PK[sn % LU_R][KT - 1][2 * lane];
+    if (sn + KT < T) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src + 2 * lane) : "memory");
+    else *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
   };
-  // L2 prefetch of the tiles (I0+i, J), i = 0..cnt-1 (4 lines of 128 B each)
-  auto prefetch_col = [&](int I0, int J, int cnt) {
-    if (J >= T) return;
+  // the warp whose column retired recycles its registers for the entering column sn+KT (pf = tile (sn+KT, sn))
+  auto reload_entering = [&](int sn) {
+    const bool cv = (sn + KT < T);
+    pf += KT * CS;                   // tile (sn+KT, sn+KT)
+#pragma unroll
+    for (int i = 0; i < NR; ++i) accT[i] = cv ? ldT(pf - (KT - i) * RS) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < NSM; ++j) *reinterpret_cast<double2*>(lt + j * 64) = cv ? ldT(pf - (NSM - j) * RS) : make_double2(0.0, 0.0);
+  };
+  // L2 prefetch of cnt tiles starting at p, stride `step` doubles (4 lines of 128 B per tile)
+  auto prefetch_tiles = [&](const double* p, int step, int cnt) {
     for (int l = lane; l < 4 * cnt; l += 32) {
-      const int i = l >> 2;
-      if (I0 + i < T) {
-        const double* p = tptr(I0 + i, J) + (l & 3) * 16;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-      }
+      const double* q = p + (l >> 2) * step + (l & 3) * 16;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
     }
   };
 
-  // when step T-KT is about to start the registers hold the trailing Schur complement of the partition
+  // when step T-KT is about to start the warps hold the trailing Schur complement of the partition
   // (rows/cols T-KT..T-1); called before the pivot column's owner recycles its registers
   const int kp = KT * 8;
   auto schur_out = [&]() {
     double* out = a.schur + (int64_t)part * kp * kp;
 #pragma unroll
     for (int i = 0; i < KT; ++i) {
-      const int r = 8 * i + g, cc = 8 * jrel + 2 * tq;
+      const double2 t = (i < NR) ? accT[i < NR ? i : 0] : *reinterpret_cast<const double2*>(lt + (i < NR ? 0 : i - NR) * 64);
+      const int r = 8 * i + 2 * tq, cc = 8 * jrel + g;
       if (!REV) {
-        *reinterpret_cast<double2*>(out + (int64_t)r * kp + cc) = acc[i];
+        out[(int64_t)r * kp + cc] = t.x;
+        out[(int64_t)(r + 1) * kp + cc] = t.y;
       } else {
-        out[(int64_t)(kp - 1 - r) * kp + (kp - 1 - cc)] = acc[i].x;
-        out[(int64_t)(kp - 1 - r) * kp + (kp - 2 - cc)] = acc[i].y;
+        out[(int64_t)(kp - 1 - r) * kp + (kp - 1 - cc)] = t.x;
+        out[(int64_t)(kp - 2 - r) * kp + (kp - 1 - cc)] = t.y;
       }
     }
   };
   if (T == KT) schur_out();
-  if (jrel == 0) { publish_package(0); load_entering_column(0); }
-
-  for (int s = 0; s < T; ++s) {
-    const int cj = (jrel == 0) ? KT : jrel;
-    // ---- independent of the package: transposed pivot-row tile; the entering row tile lands in shared memory
-    const double2 ut = cfrag_transpose(acc[0], g, tq);
-    const bool fvalid = (s + KT < T);   // (all columns of the window are inside the partition then)
-    if (fvalid) {
-      const double* src = tptr(s + KT, s + cj) + 2 * lane;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&S.FT[warp][2 * lane])), "l"(src) : "memory");
-    }
+  if (jrel == 0) {   // nothing is eliminated yet: column 0 is published as loaded (its factor tiles are already in place)
+    stage_edge(0, pf);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    // two steps ahead: this column's entering row tile; the entering column of step s+2
-    if (cj >= 2) prefetch_col(s + 2 + KT, s + cj, 1);
-    if (jrel == (KT > 2 ? 2 : KT - 1)) prefetch_col(s + 2, s + 2 + KT, KT + 1);
-    if (warp == 0) LU_TR(0);
-    mbar_wait(full_bar(s), (uint32_t)((s / LU_R) & 1));   // package(s) and D_s^-1 are in shared memory
-    if (warp == 0) LU_TR(1);
-    // ---------------- Ub(s, c) = D_s^-1 A~(s, c), held as the C fragment of Ub^T = U^T X^T ----------------
-    double2 w = make_double2(0.0, 0.0);
-    {
-      const double2 xc = *reinterpret_cast<const double2*>(&S.XC[s % LU_R][2 * lane]);
-      dmma_cc(w, ut, xc);
-      if (!REV && s + cj < T) store_transposed(tptr(s, s + cj), w, g, tq);
-    }
-    if (warp == 0) LU_TR(2);
-    // ---------------- trailing update of the column + window slide ----------------
-    const double* pk = &S.PK[s % LU_R][0][0];
-    const bool give = (s + 2 < T);
+    double* pk0 = &S.PK[0][0][0];
 #pragma unroll
     for (int i = 1; i < KT; ++i) {
-      const double2 af = *reinterpret_cast<const double2*>(pk + (i - 1) * 64 + 2 * lane);
-      dmma_cc(acc[i], af, w);
-      if (KT > 2 && i == 2 && give) {   // hand the lookahead warp its tiles the moment they are final
-        if (jrel == 1) {
-          *reinterpret_cast<double2*>(&S.tP[s & 1][2 * lane]) = acc[2];
-          named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
-        } else if (jrel == 2) {
-          store_transposed(S.tUt[s & 1], acc[1], g, tq);
-          *reinterpret_cast<double2*>(&S.tA[s & 1][2 * lane]) = acc[2];
-          store_transposed(S.tAt[s & 1], acc[2], g, tq);
-          named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
-        }
-      }
+      const double2 t = (i < NR) ? accT[i < NR ? i : 0] : *reinterpret_cast<const double2*>(lt + (i < NR ? 0 : i - NR) * 64);
+      stT_s(pk0 + (i - 1) * 64, neg2(t));
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (REV) __syncwarp();
-    double2 f = fvalid ? ld_pair_s(S.FT[warp]) : make_double2(0.0, 0.0);
-    {
-      const double2 af = *reinterpret_cast<const double2*>(pk + (KT - 1) * 64 + 2 * lane);
-      dmma_cc(f, af, w);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full_bar(0));
+    reload_entering(0);
+  }
+
+  const uint32_t ft_dst = smem_u32(ft + 2 * lane);
+  for (int s = 0; s < T; ++s) {
+    const int cj = (jrel == 0) ? KT : jrel;
+    const int slot = s % LU_R;
+    // the warp that owns the NEXT pivot column publishes package(s+1) tile by tile while it updates them
+    const bool own_next = (jrel == 1) && (s + 1 < T);
+    double* const pkn = &S.PK[(s + 1) % LU_R][0][0];
+    if (own_next) { wait_slot_free(s + 1); stage_edge(s + 1, pf + RS); }
+    // ---- independent of the package: the entering row tile lands in shared memory; L2 prefetch two steps ahead
+    const bool fvalid = (s + KT < T);   // (all columns of the window are inside the partition then)
+    if (fvalid) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ft_dst), "l"(pf + 2 * lane) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (s + 2 + KT < T) {
+      if (cj >= 2) prefetch_tiles(pf + 2 * RS, 0, 1);
+      if (jrel == (KT > 2 ? 2 : KT - 1)) prefetch_tiles(pf + (2 - KT) * RS + (2 + KT - (KT > 2 ? 2 : KT - 1)) * CS, RS, KT + 1);
     }
-    if (KT == 2 && give) {
+    if (warp == 0) LU_TR(0);
+    mbar_wait(reinterpret_cast<uint64_t*>(&S.full[slot]), (uint32_t)((s / LU_R) & 1));   // package(s), D_s^-1 ready
+    if (warp == 0) LU_TR(1);
+    // ---------------- Ub(s, c) = D_s^-1 A~(s, c), held as the C fragment of Ub^T = U^T X^T ----------------
+    // package tiles come through volatile shared-memory loads, one tile ahead of the tensor pipe (the compiler
+    // must not hoist a batch of them: the accumulators need the registers)
+    const uint32_t pk = smem_u32(&S.PK[slot][0][0] + 2 * lane);
+    double2 afn = lds_v2(pk);
+    double2 w = make_double2(0.0, 0.0);
+    dmma_cc(w, accT[0], *reinterpret_cast<const double2*>(&S.XC[slot][2 * lane]));
+    if (!REV && s + cj < T) stT(pf - KT * RS, w);
+    if (warp == 0) LU_TR(2);
+    // ---------------- trailing update of the column: A~(s+i, c)^T -= Ub^T A~(s+i, s)^T ----------------
+    const bool give = (s + 2 < T);
+    // tiles of update(s) the lookahead warp needs for D_{s+2}: t1 = row s+1, t2 = row s+2 of this column
+    auto hand_over = [&](const double2& t1, const double2& t2) {
       if (jrel == 1) {
-        *reinterpret_cast<double2*>(&S.tP[s & 1][2 * lane]) = f;
+        stT_s(S.tP[s & 1], t2);
         named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
-      } else {
-        store_transposed(S.tUt[s & 1], acc[1], g, tq);
-        *reinterpret_cast<double2*>(&S.tA[s & 1][2 * lane]) = f;
-        store_transposed(S.tAt[s & 1], f, g, tq);
+      } else if (jrel == (KT > 2 ? 2 : 0)) {
+        *reinterpret_cast<double2*>(&S.tUt[s & 1][2 * lane]) = t1;
+        *reinterpret_cast<double2*>(&S.tAt[s & 1][2 * lane]) = t2;
+        stT_s(S.tA[s & 1], t2);
         named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
       }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_bar(s));   // this warp no longer reads the slot of step s
+    };
+    // row s+i of column s+1 goes into package(s+1) as tile i-2 (row s+1 is the next pivot block itself)
+    auto pub = [&](int i, const double2& t) { if (i >= 2 && own_next) stT_s(pkn + (i - 2) * 64, neg2(t)); };
 #pragma unroll
-    for (int i = 1; i < KT; ++i) acc[i - 1] = acc[i];
-    acc[KT - 1] = f;
+    for (int i = 1; i < NR; ++i) {
+      const double2 af = afn;
+      afn = lds_v2(pk + i * 512);
+      dmma_cc(accT[i], w, af);
+      if (NR >= 3 && i == 2 && give) hand_over(accT[1], accT[2]);   // the moment they are final
+      pub(i - 1, accT[i - 1 > 0 ? i - 1 : 0]);                        // one tile behind the tensor pipe
+    }
+    double2 tl[NSM];
+#pragma unroll
+    for (int j = 0; j < NSM; ++j) {
+      const double2 af = afn;
+      afn = (NR + j < KT - 1) ? lds_v2(pk + (NR + j) * 512) : afn;
+      tl[j] = *reinterpret_cast<const double2*>(lt + j * 64);
+      dmma_cc(tl[j], w, af);
+      if (j == 0) pub(NR - 1, accT[NR - 1]); else pub(NR + j - 1, tl[j - 1 >= 0 ? j - 1 : 0]);
+    }
+    if (NR < 3 && KT >= 3 && give) hand_over(NR >= 2 ? accT[1] : tl[1 - NR >= 0 ? 1 - NR : 0], tl[2 - NR >= 0 ? 2 - NR : 0]);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    double2 fT = fvalid ? ldT(ft) : make_double2(0.0, 0.0);
+    {
+      // band-edge multiplier tile: raw copy (stored orientation, not negated)
+      double2 ae = lds_v2(smem_u32(&S.PK[slot][KT - 1][REV ? 62 - 2 * lane : 2 * lane]));
+      if (REV) ae = make_double2(ae.y, ae.x);
+      dmma_cc(fT, w, neg2(ae));
+    }
+    if (KT == 2 && give) hand_over(tl[0], fT);
+    pub(KT - 1, tl[NSM - 1]);
+    pub(KT, fT);
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(reinterpret_cast<uint64_t*>(&S.empty[slot]));   // this warp no longer reads the slot of step s
+      if (own_next) mbar_arrive(full_bar(s + 1));                 // package(s+1) is complete
+    }
+    if (!REV && own_next) {   // factor output of the new pivot column, off the critical path
+#pragma unroll
+      for (int i = 2; i < KT; ++i) {
+        const double2 t = (i < NR) ? accT[i < NR ? i : 0] : tl[i < NR ? 0 : i - NR];
+        if (s + i < T) stT(pf - (KT - i) * RS, t);
+      }
+      if (s + KT < T) stT(pf, fT);
+    }
+    // window slide
+#pragma unroll
+    for (int i = 1; i < NR; ++i) accT[i - 1] = accT[i];
+    accT[NR - 1] = tl[0];
+#pragma unroll
+    for (int j = 1; j < NSM; ++j) *reinterpret_cast<double2*>(lt + (j - 1) * 64) = tl[j];
+    *reinterpret_cast<double2*>(lt + (NSM - 1) * 64) = fT;
     jrel = (jrel == 0) ? KT - 1 : jrel - 1;
+    pf += RS;
     if (warp == 0) LU_TR(4);
     if (s + 1 == T - KT) schur_out();
-    if (jrel == 0 && s + 1 < T) { publish_package(s + 1); load_entering_column(s + 1); }
+    if (own_next) reload_entering(s + 1);
     if (warp == 0) LU_TR(5);
   }
 }
