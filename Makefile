@@ -2,7 +2,7 @@
 # CPU oracle.  `make` here is what __graft_entry__.build() runs.
 NVCC    ?= /usr/local/cuda/bin/nvcc
 ARCH    := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v $(NVEXTRA)
 CSRC    := spike_petsc_b200/csrc
 LIBDIR  := spike_petsc_b200/lib
 OBJS    := $(LIBDIR)/layout.o $(LIBDIR)/lu.o $(LIBDIR)/tips.o $(LIBDIR)/solve.o $(LIBDIR)/krylov.o $(LIBDIR)/capi.o

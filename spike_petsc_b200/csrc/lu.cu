@@ -41,8 +41,12 @@
 // Outputs (FWD): block factors in place, the bottom Schur block S_b of each partition (for V^(b)),
 // boosted-pivot count.
 #include "common.cuh"
+#include <cstdlib>
 
 #define LU_R 4            // ring depth of the step packages
+#ifndef LU_NSM_WIDE
+#define LU_NSM_WIDE 1
+#endif
 #define LU_TRACE_STEPS 64
 // optional clock64 trace of CTA 0 (tools/lu_trace.py): [step-100][16]; 0..7 column warp 0, 8..15 lookahead warp
 // LU_TRV: stamp once a register value has been produced
@@ -57,13 +61,13 @@ template <int KT>
 struct LuSmem {
   double PK[LU_R][KT][64];   // package of step s (slot s % LU_R): -A~(s+1+i, s), i = 0..KT-1, row-major
   double XC[LU_R][64];       // D_s^-1, row-major
-  double FT[KT][64];         // per column warp: landing slot of its entering row tile (cp.async)
   double LT[KT][2][64];      // per column warp: the newest row(s) of its column (transposed C-fragment order)
   double tP[2][64];          // handed over during update(u), buffer u & 1, row-major: A~(u+2, u+1)
   double tUt[2][64];         //                                                        A~(u+1, u+2)^T
   double tA[2][64];          //                                                        A~(u+2, u+2)
   double tAt[2][64];         //                                                        A~(u+2, u+2)^T
-  unsigned long long full[LU_R];    // 2 arrivals: the column's owner (package) + the lookahead warp (inverse)
+  unsigned long long xfull[LU_R];       // 1 arrival: the lookahead warp has published D_s^-1
+  unsigned long long tfull[LU_R][KT];   // 1 arrival each: package tile j of the slot has been published
   unsigned long long empty[LU_R];   // KT arrivals: every column warp is done with the slot
 };
 
@@ -77,6 +81,7 @@ struct LuArgs {
   int first_part;         // REV: first partition index handled by blockIdx 0
   double boost_thr;
   long long* trace;       // optional debug stamps; nullptr in production
+  int stagger_cycles;     // start offset of the second wave of CTAs (see k_band_lu)
 };
 
 // ---- 8x8 tiles in registers (lane = 4g + tq) -----------------------------------------------------
@@ -268,16 +273,25 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
   auto ld_tile = [&](int I, int J) -> double2 {
     return (I < T && J < T) ? ld_pair(tptr(I, J)) : make_double2(0.0, 0.0);
   };
-  auto full_bar = [&](int s) -> uint64_t* { return reinterpret_cast<uint64_t*>(&S.full[s % LU_R]); };
+  auto xfull_bar = [&](int s) -> uint64_t* { return reinterpret_cast<uint64_t*>(&S.xfull[s % LU_R]); };
+  auto tfull_bar = [&](int s, int j) -> uint64_t* { return reinterpret_cast<uint64_t*>(&S.tfull[s % LU_R][j]); };
   auto empty_bar = [&](int s) -> uint64_t* { return reinterpret_cast<uint64_t*>(&S.empty[s % LU_R]); };
   // slot of step s is free again once every column warp has finished update(s - LU_R)
   auto wait_slot_free = [&](int s) {
     if (s >= LU_R) mbar_wait(empty_bar(s), (uint32_t)((s / LU_R - 1) & 1));
   };
 
+  // Two CTAs share an SM and run identical work: started together they stay in lockstep, the tensor pipe
+  // alternating between oversubscribed (both in their updates) and idle (both between steps).  The second wave
+  // of CTAs therefore starts half a step late; the offset persists because both CTAs have the same period.
+  if (!REV && a.stagger_cycles > 0 && blockIdx.x >= (gridDim.x + 1) / 2) {
+    const long long t_end = clock64() + a.stagger_cycles;
+    while (clock64() < t_end) { }
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < LU_R; ++i) {
-      mbar_init(reinterpret_cast<uint64_t*>(&S.full[i]), 2);
+      mbar_init(reinterpret_cast<uint64_t*>(&S.xfull[i]), 1);
+      for (int j = 0; j < KT; ++j) mbar_init(reinterpret_cast<uint64_t*>(&S.tfull[i][j]), 1);
       mbar_init(reinterpret_cast<uint64_t*>(&S.empty[i]), KT);
     }
     fence_mbar_init();
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
       *reinterpret_cast<double2*>(&S.XC[s % LU_R][2 * lane]) = x;
       LU_TRV(11, x.x);
       __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(s));   // D_s^-1 is published
+      if (lane == 0) mbar_arrive(xfull_bar(s));   // D_s^-1 is published
       if (!REV) *reinterpret_cast<double2*>(tptr(s, s) + 2 * lane) = x;  // factor output
       LU_TR(12);
     }
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
   // (C-fragment order: every lane reads back its own 16 B).  KT = 13 would need 52 accumulator registers;
   // with the 72 that two CTAs per SM leave, the compiler then spills accumulators and cannot keep a
   // package tile in flight ahead of the tensor pipe.
-  constexpr int NSM = (KT >= 12) ? 2 : 1;
+  constexpr int NSM = (KT >= 12) ? LU_NSM_WIDE : 0;   // 0: the whole column in registers
   constexpr int NR = KT - NSM;
   double2 accT[NR];
   double* const lt = &S.LT[warp][0][2 * lane];   // slot j at lt + j*64
@@ -374,7 +388,6 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
   for (int j = 0; j < NSM; ++j) *reinterpret_cast<double2*>(lt + j * 64) = col_tile(NR + j, warp);
   int jrel = warp;                   // (column owned) - s, taken mod KT
   double* pf = tptr(KT, warp);       // running pointer: tile (s+KT, c)
-  double* const ft = &S.FT[warp][0];
 
   // Package of pivot column sn: tiles 0..KT-2 = -A~(sn+1+j, sn) (logical row-major), tile KT-1 = the band-edge
   // tile (sn+KT, sn), which no update ever touched: a RAW copy (stored orientation, not negated) made by cp.async.
@@ -430,11 +443,10 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    if (lane == 0) mbar_arrive(full_bar(0));
+    if (lane < KT) mbar_arrive(tfull_bar(0, lane));
     reload_entering(0);
   }
 
-  const uint32_t ft_dst = smem_u32(ft + 2 * lane);
   for (int s = 0; s < T; ++s) {
     const int cj = (jrel == 0) ? KT : jrel;
     const int slot = s % LU_R;
@@ -444,20 +456,21 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     if (own_next) { wait_slot_free(s + 1); stage_edge(s + 1, pf + RS); }
     // ---- independent of the package: the entering row tile lands in shared memory; L2 prefetch two steps ahead
     const bool fvalid = (s + KT < T);   // (all columns of the window are inside the partition then)
-    if (fvalid) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ft_dst), "l"(pf + 2 * lane) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");   // (the band-edge copy of the next package, if any)
     if (s + 2 + KT < T) {
       if (cj >= 2) prefetch_tiles(pf + 2 * RS, 0, 1);
       if (jrel == (KT > 2 ? 2 : KT - 1)) prefetch_tiles(pf + (2 - KT) * RS + (2 + KT - (KT > 2 ? 2 : KT - 1)) * CS, RS, KT + 1);
     }
     if (warp == 0) LU_TR(0);
-    mbar_wait(reinterpret_cast<uint64_t*>(&S.full[slot]), (uint32_t)((s / LU_R) & 1));   // package(s), D_s^-1 ready
+    const uint32_t par = (uint32_t)((s / LU_R) & 1);
+    mbar_wait(xfull_bar(s), par);       // D_s^-1 is in shared memory
+    mbar_wait(tfull_bar(s, 0), par);    // package tiles are consumed as their owner publishes them
     if (warp == 0) LU_TR(1);
     // ---------------- Ub(s, c) = D_s^-1 A~(s, c), held as the C fragment of Ub^T = U^T X^T ----------------
     // package tiles come through volatile shared-memory loads, one tile ahead of the tensor pipe (the compiler
     // must not hoist a batch of them: the accumulators need the registers)
     const uint32_t pk = smem_u32(&S.PK[slot][0][0] + 2 * lane);
-    double2 afn = lds_v2(pk);
+    double2 afn = lds_v2(pk);   // package tile 0 = -A~(s+1, s)
     double2 w = make_double2(0.0, 0.0);
     dmma_cc(w, accT[0], *reinterpret_cast<const double2*>(&S.XC[slot][2 * lane]));
     if (!REV && s + cj < T) stT(pf - KT * RS, w);
@@ -476,43 +489,63 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
         named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
       }
     };
-    // row s+i of column s+1 goes into package(s+1) as tile i-2 (row s+1 is the next pivot block itself)
-    auto pub = [&](int i, const double2& t) { if (i >= 2 && own_next) stT_s(pkn + (i - 2) * 64, neg2(t)); };
-#pragma unroll
-    for (int i = 1; i < NR; ++i) {
-      const double2 af = afn;
-      afn = lds_v2(pk + i * 512);
-      dmma_cc(accT[i], w, af);
-      if (NR >= 3 && i == 2 && give) hand_over(accT[1], accT[2]);   // the moment they are final
-      pub(i - 1, accT[i - 1 > 0 ? i - 1 : 0]);                        // one tile behind the tensor pipe
-    }
-    double2 tl[NSM];
-#pragma unroll
-    for (int j = 0; j < NSM; ++j) {
-      const double2 af = afn;
-      afn = (NR + j < KT - 1) ? lds_v2(pk + (NR + j) * 512) : afn;
-      tl[j] = *reinterpret_cast<const double2*>(lt + j * 64);
-      dmma_cc(tl[j], w, af);
-      if (j == 0) pub(NR - 1, accT[NR - 1]); else pub(NR + j - 1, tl[j - 1 >= 0 ? j - 1 : 0]);
-    }
-    if (NR < 3 && KT >= 3 && give) hand_over(NR >= 2 ? accT[1] : tl[1 - NR >= 0 ? 1 - NR : 0], tl[2 - NR >= 0 ? 2 - NR : 0]);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    double2 fT = fvalid ? ldT(ft) : make_double2(0.0, 0.0);
-    {
-      // band-edge multiplier tile: raw copy (stored orientation, not negated)
+    // row s+i of column s+1 goes into package(s+1) as tile i-2 (row s+1 is the next pivot block itself);
+    // every tile has its own mbarrier, so the consumers of package(s+1) trail this warp by a tile or two
+    auto pub = [&](int i, const double2& t) {
+      if (i >= 2 && own_next) {
+        stT_s(pkn + (i - 2) * 64, neg2(t));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tfull_bar(s + 1, i - 2));
+      }
+    };
+    // One skewed loop over the 13 tiles of the column (rows s+1 .. s+KT): the second k-chunk of tile i and the
+    // first k-chunk of tile i+1 are issued back to back, so two accumulation chains are in flight per warp and
+    // the operand load of tile i+1 overlaps the tensor-pipe latency of tile i.  Rows NR.. come from the
+    // shared-memory tail, row s+KT is the entering tile; everything is resolved at compile time.
+    double2 tl[NSM > 0 ? NSM : 1];
+    double2 fT = make_double2(0.0, 0.0);
+#define LU_TILE(i_) (*((i_) < NR ? &accT[(i_) < NR ? (i_) : 0] : ((i_) < KT ? &tl[((i_) >= NR && (i_) < KT) ? (i_) - NR : 0] : &fT)))
+    auto fetch_tail = [&](int i) {   // make tile i available in registers (called two iterations before its first use)
+      if (i >= NR && i < KT) tl[i - NR < 0 ? 0 : (i - NR < NSM ? i - NR : 0)] = *reinterpret_cast<const double2*>(lt + (i - NR) * 64);
+      if (i == KT) {
+        // entering row tile (s+KT, c): straight from global memory (L2: prefetched two steps ago), transposed
+        fT = fvalid ? ldT(pf) : make_double2(0.0, 0.0);
+        if (own_next) {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tfull_bar(s + 1, KT - 1));   // the raw band-edge tile of package(s+1) has landed
+        }
+      }
+    };
+    auto load_operand = [&](int i) -> double2 {   // -A~(s+i, s): package tile i-1; the last one is the raw band-edge copy
+      mbar_wait(tfull_bar(s, i - 1), par);
+      if (i < KT) return lds_v2(pk + (i - 1) * 512);
       double2 ae = lds_v2(smem_u32(&S.PK[slot][KT - 1][REV ? 62 - 2 * lane : 2 * lane]));
       if (REV) ae = make_double2(ae.y, ae.x);
-      dmma_cc(fT, w, neg2(ae));
+      return neg2(ae);
+    };
+    constexpr int FD = (KT > 6) ? 6 : 2;   // the entering tile is requested FD iterations before its first use
+    fetch_tail(1); fetch_tail(2);
+    if (KT <= FD) fetch_tail(KT > 2 ? KT : 0);
+    double2 af = afn;
+    dmma884(LU_TILE(1).x, LU_TILE(1).y, w.x, af.x);
+#pragma unroll
+    for (int i = 1; i <= KT; ++i) {
+      if (i + 2 < KT) fetch_tail(i + 2);
+      if (KT > FD && i + FD == KT) fetch_tail(KT);
+      if (i < KT) afn = load_operand(i + 1);
+      dmma884(LU_TILE(i).x, LU_TILE(i).y, w.y, af.y);
+      if (i < KT) dmma884(LU_TILE(i + 1).x, LU_TILE(i + 1).y, w.x, afn.x);
+      // tile i-1 is final by now (its last DMMA was issued an iteration ago)
+      if (i == 3 && give) hand_over(LU_TILE(1), LU_TILE(2));   // the moment they are final
+      if (i >= 2) pub(i - 1, LU_TILE(i - 1));
+      af = afn;
     }
-    if (KT == 2 && give) hand_over(tl[0], fT);
-    pub(KT - 1, tl[NSM - 1]);
+    if (KT == 2 && give) hand_over(LU_TILE(1), LU_TILE(2));
     pub(KT, fT);
+#undef LU_TILE
     __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(reinterpret_cast<uint64_t*>(&S.empty[slot]));   // this warp no longer reads the slot of step s
-      if (own_next) mbar_arrive(full_bar(s + 1));                 // package(s+1) is complete
-    }
+    if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&S.empty[slot]));   // this warp no longer reads the slot of step s
     if (!REV && own_next) {   // factor output of the new pivot column, off the critical path
 #pragma unroll
       for (int i = 2; i < KT; ++i) {
@@ -524,10 +557,10 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     // window slide
 #pragma unroll
     for (int i = 1; i < NR; ++i) accT[i - 1] = accT[i];
-    accT[NR - 1] = tl[0];
+    accT[NR - 1] = (NSM > 0) ? tl[0] : fT;
 #pragma unroll
     for (int j = 1; j < NSM; ++j) *reinterpret_cast<double2*>(lt + (j - 1) * 64) = tl[j];
-    *reinterpret_cast<double2*>(lt + (NSM - 1) * 64) = fT;
+    if (NSM > 0) *reinterpret_cast<double2*>(lt + (NSM > 0 ? NSM - 1 : 0) * 64) = fT;
     jrel = (jrel == 0) ? KT - 1 : jrel - 1;
     pf += RS;
     if (warp == 0) LU_TR(4);
@@ -545,6 +578,10 @@ static int launch_lu_kt(spk_ctx* c, int grid, int first_part) {
   a.boost_count = (long long*)c->d_boost; a.tpr = c->L.tpr; a.tipT = c->tipT; a.first_part = first_part;
   a.boost_thr = c->opts.boost_rel * c->anorm_max;
   a.trace = (long long*)c->lu_trace;
+  {
+    const char* e = getenv("SPK_LU_STAGGER");
+    a.stagger_cycles = e ? atoi(e) : 1500;
+  }
   const size_t smem = sizeof(LuSmem<KT>);
   SPK_CUDA(c, cudaFuncSetAttribute(k_band_lu<KT, REV, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_band_lu<KT, REV, TRACE><<<grid, (KT + 1) * 32, smem, c->stream>>>(a);
