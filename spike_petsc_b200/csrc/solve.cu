@@ -9,16 +9,17 @@
 //                       truncation window (tipT tile rows) where the spikes have not yet decayed;
 //                       tipT = whole partition reproduces the classical second full sweep.
 //
-// Sweep kernel anatomy (one CTA per partition / correction job, 4 warps):
+// Sweep kernel anatomy (one CTA per partition / correction job, 5 warps):
 //   warp 0 ("near")  carries the sequential recurrence  y_I = D_I^-1 (c_I - Lb(I,I-1) y_{I-1})
 //                    with 8x8 tiles spread over the lanes and warp-shuffle reductions;
 //   warps 1-3 ("far") accumulate the part of the dot products that only needs y_{<=I-2} for the
 //                    NEXT tile row (warp-shuffle reductions over the 4 lanes of a row);
-//   one elected lane keeps SW_NST tile rows in flight with bulk async copies (mbarrier tx-count).
+//   warp 4 keeps SW_NST tile rows in flight with bulk async copies (mbarrier tx-count).
 #include "common.cuh"
 
 #define SW_NST 8
-#define SW_THREADS 128
+#define SW_THREADS 160          // near warp, three far warps, one copy warp
+#define SW_COPY_THREAD 128
 
 enum { SWEEP_MAIN = 0, SWEEP_CORR = 1 };
 
@@ -41,7 +42,7 @@ struct SweepSmem {
   // forward : [0..KT-1] = Lb tiles d=-KT..-1, [KT] = D^-1 (diagonal slot), [KT+1] = right-hand-side block (8 doubles)
   // backward: [0..KT-1] = Ub tiles d=1..KT (unit block diagonal),         [KT+1] = right-hand-side block
   double stage[SW_NST][KT + 2][64];
-  double ybuf[KT + 1][8];            // ring of the last KT+1 solved tile-row blocks
+  double ybuf[2 * (KT + 1)][8];      // ring of the last KT+1 solved tile-row blocks, stored twice (no wrap-around arithmetic)
   double farpart[2][3][8];
   unsigned long long full[SW_NST];
 };
@@ -51,6 +52,27 @@ struct SweepSmem {
 // Only blocks solved earlier in the same sweep contribute (the sweep range is the solve window).
 // vin[row] is the right-hand side (streamed through the
 // bulk-copy ring together with the factor tiles), sink(I, g, value) consumes the result.
+// far warp FW (0..2) owns stage tiles FW, FW+3, ... of the far set: everything about them is a compile-time
+// constant, the loop is straight-line code (4-5 x {tile LDS, y LDS, 2 FMA}) and two shuffles.
+template <int KT, int DIR, int FW>
+__device__ __forceinline__ double far_partial(const double* stage_row, const double* ybase, int lane, int tq) {
+  double acc = 0.0;
+#pragma unroll
+  for (int t = FW; t < KT - 1; t += 3) {
+    // forward: stage tile tt (d = tt-KT) multiplies the block solved KT-tt iterations before the target row;
+    // backward: stage tile tt (d = tt+1) multiplies the block solved tt+1 iterations before it
+    const int tt = DIR > 0 ? t : t + 1;
+    const int dist = DIR > 0 ? KT - tt : tt + 1;
+    const double2 tv = *reinterpret_cast<const double2*>(stage_row + tt * 64 + 2 * lane);
+    const double2 yp = *reinterpret_cast<const double2*>(ybase - dist * 8 + 2 * tq);
+    acc = fma(tv.x, yp.x, acc);
+    acc = fma(tv.y, yp.y, acc);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  return acc;
+}
+
 template <int KT, int DIR, class Sink>
 __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, unsigned& itbase, int64_t r0, int64_t r1,
                                           const double* vin, int64_t nvalid, Sink sink) {
@@ -66,7 +88,9 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
   // earlier generic-proxy writes of this CTA (previous sweep's results) must be visible to the async proxy
   asm volatile("fence.proxy.async;" ::: "memory");
   __syncthreads();
-  for (int e = threadIdx.x; e < RING * 8; e += blockDim.x) (&S.ybuf[0][0])[e] = 0.0;
+  // y ring, written twice (slot and slot+RING) so that "the block solved d iterations ago" is a plain
+  // subtraction; zero-filled: blocks outside the sweep window contribute nothing
+  for (int e = threadIdx.x; e < 2 * RING * 8; e += blockDim.x) (&S.ybuf[0][0])[e] = 0.0;
   for (int e = threadIdx.x; e < 2 * 3 * 8; e += blockDim.x) (&S.farpart[0][0][0])[e] = 0.0;
   __syncthreads();
   constexpr int NTILE = DIR > 0 ? KT + 1 : KT;
@@ -85,11 +109,10 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
     bulk_g2s(&S.stage[st][0][0], src0 + (int64_t)it * src_step, NTILE * 512, bar);
     if (rb) bulk_g2s(&S.stage[st][KT + 1][0], rhs0 + (int64_t)DIR * it * 8, 64, bar);
   };
-  if (threadIdx.x == 32) {
+  if (threadIdx.x == SW_COPY_THREAD) {
     for (int it = 0; it < SW_NST && it < nrows; ++it) issue(it);
   }
-  // y ring: the block solved at iteration `it` lives in slot it % RING
-  int slot = 0;   // slot of the current iteration
+  int slot = 0;   // ring slot of the current iteration (it % RING)
   for (int it = 0; it < nrows; ++it) {
     const unsigned gi = ib + (unsigned)it;
     if (warp == 0) {
@@ -103,14 +126,11 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
       if (rhs_bulk_ok(it)) rhs = S.stage[st][KT + 1][g];
       else rhs = (I * 8 + g < nvalid) ? vin[I * 8 + g] : 0.0;
       const double cg = rhs - (S.farpart[par][0][g] + S.farpart[par][1][g] + S.farpart[par][2][g]);
-      // adjacent tile: forward Lb(I,I-1) is stage tile KT-1 (d=-1); backward Ub(I,I+1) is stage tile 0 (d=+1)
-      double part = 0.0;
-      if (it > 0) {
-        const int ps = slot == 0 ? RING - 1 : slot - 1;
-        const double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 0][2 * lane]);
-        const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[ps][2 * tq]);
-        part = fma(t.x, yp.x, t.y * yp.y);
-      }
+      // adjacent tile: forward Lb(I,I-1) is stage tile KT-1 (d=-1); backward Ub(I,I+1) is stage tile 0 (d=+1);
+      // the block solved one iteration ago sits at ring position slot+RING-1 (zero at iteration 0)
+      const double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 0][2 * lane]);
+      const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[slot + RING - 1][2 * tq]);
+      double part = fma(t.x, yp.x, t.y * yp.y);
       part += __shfl_xor_sync(0xffffffffu, part, 1);
       part += __shfl_xor_sync(0xffffffffu, part, 2);
       double yv = cg - part;  // replicated in the 4 lanes of row g
@@ -123,39 +143,28 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
         yv += __shfl_xor_sync(0xffffffffu, yv, 1);
         yv += __shfl_xor_sync(0xffffffffu, yv, 2);
       }
-      if (tq == 0) { S.ybuf[slot][g] = yv; sink(I, g, yv); }
-    } else {
+      if (tq == 0) { S.ybuf[slot][g] = yv; S.ybuf[slot + RING][g] = yv; sink(I, g, yv); }
+    } else if (warp <= 3) {
       // -------- far warps: partial sums for the NEXT iteration from blocks solved >= 2 iterations before it
       const int itn = it + 1;
       if (itn < nrows) {
         const unsigned gn = gi + 1u;
         const int stn = (int)(gn % SW_NST);
         mbar_wait(reinterpret_cast<uint64_t*>(&S.full[stn]), (gn / SW_NST) & 1u);
-        const int fw = warp - 1;
-        const int sn = slot + 1 == RING ? 0 : slot + 1;   // slot of iteration itn
-        double acc = 0.0;
-        // forward: stage tile tt (d = tt-KT) multiplies the block solved KT-tt iterations before itn;
-        // backward: stage tile tt (d = tt+1) multiplies the block solved tt+1 iterations before itn
-#pragma unroll
-        for (int t = fw; t < KT - 1; t += 3) {
-          const int tt = DIR > 0 ? t : t + 1;
-          const int dist = DIR > 0 ? KT - tt : tt + 1;
-          if (itn - dist >= 0) {
-            int ys = sn - dist;
-            if (ys < 0) ys += RING;
-            const double2 tv = *reinterpret_cast<const double2*>(&S.stage[stn][tt][2 * lane]);
-            const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[ys][2 * tq]);
-            acc = fma(tv.x, yp.x, acc);
-            acc = fma(tv.y, yp.y, acc);
-          }
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (tq == 0) S.farpart[itn & 1][fw][g] = acc;
+        const int sn = slot + 1 == RING ? 0 : slot + 1;   // ring slot of iteration itn
+        const double* srow = &S.stage[stn][0][0];
+        const double* ybase = &S.ybuf[sn + RING][0];
+        double acc;
+        if (warp == 1) acc = far_partial<KT, DIR, 0>(srow, ybase, lane, tq);
+        else if (warp == 2) acc = far_partial<KT, DIR, 1>(srow, ybase, lane, tq);
+        else acc = far_partial<KT, DIR, 2>(srow, ybase, lane, tq);
+        if (tq == 0) S.farpart[itn & 1][warp - 1][g] = acc;
       }
+    } else {
+      // -------- copy warp: refill the stage the near warp finished one iteration ago
+      if (threadIdx.x == SW_COPY_THREAD && it >= 1 && it - 1 + SW_NST < nrows) issue(it - 1 + SW_NST);
     }
     __syncthreads();
-    if (threadIdx.x == 32 && it + SW_NST < nrows) issue(it + SW_NST);
     slot = slot + 1 == RING ? 0 : slot + 1;
   }
 }
