@@ -166,20 +166,19 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
   }
 
   // =========================== column warps ================================================
-  // The window tiles are held TRANSPOSED: accT[i] = C fragment of A~(s+i, c)^T, i = 0..KT-1, for the warp's
-  // current column c = s + cj (cj = jrel, or KT for the warp whose column retired at this step and that
-  // has taken over the entering column s+KT).  Then  Ub^T = U^T X^T  and  A~^T -= Ub^T P^T  take their
-  // operands as they are: accT[0], the inverse and the package tiles (row-major) -- no layout change at all.
+  // accT[i] = C fragment (row-major) of A~(s+i, c), i = 0..KT-1, for the warp's current column c = s + cj
+  // (cj = jrel, or KT for the warp whose column retired at this step and that has taken over the entering
+  // column s+KT).  All tiles move between memory and registers as they are (one 16 B access per lane); the one
+  // layout change per step is the register transposition of the pivot-row tile accT[0]: with U^T in hand,
+  // Ub^T = U^T X^T (right operand of every update) and Ub = X U (factor output) are two DMMA pairs.
   constexpr int SGN = REV ? -1 : 1;
   const int RS = SGN * (tpr - 1) * SPK_TILE_ELEMS;   // one tile row down, same column (doubles)
   constexpr int CS = SGN * SPK_TILE_ELEMS;           // one tile column to the right
-  // per-lane element offsets of the transposed fragment inside a stored tile (logical (2tq+e, g))
-  const int o0 = REV ? 63 - (16 * tq + g) : 16 * tq + g;
-  const int o1 = REV ? o0 - 8 : o0 + 8;
-  const int l0 = 16 * tq + g;                        // same, logical orientation (shared memory)
-  auto ldT = [&](const double* tile) -> double2 { return make_double2(tile[o0], tile[o1]); };
-  auto stT = [&](double* tile, const double2& v) { tile[o0] = v.x; tile[o1] = v.y; };
-  auto stT_s = [&](double* tile, const double2& v) { tile[l0] = v.x; tile[l0 + 8] = v.y; };
+  const int l0 = 16 * tq + g;
+  auto ldT = [&](const double* tile) -> double2 { return ld_pair(tile); };
+  auto stT = [&](double* tile, const double2& v) { *reinterpret_cast<double2*>(tile + 2 * lane) = v; };   // (!REV only)
+  auto stT_s = [&](double* tile, const double2& v) { *reinterpret_cast<double2*>(tile + 2 * lane) = v; };
+  auto stTr_s = [&](double* tile, const double2& v) { tile[l0] = v.x; tile[l0 + 8] = v.y; };   // shared-memory tile <- M^T
 
   // rows 0..NR-1 of the column live in registers, the NSM newest rows in the warp's shared-memory slots
   // (C-fragment order: every lane reads back its own 16 B).  KT = 13 would need 52 accumulator registers;
@@ -229,13 +228,12 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
 #pragma unroll
     for (int i = 0; i < KT; ++i) {
       const double2 t = (i < NR) ? accT[i < NR ? i : 0] : *reinterpret_cast<const double2*>(lt + (i < NR ? 0 : i - NR) * 64);
-      const int r = 8 * i + 2 * tq, cc = 8 * jrel + g;
+      const int r = 8 * i + g, cc = 8 * jrel + 2 * tq;
       if (!REV) {
-        out[(int64_t)r * kp + cc] = t.x;
-        out[(int64_t)(r + 1) * kp + cc] = t.y;
+        *reinterpret_cast<double2*>(out + (int64_t)r * kp + cc) = t;
       } else {
         out[(int64_t)(kp - 1 - r) * kp + (kp - 1 - cc)] = t.x;
-        out[(int64_t)(kp - 2 - r) * kp + (kp - 1 - cc)] = t.y;
+        out[(int64_t)(kp - 1 - r) * kp + (kp - 2 - cc)] = t.y;
       }
     }
   };
@@ -269,6 +267,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
       if (cj >= 2) prefetch_tiles(pf + 2 * RS, 0, 1);
       if (jrel == (KT > 2 ? 2 : KT - 1)) prefetch_tiles(pf + (2 - KT) * RS + (2 + KT - (KT > 2 ? 2 : KT - 1)) * CS, RS, KT + 1);
     }
+    const double2 ut = cfrag_transpose(accT[0], g, tq);   // pivot-row tile, transposed in registers
     if (warp == 0) LU_TR(0);
     const uint32_t par = (uint32_t)((s / LU_R) & 1);
     mbar_wait(xfull_bar(s), par);       // D_s^-1 is in shared memory
@@ -280,8 +279,15 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     const uint32_t pk = smem_u32(&S.PK[slot][0][0] + 2 * lane);
     double2 afn = lds_v2(pk);   // package tile 0 = -A~(s+1, s)
     double2 w = make_double2(0.0, 0.0);
-    dmma_cc(w, accT[0], *reinterpret_cast<const double2*>(&S.XC[slot][2 * lane]));
-    if (!REV && s + cj < T) stT(pf - KT * RS, w);
+    {
+      const double2 xc = *reinterpret_cast<const double2*>(&S.XC[slot][2 * lane]);
+      dmma_cc(w, ut, xc);                        // Ub^T = U^T X^T
+      if (!REV && s + cj < T) {
+        double2 ub = make_double2(0.0, 0.0);
+        dmma_cc(ub, xc, ut);                     // Ub = X U, the stored factor
+        stT(pf - KT * RS, ub);
+      }
+    }
     if (warp == 0) LU_TR(2);
     // ---------------- trailing update of the column: A~(s+i, c)^T -= Ub^T A~(s+i, s)^T ----------------
     const bool give = (s + 2 < T);
@@ -291,8 +297,8 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
         stT_s(S.tP[s & 1], t2);
         named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
       } else if (jrel == (KT > 2 ? 2 : 0)) {
-        *reinterpret_cast<double2*>(&S.tUt[s & 1][2 * lane]) = t1;
-        *reinterpret_cast<double2*>(&S.tAt[s & 1][2 * lane]) = t2;
+        stTr_s(S.tUt[s & 1], t1);
+        stTr_s(S.tAt[s & 1], t2);
         stT_s(S.tA[s & 1], t2);
         named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
       }
@@ -336,14 +342,14 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     fetch_tail(1); fetch_tail(2);
     if (KT <= FD) fetch_tail(KT > 2 ? KT : 0);
     double2 af = afn;
-    dmma884(LU_TILE(1).x, LU_TILE(1).y, w.x, af.x);
+    dmma884(LU_TILE(1).x, LU_TILE(1).y, af.x, w.x);
 #pragma unroll
     for (int i = 1; i <= KT; ++i) {
       if (i + 2 < KT) fetch_tail(i + 2);
       if (KT > FD && i + FD == KT) fetch_tail(KT);
       if (i < KT) afn = load_operand(i + 1);
-      dmma884(LU_TILE(i).x, LU_TILE(i).y, w.y, af.y);
-      if (i < KT) dmma884(LU_TILE(i + 1).x, LU_TILE(i + 1).y, w.x, afn.x);
+      dmma884(LU_TILE(i).x, LU_TILE(i).y, af.y, w.y);
+      if (i < KT) dmma884(LU_TILE(i + 1).x, LU_TILE(i + 1).y, afn.x, w.x);
       // tile i-1 is final by now (its last DMMA was issued an iteration ago)
       if (i == 3 && give) hand_over(LU_TILE(1), LU_TILE(2));   // the moment they are final
       if (i >= 2) pub(i - 1, LU_TILE(i - 1));
