@@ -289,7 +289,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
       }
     }
     if (warp == 0) LU_TR(2);
-    // ---------------- trailing update of the column: A~(s+i, c)^T -= Ub^T A~(s+i, s)^T ----------------
+    // ---------------- trailing update of the column: A~(s+i, c) -= A~(s+i, s) Ub(s, c) ----------------
     const bool give = (s + 2 < T);
     // tiles of update(s) the lookahead warp needs for D_{s+2}: t1 = row s+1, t2 = row s+2 of this column
     auto hand_over = [&](const double2& t1, const double2& t2) {

@@ -6,7 +6,7 @@
 
 #define LU_R 4            // ring depth of the step packages
 #ifndef LU_NSM_WIDE
-#define LU_NSM_WIDE 1
+#define LU_NSM_WIDE 0
 #endif
 #define LU_TRACE_STEPS 64
 // optional clock64 trace of CTA 0 (tools/lu_trace.py): [step-100][16]; 0..7 column warp 0, 8..15 lookahead warp
