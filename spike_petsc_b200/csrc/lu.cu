@@ -15,26 +15,31 @@
 //     KT tiles live in registers as DMMA m8n8k4 accumulator fragments (2 doubles/lane/tile), so the
 //     whole K x K window is register resident and every band entry is read and written once.  Tiles
 //     entering the window are loaded straight into the fragments (one coalesced 16 B load per lane
-//     and tile, issued a step ahead, L2-prefetched two steps ahead).
+//     and tile, L2-prefetched two steps ahead).
 //   * per 8-pivot step s a column warp scales ITS OWN pivot-row tile, Ub(s,J) = D_s^-1 A~(s,J)
-//     (2 DMMAs), then updates its column A~(I,J) -= A~(I,s) Ub(s,J) (2 DMMAs per tile; the left
-//     operands come from the step PACKAGE: the pivot-column tiles -A~(s+1.., s), written to shared
-//     memory by the column's owner when it finished update(s-1)).  Packages live in a 4-deep ring
-//     guarded by full/empty mbarriers, so warps drift apart by up to a step instead of meeting at
-//     barriers.
+//     (2 DMMAs), then updates its column A~(I,J) -= A~(I,s) Ub(s,J) (2 DMMAs per tile, issued skewed so
+//     that two accumulation chains are in flight).  The left operands come from the step PACKAGE: the
+//     pivot-column tiles -A~(s+1.., s), published to shared memory by the warp that owns column s
+//     WHILE it updates them during step s-1, one mbarrier per tile: the consumers of package(s) trail
+//     their producer by a tile or two instead of waiting for its whole column.  Packages live in a
+//     4-deep ring; an `empty` mbarrier per slot tells the producer when all column warps have left it.
 //   * operand layouts: a DMMA contracts over k, so the SAME permutation of k may be applied to both
 //     operands.  With k = 2*(lane%4)+h for k-chunk h, the left operand of M1*M2 is the accumulator
-//     ("C") fragment of M1 itself and the right operand is the C fragment of M2^T.  Every product in
-//     this kernel is arranged so that its operands are C fragments somebody already holds (tiles are
-//     row-major = C-fragment order in memory, shared memory and registers); the only layout change
-//     left is one register transposition of the pivot-row tile per column warp and step.
+//     ("C") fragment of M1 itself and the right operand is the C fragment of M2^T.  Tiles are row-major
+//     = C-fragment order in global memory, shared memory and registers, so package tiles and
+//     accumulators are used as they are; the one layout change per warp and step is a register
+//     transposition (shuffles) of the pivot-row tile, which yields Ub^T = U^T X^T (right operand of
+//     every update) and Ub = X U (the stored factor).
 //   * the LOOKAHEAD warp (warp KT) runs the only truly sequential part of the factorisation, the chain
-//     D_t^-1 -> D_t+1 -> D_t+1^-1, privately and one step ahead of the column warps: as soon as the
-//     three tiles A~(t,t-1), A~(t-1,t), A~(t,t) are final after update(t-2) (they are the first tiles
-//     their owners update, and are handed over through shared memory at once) it recomputes
-//     D_t = A~(t,t) - A~(t,t-1) (D_t-1^-1 A~(t-1,t)) with the same DMMA sequence the column warps use
-//     (bit-identical), inverts it in registers and publishes D_t^-1 in A-fragment order (the second
-//     arrival on the package's `full` barrier).  The column warps never wait for a pivot-block inverse.
+//     D_t^-1 -> D_t+1 -> D_t+1^-1, privately and ahead of the column warps: as soon as the three tiles
+//     A~(t,t-1), A~(t-1,t), A~(t,t) are final after update(t-2) (they are handed over through shared
+//     memory early in that update) it forms D_t = A~(t,t) - A~(t,t-1) (D_t-1^-1 A~(t-1,t)) and inverts
+//     it ON THE TENSOR CORES: Newton-Schulz X <- X + (I - X D) X carried for X and X^T (every operand a
+//     C fragment in registers, 8 DMMAs per iteration, residual squares per step, stops below fp64
+//     round-off), started from the entry-wise Jacobi iterate (2I - Dg^-1 D) Dg^-1 for diagonally dominant
+//     blocks, else from an FP32 Gauss-Jordan without pivoting on the FP32 pipe, else the exact FP64
+//     Gauss-Jordan with the boosting rule (tiny pivots).  D_t^-1 goes to shared memory (own mbarrier)
+//     and to the diagonal slot of the band.  The column warps never wait for a pivot-block inverse.
 //   * REV=true runs the same elimination on the row/column-reversed matrix (= bottom-up elimination
 //     of the partition's first tipT tile rows) without storing factors: it only yields the top
 //     Schur block S_t needed for the W^(t) spike tip.
@@ -46,7 +51,7 @@ template <int KT>
 struct LuSmem {
   double PK[LU_R][KT][64];   // package of step s (slot s % LU_R): -A~(s+1+i, s), i = 0..KT-1, row-major
   double XC[LU_R][64];       // D_s^-1, row-major
-  double LT[KT][2][64];      // per column warp: the newest row(s) of its column (transposed C-fragment order)
+  double LT[KT][2][64];      // per column warp: optional shared-memory tail of its column (LU_NSM_WIDE rows)
   double tP[2][64];          // handed over during update(u), buffer u & 1, row-major: A~(u+2, u+1)
   double tUt[2][64];         //                                                        A~(u+1, u+2)^T
   double tA[2][64];          //                                                        A~(u+2, u+2)
