@@ -3,122 +3,138 @@
 //   W_i^(t)   = S_t(i)^-1 C_i        (S_t = leading Schur block left by the UL window of partition i)
 //   Rinv_i    = (I - W_{i+1}^(t) V_i^(b))^-1      (truncated SPIKE reduced block, explicit inverse)
 // [EXTERNAL algorithm: SPIKE (Polizzi/Sameh), SaP::GPU; the reference only names it, README.md:4.]
-// The dense solves are blocked Gauss-Jordan eliminations with matrix AND right-hand sides resident in
-// shared memory (2 * kp*(kp+1) doubles: 175 KB at kp = 104, within the 227 KB a B200 CTA may opt into).
-#include "common.cuh"
+//
+// The dense solves are BLOCKED Gauss-Jordan eliminations on FP64 tensor cores with matrix AND right-hand sides
+// resident in shared memory as 8x8 tiles (row-major, 512 B each = DMMA accumulator-fragment order, see lu.cu):
+// per block step k (kt = kp/8 of them)
+//   (1) warp 0 inverts the pivot tile M(k,k) with the pivot-block inverse of the band LU (Newton-Schulz on the
+//       tensor cores from a Jacobi / FP32 Gauss-Jordan start, exact FP64 Gauss-Jordan with the boosting rule as
+//       fallback; lu_dev.cuh) -- one step ahead: it updates and inverts M(k+1,k+1) while the other warps run (3);
+//   (2) the pivot tile row is scaled, T <- D^-1 T (2 DMMAs per tile), and its transposes are parked in a row
+//       buffer so that step (3) reads every operand with one 16 B load per lane;
+//   (3) every other tile row is eliminated: T(I,J) -= M(I,k) T(k,J) (2 DMMAs per tile).
+// No pivoting across blocks -- these matrices are the Schur blocks the no-pivot band LU itself would go on to
+// factor, and I - W V of decaying spikes.  Right-hand-side tile columns that are still zero (the coupling
+// blocks are block triangular) are skipped.
+#include "lu_dev.cuh"
 
-#define TIPS_THREADS 256
+#define TIPS_THREADS 512
+#define TIPS_WARPS (TIPS_THREADS / 32)
 
-// Solve M X = R (kp x kp matrix, ncols right-hand sides), everything resident in shared memory, by
-// BLOCKED Gauss-Jordan: kp/8 steps, each inverting an 8x8 pivot block (one warp, same in-register
-// Gauss-Jordan + boosting rule as the band LU), scaling the pivot block row and eliminating the block
-// column from all other rows with a register-blocked rank-8 update.  No pivoting across blocks --
-// these matrices are the Schur blocks the no-pivot band LU itself would go on to factor, and
-// I - W V of decaying spikes.  256 threads as a 16 x 16 grid over (rows, columns).
-__device__ __forceinline__ void gj8_inverse_warp(const double* D, int ld, double* Dv, double thr) {
-  // lanes 0..7 hold rows; result Dv[8][8] row-major
-  const int lane = threadIdx.x & 31, r8 = lane & 7;
-  double row[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) row[c] = D[r8 * ld + c];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const double piv = __shfl_sync(0xffffffffu, row[k], k);
-    double r0;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(piv));
-    const bool isp = (r8 == k);
-    const double q = isp ? 0.0 : row[k] * r0;
-    const double e = fma(-piv, r0, 1.0);
-    const double t = fma(e, e, e);
-    double f = fma(q, t, q);
-    double rc = fma(r0, t, r0);
-    if (fabs(piv) < thr) {
-      rc = (piv < 0.0) ? -1.0 / thr : 1.0 / thr;
-      f = isp ? 0.0 : row[k] * rc;
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      if (c == k) continue;
-      const double u = __shfl_sync(0xffffffffu, row[c], k);
-      row[c] = isp ? u * rc : fma(-f, u, row[c]);
-    }
-    row[k] = isp ? rc : -f;
+// shared-memory carve-up: M[kt][kt], X[kt][ktx], PT[kt+ktx] (transposed scaled pivot row), Dv (pivot inverse)
+// wide tips (kt > 14) do not fit M and all kt right-hand-side tile columns in 227 KB: two column passes
+__host__ __device__ __forceinline__ int tip_pass_tiles(int kt) { return kt <= 14 ? kt : (kt + 1) / 2; }
+struct TipSmem { double* M; double* X; double* PT; double* Dv; };
+__device__ __forceinline__ TipSmem tip_carve(double* sm, int kt) {
+  TipSmem t;
+  const int ktx = tip_pass_tiles(kt);
+  t.M = sm; t.X = t.M + (size_t)kt * kt * 64; t.PT = t.X + (size_t)kt * ktx * 64; t.Dv = t.PT + (size_t)(kt + ktx) * 64;   // two tiles
+  return t;
+}
+static size_t tips_smem(int kt) { return sizeof(double) * 64 * ((size_t)kt * kt + (size_t)kt * tip_pass_tiles(kt) + kt + tip_pass_tiles(kt) + 2) + 64; }
+
+// Solve M X = R in place (X <- M^-1 R); M: kt x kt tiles, X: kt x ktx tiles, both tile-major in shared memory.
+// xfirst[J] (optional, shared memory, ktx ints): first block row in which right-hand-side tile column J is
+// nonzero on entry -- column J then stays zero until block step xfirst[J] and is skipped before it.
+__device__ __forceinline__ double2 tip_invert8(const double2& d, int g, int tq, double thr, double rthr) {
+  int nboost = 0;
+  const double2 dt = cfrag_transpose(d, g, tq);
+  double2 x, xt;
+  jacobi_start8(d, dt, x, xt, g, tq);
+  if (!ns_refine8(d, dt, x, xt, g, tq)) {
+    const float2 xf = gj8_f32_cfrag(d, g, tq);
+    const float2 xft = cfrag_transpose_f(xf, g, tq);
+    x = make_double2(f2d_bits(xf.x), f2d_bits(xf.y));
+    xt = make_double2(f2d_bits(xft.x), f2d_bits(xft.y));
+    if (!ns_refine8(d, dt, x, xt, g, tq)) x = gj8_cfrag(d, g, tq, thr, rthr, nboost);
   }
-  if (lane < 8) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) Dv[lane * 8 + c] = row[c];
+  return x;
+}
+
+__device__ void dense_solve_tiles(const TipSmem& T, int kt, int ktx, const int* xfirst, double thr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int l0 = 16 * tq + g;
+  const double rthr = 1.0 / thr;
+  // Dv[k & 1] = inverse of the pivot tile of step k.  Warp 0 is the lookahead warp: in step k it first updates
+  // the NEXT pivot tile M(k+1,k+1) and inverts it while the other warps eliminate the rest of block column k.
+  if (warp == 0) {
+    const double2 d = *reinterpret_cast<const double2*>(T.M + 2 * lane);
+    *reinterpret_cast<double2*>(T.Dv + 2 * lane) = tip_invert8(d, g, tq, thr, rthr);
+  }
+  __syncthreads();
+  for (int k = 0; k < kt; ++k) {
+    // ---- (2) scale the pivot tile row: items = M tiles right of the pivot, then the live X tiles
+    const int nm = kt - (k + 1);
+    {
+      const double2 dinv = *reinterpret_cast<const double2*>(T.Dv + (k & 1) * 64 + 2 * lane);
+      for (int it = warp; it < nm + ktx; it += TIPS_WARPS) {
+        const bool ism = it < nm;
+        const int J = ism ? k + 1 + it : it - nm;
+        if (!ism && xfirst && xfirst[J] > k) continue;                       // still a zero tile
+        double* tile = ism ? T.M + ((size_t)k * kt + J) * 64 : T.X + ((size_t)k * ktx + J) * 64;
+        const double2 tt = make_double2(tile[l0], tile[l0 + 8]);             // C fragment of tile^T
+        double2 r = make_double2(0.0, 0.0);
+        dmma_cc(r, dinv, tt);                                                // D^-1 * tile
+        __syncwarp();
+        *reinterpret_cast<double2*>(tile + 2 * lane) = r;
+        double* pt = T.PT + (size_t)it * 64;                                 // transposed copy for step (3)
+        pt[l0] = r.x; pt[l0 + 8] = r.y;
+      }
+    }
+    __syncthreads();
+    // ---- (3) eliminate block column k from all other tile rows; one warp per (row I, item) pair
+    const bool look = (k + 1 < kt);
+    if (look && warp == 0) {
+      // next pivot tile first: M(k+1,k+1) -= M(k+1,k) T'(k,k+1)  (item 0 of row k+1), then its inverse
+      double* tile = T.M + ((size_t)(k + 1) * kt + k + 1) * 64;
+      const double2 a = neg2(*reinterpret_cast<const double2*>(T.M + ((size_t)(k + 1) * kt + k) * 64 + 2 * lane));
+      double2 acc = *reinterpret_cast<const double2*>(tile + 2 * lane);
+      dmma_cc(acc, a, *reinterpret_cast<const double2*>(T.PT + 2 * lane));
+      *reinterpret_cast<double2*>(tile + 2 * lane) = acc;
+      *reinterpret_cast<double2*>(T.Dv + ((k + 1) & 1) * 64 + 2 * lane) = tip_invert8(acc, g, tq, thr, rthr);
+    } else {
+      const int nitem = nm + ktx;
+      const int total = (kt - 1) * nitem;
+      const int w0 = look ? warp - 1 : warp, nw = look ? TIPS_WARPS - 1 : TIPS_WARPS;
+      int Iprev = -1;
+      double2 a = make_double2(0.0, 0.0);
+      for (int w = w0; w < total; w += nw) {
+        const int ri = w / nitem, it = w - ri * nitem;
+        const int I = ri < k ? ri : ri + 1;
+        const bool ism = it < nm;
+        const int J = ism ? k + 1 + it : it - nm;
+        if (!ism && xfirst && xfirst[J] > k) continue;
+        if (look && ism && I == k + 1 && J == k + 1) continue;               // the lookahead warp's tile
+        if (I != Iprev) { a = neg2(*reinterpret_cast<const double2*>(T.M + ((size_t)I * kt + k) * 64 + 2 * lane)); Iprev = I; }
+        double* tile = ism ? T.M + ((size_t)I * kt + J) * 64 : T.X + ((size_t)I * ktx + J) * 64;
+        double2 acc = *reinterpret_cast<const double2*>(tile + 2 * lane);
+        const double2 b = *reinterpret_cast<const double2*>(T.PT + (size_t)it * 64 + 2 * lane);
+        dmma_cc(acc, a, b);                                                  // T(I,J) -= M(I,k) T'(k,J)
+        *reinterpret_cast<double2*>(tile + 2 * lane) = acc;
+      }
+    }
+    __syncthreads();
   }
 }
 
-__device__ void dense_solve_smem(double* M, double* X, int ld, int kp, int ncols, int ldx, double* Dv, double thr) {
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int c0 = 0; c0 < kp; c0 += 8) {
-    // (1) inverse of the pivot block
-    if (warp == 0) gj8_inverse_warp(M + c0 * ld + c0, ld, Dv, thr);
-    __syncthreads();
-    // (2) pivot block row <- Dinv * (pivot block row), one thread per column (M columns right of the block, all X columns)
-    const int nm = kp - (c0 + 8);
-    for (int cc = tid; cc < nm + ncols; cc += TIPS_THREADS) {
-      double* col = (cc < nm) ? (M + c0 * ld + (c0 + 8 + cc)) : (X + c0 * ldx + (cc - nm));
-      const int st = (cc < nm) ? ld : ldx;
-      double v[8], o[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = col[k * st];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc = fma(Dv[r * 8 + k], v[k], acc);
-        o[r] = acc;
-      }
-#pragma unroll
-      for (int r = 0; r < 8; ++r) col[r * st] = o[r];
-    }
-    __syncthreads();
-    // (3) eliminate the block column from every other row: rank-8 update, thread = rows {ty+16m} x cols {tx+16q}
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      double* T = pass == 0 ? M : X;
-      const int tld = pass == 0 ? ld : ldx;
-      const int cbeg = pass == 0 ? c0 + 8 : 0;
-      const int cend = pass == 0 ? kp : ncols;
-      if (cbeg + tx >= cend) continue;
-      for (int rbase = ty; rbase < kp; rbase += 16 * 4) {      // 4 rows per register block
-        double acc[4][8];
-        int rr[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          rr[m] = rbase + 16 * m;
-          const bool live = rr[m] < kp && (rr[m] < c0 || rr[m] >= c0 + 8);
-          if (!live) rr[m] = -1;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int c = cbeg + tx + 16 * q;
-            acc[m][q] = (live && c < cend) ? T[rr[m] * tld + c] : 0.0;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          double pk[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) { const int c = cbeg + tx + 16 * q; pk[q] = (c < cend) ? T[(c0 + k) * tld + c] : 0.0; }
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const double l = (rr[m] >= 0) ? M[rr[m] * ld + c0 + k] : 0.0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[m][q] = fma(-l, pk[q], acc[m][q]);
-          }
-        }
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          if (rr[m] < 0) continue;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) { const int c = cbeg + tx + 16 * q; if (c < cend) T[rr[m] * tld + c] = acc[m][q]; }
-        }
-      }
-    }
-    __syncthreads();
+// tile-major shared memory <- row-major kp x kp global matrix (columns c0t.. of it, nct tile columns)
+__device__ __forceinline__ void load_tiles(double* dst, int ldt, const double* src, int kp, int kt, int c0t, int nct) {
+  for (int e = threadIdx.x; e < kt * nct * 32; e += blockDim.x) {
+    const int pr = e & 31, t = e >> 5;            // pair index inside the tile, tile index
+    const int I = t / nct, J = t - I * nct;
+    const int r = pr >> 2, c = (pr & 3) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(src + (size_t)(8 * I + r) * kp + 8 * (c0t + J) + c);
+    *reinterpret_cast<double2*>(dst + ((size_t)I * ldt + J) * 64 + 2 * pr) = v;
+  }
+}
+__device__ __forceinline__ void store_tiles(double* dst, int kp, const double* src, int ldt, int kt, int c0t, int nct) {
+  for (int e = threadIdx.x; e < kt * nct * 32; e += blockDim.x) {
+    const int pr = e & 31, t = e >> 5;
+    const int I = t / nct, J = t - I * nct;
+    const int r = pr >> 2, c = (pr & 3) * 2;
+    *reinterpret_cast<double2*>(dst + (size_t)(8 * I + r) * kp + 8 * (c0t + J) + c) =
+        *reinterpret_cast<const double2*>(src + ((size_t)I * ldt + J) * 64 + 2 * pr);
   }
 }
 
@@ -132,46 +148,37 @@ struct TipArgs {
   double thr;           // pivot boosting threshold (same rule as the band LU)
 };
 
-struct TipSmem { double* M; double* X; double* Dv; };
-// wide tips (kp > 112) do not fit M and all kp right-hand sides in 227 KB: they run two column passes
-__host__ __device__ __forceinline__ int tip_pass_cols(int kp) { return kp <= 112 ? kp : kp / 2; }
-__device__ __forceinline__ TipSmem tip_carve(double* sm, int kp) {
-  TipSmem t;
-  const int ld = kp + 1, ldx = tip_pass_cols(kp) + 1;
-  t.M = sm; t.X = sm + (size_t)kp * ld; t.Dv = t.X + (size_t)kp * ldx;
-  return t;
-}
-
 // which==0: out[p] = Sb[p]^-1 B_p ; which==1: out[p] = St[p]^-1 C_p
 __global__ void __launch_bounds__(TIPS_THREADS) k_spike_tip(const TipArgs a) {
-  extern __shared__ __align__(16) double sm[];
-  const int kp = a.L.kt * 8, ld = kp + 1, KT = a.L.kt;
-  const TipSmem T = tip_carve(sm, kp);
+  extern __shared__ __align__(128) double sm[];
+  __shared__ int xfirst[SPK_MAX_KT];
+  const int KT = a.L.kt, kp = KT * 8;
+  const TipSmem T = tip_carve(sm, KT);
   const int p = blockIdx.x + a.first_part;
   const double* S = a.S + (size_t)p * kp * kp;
   double* out = a.out + (size_t)p * kp * kp;
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  // right-hand side block straight from the (never overwritten) coupling tiles of the band
+  // right-hand side block straight from the (never overwritten) coupling tiles of the band:
+  //   B(I,J) = tile (tb-KT+I, tb+J), inside the band iff J <= I ;  C(I,J) = tile (tb+I, tb-KT+J), iff J >= I
   const int64_t tb = (a.which == 0) ? a.pstart[p + 1] : a.pstart[p];
-  const int nc = tip_pass_cols(kp), ldx = nc + 1;
-  for (int c0 = 0; c0 < kp; c0 += nc) {
-    for (int r = ty; r < kp; r += 16) {
-      for (int c = tx; c < kp; c += 16) T.M[r * ld + c] = S[(size_t)r * kp + c];
-      for (int cc = tx; cc < nc; cc += 16) {
-        const int c = c0 + cc;
-        double v = 0.0;
-        if (a.which == 0) {  // B(r,c) = A(8(tb-KT)+r, 8tb+c), in band iff c/8 <= r/8
-          if ((c >> 3) <= (r >> 3)) v = a.band[a.L.elem_off((tb - KT) * 8 + r, tb * 8 + c)];
-        } else {             // C(r,c) = A(8tb+r, 8(tb-KT)+c), in band iff c/8 >= r/8
-          if ((c >> 3) >= (r >> 3)) v = a.band[a.L.elem_off(tb * 8 + r, (tb - KT) * 8 + c)];
-        }
-        T.X[r * ldx + cc] = v;
+  const int ktx = tip_pass_tiles(KT);
+  for (int c0t = 0; c0t < KT; c0t += ktx) {
+    const int nct = (KT - c0t < ktx) ? KT - c0t : ktx;
+    load_tiles(T.M, KT, S, kp, KT, 0, KT);
+    for (int e = threadIdx.x; e < KT * ktx * 32; e += blockDim.x) {
+      const int pr = e & 31, t = e >> 5;
+      const int I = t / ktx, Jl = t - I * ktx, J = c0t + Jl;
+      double2 v = make_double2(0.0, 0.0);
+      if (Jl < nct) {
+        if (a.which == 0) { if (J <= I) v = *reinterpret_cast<const double2*>(a.band + a.L.tile_off(tb - KT + I, tb + J) + 2 * pr); }
+        else              { if (J >= I) v = *reinterpret_cast<const double2*>(a.band + a.L.tile_off(tb + I, tb - KT + J) + 2 * pr); }
       }
+      *reinterpret_cast<double2*>(T.X + ((size_t)I * ktx + Jl) * 64 + 2 * pr) = v;
     }
+    // first nonzero block row of each right-hand-side tile column: B: row J ; C: row 0
+    if (threadIdx.x < ktx) xfirst[threadIdx.x] = (threadIdx.x < nct) ? (a.which == 0 ? c0t + (int)threadIdx.x : 0) : KT;
     __syncthreads();
-    dense_solve_smem(T.M, T.X, ld, kp, nc, ldx, T.Dv, a.thr);
-    for (int r = ty; r < kp; r += 16)
-      for (int cc = tx; cc < nc; cc += 16) out[(size_t)r * kp + c0 + cc] = T.X[r * ldx + cc];
+    dense_solve_tiles(T, KT, ktx, xfirst, a.thr);
+    store_tiles(out, kp, T.X, ktx, KT, c0t, nct);
     __syncthreads();
   }
 }
@@ -184,69 +191,76 @@ struct RedArgs {
 };
 // Rinv[i] = (I - Wt[i+1] Vb[i])^-1
 __global__ void __launch_bounds__(TIPS_THREADS) k_reduced_factor(const RedArgs a) {
-  extern __shared__ __align__(16) double sm[];
-  const int kp = a.kp, ld = kp + 1;
-  const TipSmem T = tip_carve(sm, kp);
+  extern __shared__ __align__(128) double sm[];
+  const int kp = a.kp, KT = kp / 8;
+  const TipSmem T = tip_carve(sm, KT);
   const int i = blockIdx.x + a.first_iface;
   const double* V = a.Vb + (size_t)i * kp * kp;
   const double* W = (i == a.remote_iface) ? a.remoteWt : a.Wt + (size_t)(i + a.wt_part_offset) * kp * kp;
   double* out = a.Rinv + (size_t)i * kp * kp;
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  const int nc = tip_pass_cols(kp), ldx = nc + 1;
-  for (int c0 = 0; c0 < kp; c0 += nc) {
-    // M = I - W V: stage W in M's space and V in X's space (coalesced), accumulate each thread's
-    // (<= 8 x 8) output patch in registers, then overwrite.  (Wide tips: V does not fit next to M in one
-    // pass; they take the slower global-memory product below.)
-    if (nc == kp) {
-      for (int r = ty; r < kp; r += 16)
-        for (int c = tx; c < kp; c += 16) { T.M[r * ld + c] = W[(size_t)r * kp + c]; T.X[r * ldx + c] = V[(size_t)r * kp + c]; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int ktx = tip_pass_tiles(KT);
+  for (int c0t = 0; c0t < KT; c0t += ktx) {
+    const int nct = (KT - c0t < ktx) ? KT - c0t : ktx;
+    // M = I - W V on the tensor cores
+    if (ktx == KT) {
+      // stage W in M's space and V in X's space, keep every warp's output tiles in registers until all
+      // operands have been read, then overwrite M
+      load_tiles(T.M, KT, W, kp, KT, 0, KT);
+      load_tiles(T.X, KT, V, kp, KT, 0, KT);
       __syncthreads();
-      double acc[8][8];
+      constexpr int MAXT = (14 * 14 + TIPS_WARPS - 1) / TIPS_WARPS;
+      double2 acc[MAXT];
 #pragma unroll
-      for (int m = 0; m < 8; ++m)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[m][q] = 0.0;
-      for (int k = 0; k < kp; ++k) {
-        double wv[8], vv[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) { const int r = ty + 16 * m; wv[m] = (r < kp) ? T.M[r * ld + k] : 0.0; }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { const int c = tx + 16 * q; vv[q] = (c < kp) ? T.X[k * ldx + c] : 0.0; }
-#pragma unroll
-        for (int m = 0; m < 8; ++m)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[m][q] = fma(wv[m], vv[q], acc[m][q]);
+      for (int n = 0; n < MAXT; ++n) {
+        const int t = warp + TIPS_WARPS * n;
+        acc[n] = make_double2(0.0, 0.0);
+        if (t < KT * KT) {
+          const int I = t / KT, J = t - I * KT;
+          acc[n] = make_double2((I == J && g == 2 * tq) ? 1.0 : 0.0, (I == J && g == 2 * tq + 1) ? 1.0 : 0.0);
+          for (int q = 0; q < KT; ++q) {
+            const double2 wv = *reinterpret_cast<const double2*>(T.M + ((size_t)I * KT + q) * 64 + 2 * lane);
+            const double* vt = T.X + ((size_t)q * KT + J) * 64;
+            const double2 vv = make_double2(vt[16 * tq + g], vt[16 * tq + g + 8]);   // C fragment of V(q,J)^T
+            dmma_cc(acc[n], neg2(wv), vv);
+          }
+        }
       }
       __syncthreads();
 #pragma unroll
-      for (int m = 0; m < 8; ++m)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = ty + 16 * m, c = tx + 16 * q;
-          if (r < kp && c < kp) { T.M[r * ld + c] = ((r == c) ? 1.0 : 0.0) - acc[m][q]; T.X[r * ldx + c] = (r == c) ? 1.0 : 0.0; }
-        }
+      for (int n = 0; n < MAXT; ++n) {
+        const int t = warp + TIPS_WARPS * n;
+        if (t < KT * KT) *reinterpret_cast<double2*>(T.M + (size_t)t * 64 + 2 * lane) = acc[n];
+      }
     } else {
-      for (int r = ty; r < kp; r += 16) {
-        const double* wr = W + (size_t)r * kp;
-        for (int c = tx; c < kp; c += 16) {
-          double s0 = (r == c) ? 1.0 : 0.0, s1 = 0.0;
-          int q = 0;
-          for (; q + 1 < kp; q += 2) { s0 = fma(-wr[q], V[(size_t)q * kp + c], s0); s1 = fma(-wr[q + 1], V[(size_t)(q + 1) * kp + c], s1); }
-          for (; q < kp; ++q) s0 = fma(-wr[q], V[(size_t)q * kp + c], s0);
-          T.M[r * ld + c] = s0 + s1;
+      // wide tips: operands straight from global memory (L2): W tiles as they are, V tiles transposed
+      for (int t = warp; t < KT * KT; t += TIPS_WARPS) {
+        const int I = t / KT, J = t - I * KT;
+        double2 acc = make_double2((I == J && g == 2 * tq) ? 1.0 : 0.0, (I == J && g == 2 * tq + 1) ? 1.0 : 0.0);
+        for (int q = 0; q < KT; ++q) {
+          const double2 wv = *reinterpret_cast<const double2*>(W + (size_t)(8 * I + g) * kp + 8 * q + 2 * tq);
+          const double* vt = V + (size_t)(8 * q) * kp + 8 * J;      // C fragment of V(q,J)^T: rows 2tq, 2tq+1, column g
+          const double2 vv = make_double2(vt[(size_t)(2 * tq) * kp + g], vt[(size_t)(2 * tq + 1) * kp + g]);
+          dmma_cc(acc, neg2(wv), vv);
         }
-        for (int cc = tx; cc < nc; cc += 16) T.X[r * ldx + cc] = (r == c0 + cc) ? 1.0 : 0.0;
+        *reinterpret_cast<double2*>(T.M + ((size_t)I * KT + J) * 64 + 2 * lane) = acc;
       }
     }
     __syncthreads();
-    dense_solve_smem(T.M, T.X, ld, kp, nc, ldx, T.Dv, a.thr);
-    for (int r = ty; r < kp; r += 16)
-      for (int cc = tx; cc < nc; cc += 16) out[(size_t)r * kp + c0 + cc] = T.X[r * ldx + cc];
+    for (int e = threadIdx.x; e < KT * ktx * 32; e += blockDim.x) {   // right-hand side: identity columns of this pass
+      const int pr = e & 31, t = e >> 5;
+      const int I = t / ktx, Jl = t - I * ktx;
+      const int r = pr >> 2, c = (pr & 3) * 2;
+      const bool dg = (Jl < nct) && (I == c0t + Jl);
+      *reinterpret_cast<double2*>(T.X + ((size_t)I * ktx + Jl) * 64 + 2 * pr) = make_double2((dg && r == c) ? 1.0 : 0.0, (dg && r == c + 1) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    dense_solve_tiles(T, KT, ktx, nullptr, a.thr);
+    store_tiles(out, kp, T.X, ktx, KT, c0t, nct);
     __syncthreads();
   }
 }
-
-static size_t tips_smem(int kp) { return sizeof(double) * ((size_t)kp * (kp + 1) + (size_t)kp * (tip_pass_cols(kp) + 1) + 64) + 64; }
 
 // Spike tips for this rank.  Interface i couples partition i (bottom) with partition i+1 (top);
 // interface P-1 is the boundary with the right-neighbour rank (its W^(t) arrives in c->remoteWt).
@@ -255,7 +269,7 @@ static size_t tips_smem(int kp) { return sizeof(double) * ((size_t)kp * (kp + 1)
 int spk_launch_tips(spk_ctx* c, int what, int unused) {
   (void)unused;
   const int kp = c->kp, P = c->P;
-  const size_t smem = tips_smem(kp);
+  const size_t smem = tips_smem(c->L.kt);
   SPK_CUDA(c, cudaFuncSetAttribute(k_spike_tip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SPK_CUDA(c, cudaFuncSetAttribute(k_reduced_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const bool has_left = c->opts.rank > 0, has_right = c->opts.rank + 1 < c->opts.nranks;
