@@ -287,11 +287,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     {
       const double2 xc = *reinterpret_cast<const double2*>(&S.XC[slot][2 * lane]);
       dmma_cc(w, ut, xc);                        // Ub^T = U^T X^T
-      if (!REV && s + cj < T) {
-        double2 ub = make_double2(0.0, 0.0);
-        dmma_cc(ub, xc, ut);                     // Ub = X U, the stored factor
-        stT(pf - KT * RS, ub);
-      }
+      if (!REV && s + cj < T) stT(pf - KT * RS, cfrag_transpose(w, g, tq));   // Ub, the stored factor
     }
     if (warp == 0) LU_TR(2);
     // ---------------- trailing update of the column: A~(s+i, c) -= A~(s+i, s) Ub(s, c) ----------------

@@ -151,12 +151,10 @@ __device__ __forceinline__ float2 gj8_f32_cfrag(const double2& d, int g, int tq)
 // squares per step; stops once the next update is below fp64 round-off.  false: the iteration does not contract.
 __device__ __forceinline__ bool ns_refine8(const double2& d, const double2& dt, double2& x, double2& xt, int g, int tq) {
   const double2 eye = make_double2(g == 2 * tq ? 1.0 : 0.0, g == 2 * tq + 1 ? 1.0 : 0.0);
-  const double2 ndt = neg2(dt);
 #pragma unroll 1
   for (int it = 0; it < 7; ++it) {
-    double2 r = eye, rt = eye;
-    dmma_cc(r, neg2(x), dt);                          // R   = I - X D
-    dmma_cc(rt, ndt, x);                              // R^T = I - D^T X^T
+    double2 r = eye;
+    dmma_cc(r, neg2(x), dt);                          // R = I - X D
     // residual entries: all < 2^-28 -> this update is the last one; any >= 2^-4 at the start -> not contracting
     const bool big = mag_ge_pow2(r.x, -28) || mag_ge_pow2(r.y, -28);
     const bool huge = mag_ge_pow2(r.x, -4) || mag_ge_pow2(r.y, -4);
@@ -164,8 +162,8 @@ __device__ __forceinline__ bool ns_refine8(const double2& d, const double2& dt, 
     if (mhuge != 0u && (it == 0 || it == 6)) return false;
     const double2 xto = xt;
     dmma_cc(x, r, xto);                               // X   += R X
-    dmma_cc(xt, xto, r);                              // X^T += X^T R^T
     if (mbig == 0u) return true;
+    dmma_cc(xt, xto, r);                              // X^T += X^T R^T   (operand of the next iteration)
   }
   return false;
 }
