@@ -165,6 +165,53 @@ def test_boosting_counts_zero_pivots(spk, oracle):
     S.close()
 
 
+@pytest.mark.parametrize("kind", ["second_difference", "weak_rows"])
+def test_pivot_block_inverse_tiers(spk, oracle, kind):
+    """The LU kernel inverts 8x8 pivot blocks by Newton-Schulz on the tensor cores, started from a Jacobi
+    iterate; blocks that are not diagonally dominant must fall through to the FP32 Gauss-Jordan start (and,
+    for tiny pivots, to the exact FP64 Gauss-Jordan) and still reproduce the no-pivot LU of the reference
+    path (oracle.band_lu / oracle.block_lu)."""
+    n = 4096
+    if kind == "second_difference":      # tridiag(-1, 2, -1) inside a K=9 band: |offdiag|/|diag| = 1/2 in every block
+        k = 9
+        a = np.zeros((n, 2 * k + 1))
+        a[:, k] = 2.0
+        a[1:, k - 1] = -1.0
+        a[:-1, k + 1] = -1.0
+    else:                                # random band, rows only weakly dominant (delta = 0.35 of the off-diagonal sum)
+        k = 20
+        a = oracle.gen_band(n, k, delta=0.35, seed=7)
+    wide, nb, kw = oracle.block_lu(a)
+    S = spk.Spike(partitions=1, tip_tiles=-1)
+    S.set_band_dense(a, k)
+    S.factor()
+    f = S.get_band_rows()
+    ref = wide[:, kw - k:kw + k + 1]
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(f - ref).max() <= 1e-9 * scale, np.abs(f - ref).max() / scale
+    lu, _ = oracle.band_lu(a)
+    u = oracle.gen_vec(n, 11)
+    b = oracle.band_mult(a, u)
+    xref = oracle.band_solve(lu, b)
+    assert relerr(S.solve(b), xref) < 1e-9
+    S.close()
+
+
+@pytest.mark.parametrize("n,k,P,tip", [(40_000, 100, 8, 0), (30_000, 64, 6, -1), (30_001, 117, 5, -1), (20_000, 128, 4, 0)])
+def test_two_column_lu_variant(spk, oracle, monkeypatch, n, k, P, tip):
+    """csrc/lu2.cu (two window columns per warp, opt-in through SPK_LU_TWOCOL) computes the same factorisation."""
+    monkeypatch.setenv("SPK_LU_TWOCOL", "1")
+    a = oracle.gen_band(n, k)
+    lu, _ = oracle.band_lu(a)
+    S = spk.Spike(partitions=P, tip_tiles=tip)
+    S.set_band_dense(a, k)
+    S.factor()
+    u = oracle.gen_vec(n, 3)
+    b = oracle.band_mult(a, u)
+    assert relerr(S.solve(b), oracle.band_solve(lu, b)) < RTOL
+    S.close()
+
+
 def test_error_paths(spk, oracle):
     S = spk.Spike()
     with pytest.raises(spk.SpikeError):
