@@ -94,24 +94,50 @@ __device__ void dense_solve_tiles(const TipSmem& T, int kt, int ktx, const int* 
       *reinterpret_cast<double2*>(tile + 2 * lane) = acc;
       *reinterpret_cast<double2*>(T.Dv + ((k + 1) & 1) * 64 + 2 * lane) = tip_invert8(acc, g, tq, thr, rthr);
     } else {
+      // flattened (row, item) pairs dealt round-robin to the warps; (ri, it) advance incrementally, two pairs per
+      // trip so that two independent accumulations are in flight
       const int nitem = nm + ktx;
-      const int total = (kt - 1) * nitem;
       const int w0 = look ? warp - 1 : warp, nw = look ? TIPS_WARPS - 1 : TIPS_WARPS;
-      int Iprev = -1;
-      double2 a = make_double2(0.0, 0.0);
-      for (int w = w0; w < total; w += nw) {
-        const int ri = w / nitem, it = w - ri * nitem;
-        const int I = ri < k ? ri : ri + 1;
-        const bool ism = it < nm;
-        const int J = ism ? k + 1 + it : it - nm;
-        if (!ism && xfirst && xfirst[J] > k) continue;
-        if (look && ism && I == k + 1 && J == k + 1) continue;               // the lookahead warp's tile
-        if (I != Iprev) { a = neg2(*reinterpret_cast<const double2*>(T.M + ((size_t)I * kt + k) * 64 + 2 * lane)); Iprev = I; }
-        double* tile = ism ? T.M + ((size_t)I * kt + J) * 64 : T.X + ((size_t)I * ktx + J) * 64;
-        double2 acc = *reinterpret_cast<const double2*>(tile + 2 * lane);
-        const double2 b = *reinterpret_cast<const double2*>(T.PT + (size_t)it * 64 + 2 * lane);
-        dmma_cc(acc, a, b);                                                  // T(I,J) -= M(I,k) T'(k,J)
-        *reinterpret_cast<double2*>(tile + 2 * lane) = acc;
+      int ri = 0, it = w0;
+      while (it >= nitem) { it -= nitem; ++ri; }
+      const int nrow = kt - 1;
+      auto item_live = [&](int ri_, int it_) -> bool {
+        if (ri_ >= nrow) return false;
+        const bool ism = it_ < nm;
+        const int J = ism ? k + 1 + it_ : it_ - nm;
+        if (!ism && xfirst && xfirst[J] > k) return false;
+        const int I = ri_ < k ? ri_ : ri_ + 1;
+        if (look && ism && I == k + 1 && J == k + 1) return false;           // the lookahead warp's tile
+        return true;
+      };
+      auto item_tile = [&](int ri_, int it_) -> double* {
+        const int I = ri_ < k ? ri_ : ri_ + 1;
+        return it_ < nm ? T.M + ((size_t)I * kt + k + 1 + it_) * 64 : T.X + ((size_t)I * ktx + it_ - nm) * 64;
+      };
+      while (ri < nrow) {
+        int ri2 = ri, it2 = it + nw;
+        while (it2 >= nitem) { it2 -= nitem; ++ri2; }
+        const bool l1 = item_live(ri, it), l2 = item_live(ri2, it2);
+        double* t1 = item_tile(ri, it);
+        double* t2 = item_tile(ri2 < nrow ? ri2 : ri, ri2 < nrow ? it2 : it);
+        const int I1 = ri < k ? ri : ri + 1, I2 = (ri2 < nrow ? (ri2 < k ? ri2 : ri2 + 1) : I1);
+        double2 a1, a2, c1, c2, b1, b2;
+        if (l1) {
+          a1 = neg2(*reinterpret_cast<const double2*>(T.M + ((size_t)I1 * kt + k) * 64 + 2 * lane));
+          c1 = *reinterpret_cast<const double2*>(t1 + 2 * lane);
+          b1 = *reinterpret_cast<const double2*>(T.PT + (size_t)it * 64 + 2 * lane);
+        }
+        if (l2) {
+          a2 = neg2(*reinterpret_cast<const double2*>(T.M + ((size_t)I2 * kt + k) * 64 + 2 * lane));
+          c2 = *reinterpret_cast<const double2*>(t2 + 2 * lane);
+          b2 = *reinterpret_cast<const double2*>(T.PT + (size_t)it2 * 64 + 2 * lane);
+        }
+        if (l1) dmma884(c1.x, c1.y, a1.x, b1.x);
+        if (l2) dmma884(c2.x, c2.y, a2.x, b2.x);
+        if (l1) { dmma884(c1.x, c1.y, a1.y, b1.y); *reinterpret_cast<double2*>(t1 + 2 * lane) = c1; }   // T(I,J) -= M(I,k) T'(k,J)
+        if (l2) { dmma884(c2.x, c2.y, a2.y, b2.y); *reinterpret_cast<double2*>(t2 + 2 * lane) = c2; }
+        ri = ri2; it = it2 + nw;
+        while (it >= nitem) { it -= nitem; ++ri; }
       }
     }
     __syncthreads();
