@@ -225,6 +225,8 @@ class Spike:
         self._ck(lib().spk_tip_size(self._h, C.byref(kp)), "spk_tip_size")
         return kp.value
 
+    overlapped_factor = True   # supports factor phases 10/11 (W^(t) exchange overlapped with the band LU)
+
     def factor_phase(self, phase: int):
         self._ck(lib().spk_factor_phase(self._h, phase), f"spk_factor_phase({phase})")
 

@@ -330,7 +330,7 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
   int rc = SPK_OK;
   if (phase == 0) {
     if (c->factored) { SPK_SET_ERR(c, "band already factored (factorisation is in place)"); return SPK_ERR_STATE; }
-    c->launches = 0;
+    c->launches = 0; c->have_remote_wt = 0; c->boundary_done = 0;
     SPK_CUDA(c, cudaMemsetAsync(c->d_boost, 0, sizeof(int64_t), c->stream));
     SPK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     // W^(t) needs the unfactored top windows: UL pass first (read only), then the in-place LU
@@ -339,18 +339,40 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
     if (rc) return rc;
     return SPK_OK;
   }
+  if (phase == 10) {   // overlapped protocol, step 1: tip windows and -- if a left neighbour exists -- my first W^(t)
+    if (c->factored) { SPK_SET_ERR(c, "band already factored (factorisation is in place)"); return SPK_ERR_STATE; }
+    c->launches = 0; c->have_remote_wt = 0; c->boundary_done = 0;
+    SPK_CUDA(c, cudaMemsetAsync(c->d_boost, 0, sizeof(int64_t), c->stream));
+    SPK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    STAGE_BEGIN(c, 0);
+    rc = spk_launch_ul_tips(c);
+    if (rc == SPK_OK && c->opts.rank > 0) rc = spk_launch_tips(c, 2, 0);
+    STAGE_END(c, 0);
+    return rc;
+  }
+  if (phase == 11) {   // step 2: the band LU (the W^(t) exchange travels meanwhile)
+    STAGE_BEGIN(c, 1); rc = spk_launch_lu(c); STAGE_END(c, 1);
+    return rc;
+  }
   if (phase == 1) {
-    STAGE_BEGIN(c, 2); rc = spk_launch_tips(c, 0, 0); STAGE_END(c, 2);
+    // local tips and reduced blocks; the boundary block rides along when the neighbour's W^(t) is already here
+    const bool has_right = c->opts.rank + 1 < c->opts.nranks;
+    const bool with_boundary = has_right && c->have_remote_wt;
+    STAGE_BEGIN(c, 2); rc = spk_launch_tips(c, with_boundary ? 3 : 0, 0); STAGE_END(c, 2);
     if (rc) return rc;
-    if (c->opts.rank + 1 >= c->opts.nranks) {   // no right neighbour: done
+    if (with_boundary) c->boundary_done = 1;
+    if (!has_right || with_boundary) {
       SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
       c->factored = 1; c->timed_factor = 1;
     }
     return SPK_OK;
   }
   if (phase == 2) {  // after SPK_BND_REMOTE_WT has been set
-    rc = spk_launch_tips(c, 1, 0);
-    if (rc) return rc;
+    if (!c->boundary_done) {
+      rc = spk_launch_tips(c, 1, 0);
+      if (rc) return rc;
+      c->boundary_done = 1;
+    }
     SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     c->factored = 1; c->timed_factor = 1;
     return SPK_OK;
@@ -568,6 +590,7 @@ extern "C" int spk_set_boundary(spk_ctx* c, int which, const double* buf) {
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   SPK_CUDA(c, cudaMemcpyAsync(p, buf, sizeof(double) * n, c->opts.mem == SPK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   if (c->opts.mem != SPK_MEM_DEVICE) SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (which == SPK_BND_REMOTE_WT) c->have_remote_wt = 1;
   return SPK_OK;
 }
 

@@ -69,7 +69,8 @@ struct spk_ctx {
   double *remoteWt, *remoteGtop, *remoteXbot, *xtopRemote, *xbBoundary;
   double *haloL, *haloR; // MatMult halos (8*kt entries of the neighbours' x)
   double *cur_x;       // output vector of the solve in progress (split-phase)
-  int have_remote_wt;
+  int have_remote_wt;  // the right neighbour's W^(t) has been set for the factorisation in progress
+  int boundary_done;   // the boundary reduced block has been factored
   // operator for Krylov
   CsrDev opA;
   // bookkeeping

@@ -292,6 +292,9 @@ __global__ void __launch_bounds__(TIPS_THREADS) k_reduced_factor(const RedArgs a
 // interface P-1 is the boundary with the right-neighbour rank (its W^(t) arrives in c->remoteWt).
 //   what = 0: every local tip and local reduced block
 //   what = 1: only the boundary reduced block (after remoteWt has been set)
+//   what = 2: only W^(t) of my first partition (needs the tip windows, not the band LU: sent to the left
+//             neighbour while the LU runs)
+//   what = 3: like 0, and the boundary reduced block in the same launch (remoteWt already set)
 int spk_launch_tips(spk_ctx* c, int what, int unused) {
   (void)unused;
   const int kp = c->kp, P = c->P;
@@ -311,6 +314,13 @@ int spk_launch_tips(spk_ctx* c, int what, int unused) {
   }
   TipArgs t;
   t.band = c->band; t.L = c->L; t.pstart = c->d_pstart; t.thr = c->opts.boost_rel * c->anorm_max;
+  if (what == 2) {
+    if (!has_left) return SPK_OK;
+    t.S = c->St; t.out = c->Wt; t.first_part = 0; t.which = 1;
+    k_spike_tip<<<1, TIPS_THREADS, smem, c->stream>>>(t);
+    SPK_KERNEL_CHECK(c);
+    return SPK_OK;
+  }
   // V^(b) of partitions 0..P-2 (+ P-1 when a right neighbour exists)
   const int nvb = (P - 1) + (has_right ? 1 : 0);
   if (nvb > 0) {
@@ -325,9 +335,10 @@ int spk_launch_tips(spk_ctx* c, int what, int unused) {
     k_spike_tip<<<P - wfirst, TIPS_THREADS, smem, c->stream>>>(t);
     SPK_KERNEL_CHECK(c);
   }
-  if (P - 1 > 0) {
-    r.first_iface = 0; r.remote_iface = -1;
-    k_reduced_factor<<<P - 1, TIPS_THREADS, smem, c->stream>>>(r);
+  const int nred = (P - 1) + ((what == 3 && has_right) ? 1 : 0);   // interface P-1 = boundary with the right rank
+  if (nred > 0) {
+    r.first_iface = 0; r.remote_iface = (what == 3 && has_right) ? P - 1 : -1;
+    k_reduced_factor<<<nred, TIPS_THREADS, smem, c->stream>>>(r);
     SPK_KERNEL_CHECK(c);
   }
   return SPK_OK;

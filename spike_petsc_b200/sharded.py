@@ -45,6 +45,18 @@ class ShardedSpike:
             for req in td.batch_isend_irecv(ops):
                 req.wait()
 
+    def _shift_start(self, send_buf, recv_buf, direction: int):
+        """Like _shift, but returns the pending requests instead of waiting for them."""
+        import torch.distributed as td
+        ops = []
+        dst = self.rank + direction
+        src = self.rank - direction
+        if 0 <= dst < self.world:
+            ops.append(td.P2POp(td.isend, send_buf, dst))
+        if 0 <= src < self.world:
+            ops.append(td.P2POp(td.irecv, recv_buf, src))
+        return td.batch_isend_irecv(ops) if ops else []
+
     def _alloc(self, like):
         import torch
         kp = self.e.tip_size()
@@ -61,16 +73,32 @@ class ShardedSpike:
             self._alloc(like)
         b = self._bufs
         has_left, has_right = self.rank > 0, self.rank + 1 < self.world
-        self.e.factor_phase(0)
+        if self.world == 1 or not getattr(self.e, "overlapped_factor", False):
+            self.e.factor_phase(0)
+            self.e.factor_phase(1)
+            if self.world > 1:
+                if has_left:
+                    self.e.get_boundary(capi.BND_WT_FIRST, self._ptr(b["wt_out"]))
+                self._sync(like)
+                self._shift(b["wt_out"], b["wt_in"], -1)
+                if has_right:
+                    self.e.set_boundary(capi.BND_REMOTE_WT, self._ptr(b["wt_in"]))
+                    self.e.factor_phase(2)
+            return
+        # overlapped protocol: W^(t) of my first partition only needs the tip windows, so it travels to the
+        # left neighbour on the NCCL stream while the band LU runs on the compute stream
+        self.e.factor_phase(10)
+        if has_left:
+            self.e.get_boundary(capi.BND_WT_FIRST, self._ptr(b["wt_out"]))
+        reqs = self._shift_start(b["wt_out"], b["wt_in"], -1)
+        self.e.factor_phase(11)
+        for req in reqs:
+            req.wait()
+        if has_right:
+            self.e.set_boundary(capi.BND_REMOTE_WT, self._ptr(b["wt_in"]))
         self.e.factor_phase(1)
-        if self.world > 1:
-            if has_left:
-                self.e.get_boundary(capi.BND_WT_FIRST, self._ptr(b["wt_out"]))
-            self._sync(like)
-            self._shift(b["wt_out"], b["wt_in"], -1)
-            if has_right:
-                self.e.set_boundary(capi.BND_REMOTE_WT, self._ptr(b["wt_in"]))
-                self.e.factor_phase(2)
+        if has_right:
+            self.e.factor_phase(2)
 
     def solve(self, bvec, xvec):
         """bvec, xvec: this rank's rows of b and x (tensors on the rank's device; may alias)."""

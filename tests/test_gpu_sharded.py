@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(spk, oracle, n, k, R, parts, tip, delta=1.2):
+def _run(spk, oracle, n, k, R, parts, tip, delta=1.2, overlapped=False):
     import torch
     from spike_petsc_b200 import capi
     bounds = spk.shard_rows(n, R)
@@ -34,14 +34,28 @@ def _run(spk, oracle, n, k, R, parts, tip, delta=1.2):
     y = np.concatenate([t.cpu().numpy() for t in ys])
     assert np.linalg.norm(y - bfull) / np.linalg.norm(bfull) < 1e-14
     # ---- factor with the W^(t) exchange
-    for e in E:
-        e.factor_phase(0); e.factor_phase(1)
     wt = [torch.zeros(kp * kp, dtype=torch.float64, device=dev) for _ in range(R)]
-    for r in range(1, R):
-        E[r].get_boundary(capi.BND_WT_FIRST, wt[r].data_ptr())
-    for r in range(R - 1):
-        E[r].set_boundary(capi.BND_REMOTE_WT, wt[r + 1].data_ptr())
-        E[r].factor_phase(2)
+    if not overlapped:
+        for e in E:
+            e.factor_phase(0); e.factor_phase(1)
+        for r in range(1, R):
+            E[r].get_boundary(capi.BND_WT_FIRST, wt[r].data_ptr())
+        for r in range(R - 1):
+            E[r].set_boundary(capi.BND_REMOTE_WT, wt[r + 1].data_ptr())
+            E[r].factor_phase(2)
+    else:   # the order ShardedSpike uses with NCCL: first W^(t) before the LU, boundary block with the local ones
+        for e in E:
+            e.factor_phase(10)
+        for r in range(1, R):
+            E[r].get_boundary(capi.BND_WT_FIRST, wt[r].data_ptr())
+        for e in E:
+            e.factor_phase(11)
+        for r in range(R):
+            if r + 1 < R:
+                E[r].set_boundary(capi.BND_REMOTE_WT, wt[r + 1].data_ptr())
+            E[r].factor_phase(1)
+            if r + 1 < R:
+                E[r].factor_phase(2)
     # ---- solve with the two vector exchanges
     bs = [torch.from_numpy(bfull[bounds[r]:bounds[r + 1]].copy()).to(dev) for r in range(R)]
     xo = [torch.empty_like(b) for b in bs]
@@ -73,3 +87,9 @@ def _run(spk, oracle, n, k, R, parts, tip, delta=1.2):
                                               (30_008, 37, 3, 1, -1), (200_000, 50, 8, 2, 0)])
 def test_sharded_matches_reference_cpu_path(spk, oracle, n, k, R, parts, tip):
     assert _run(spk, oracle, n, k, R, parts, tip) < 1e-10
+
+
+@pytest.mark.parametrize("n,k,R,parts,tip", [(64_000, 100, 4, 3, 0), (30_008, 37, 3, 1, -1), (200_000, 50, 8, 2, 0)])
+def test_sharded_overlapped_factor_protocol(spk, oracle, n, k, R, parts, tip):
+    """factor phases 10/11: the W^(t) exchange overlaps the band LU, the boundary block rides with the local ones."""
+    assert _run(spk, oracle, n, k, R, parts, tip, overlapped=True) < 1e-10
