@@ -152,7 +152,6 @@ int spk_launch_absmax(spk_ctx* c, const double* band, double* out_dev);
 int spk_launch_matmult(spk_ctx* c, const double* band, const double* x, double* y);
 int spk_launch_lu(spk_ctx* c);            // per-partition LU (+ S_b capture, dinv)
 int spk_launch_ul_tips(spk_ctx* c);       // UL window -> S_t
-int spk_launch_lu2(spk_ctx* c, bool rev, int grid, int first_part);  // lu2.cu: two columns per warp (kt >= 8), -1 if out of range
 int spk_launch_tips(spk_ctx* c, int what, int unused);  // 0: local tips + reduced blocks, 1: boundary reduced block
 int spk_launch_rtop_left(spk_ctx* c);
 int spk_launch_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld);   // g = D^-1 b

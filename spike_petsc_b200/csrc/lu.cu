@@ -30,16 +30,15 @@
 //     accumulators are used as they are; the one layout change per warp and step is a register
 //     transposition (shuffles) of the pivot-row tile, which yields Ub^T = U^T X^T (right operand of
 //     every update) and Ub = X U (the stored factor).
-//   * the LOOKAHEAD warp (warp KT) runs the only truly sequential part of the factorisation, the chain
-//     D_t^-1 -> D_t+1 -> D_t+1^-1, privately and ahead of the column warps: as soon as the three tiles
-//     A~(t,t-1), A~(t-1,t), A~(t,t) are final after update(t-2) (they are handed over through shared
-//     memory early in that update) it forms D_t = A~(t,t) - A~(t,t-1) (D_t-1^-1 A~(t-1,t)) and inverts
-//     it ON THE TENSOR CORES: Newton-Schulz X <- X + (I - X D) X carried for X and X^T (every operand a
-//     C fragment in registers, 8 DMMAs per iteration, residual squares per step, stops below fp64
-//     round-off), started from the entry-wise Jacobi iterate (2I - Dg^-1 D) Dg^-1 for diagonally dominant
-//     blocks, else from an FP32 Gauss-Jordan without pivoting on the FP32 pipe, else the exact FP64
-//     Gauss-Jordan with the boosting rule (tiny pivots).  D_t^-1 goes to shared memory (own mbarrier)
-//     and to the diagonal slot of the band.  The column warps never wait for a pivot-block inverse.
+//   * the INVERTER warp (warp KT) owns the only truly sequential part of the factorisation, the pivot-block
+//     inverses.  The owner of the next pivot column updates row s+1 of its column first -- that tile is
+//     D_{s+1} -- and hands it over through shared memory at once; the inverter inverts it ON THE TENSOR CORES
+//     while the column warps run the rest of update(s): Newton-Schulz X <- X + (I - X D) X carried for X and
+//     X^T (every operand a C fragment in registers, no shuffles, residual squares per step, stops below fp64
+//     round-off), started from the entry-wise Jacobi iterate (2I - Dg^-1 D) Dg^-1 for diagonally dominant blocks,
+//     else from an FP32 Gauss-Jordan without pivoting on the FP32 pipe, else the exact FP64 Gauss-Jordan with
+//     the boosting rule (tiny pivots).  D_{s+1}^-1 goes to shared memory (own mbarrier) and to the diagonal
+//     slot of the band; it is normally there before the column warps finish update(s).
 //   * REV=true runs the same elimination on the row/column-reversed matrix (= bottom-up elimination
 //     of the partition's first tipT tile rows) without storing factors: it only yields the top
 //     Schur block S_t needed for the W^(t) spike tip.
@@ -52,11 +51,9 @@ struct LuSmem {
   double PK[LU_R][KT][64];   // package of step s (slot s % LU_R): -A~(s+1+i, s), i = 0..KT-1, row-major
   double XC[LU_R][64];       // D_s^-1, row-major
   double LT[KT][2][64];      // per column warp: optional shared-memory tail of its column (LU_NSM_WIDE rows)
-  double tP[2][64];          // handed over during update(u), buffer u & 1, row-major: A~(u+2, u+1)
-  double tUt[2][64];         //                                                        A~(u+1, u+2)^T
-  double tA[2][64];          //                                                        A~(u+2, u+2)
-  double tAt[2][64];         //                                                        A~(u+2, u+2)^T
-  unsigned long long xfull[LU_R];       // 1 arrival: the lookahead warp has published D_s^-1
+  double tD[2][64];          // next pivot block D_{u+1} = A~(u+1, u+1), handed over early in update(u), buffer u & 1
+  double tDt[2][64];         // its transpose
+  unsigned long long xfull[LU_R];       // 1 arrival: the inverter warp has published D_s^-1
   unsigned long long tfull[LU_R][KT];   // 1 arrival each: package tile j of the slot has been published
   unsigned long long empty[LU_R];   // KT arrivals: every column warp is done with the slot
 };
@@ -68,7 +65,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
   // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived
   // from it (column bookkeeping, running pointers, ring slots) in uniform registers
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const bool is_lookahead = (warp == KT);
+  const bool is_inverter = (warp == KT);
   const int g = lane >> 2, tq = lane & 3;
   const int part = blockIdx.x + (REV ? a.first_part : 0);
   const int64_t t0 = a.pstart[part];
@@ -111,38 +108,23 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
   }
   __syncthreads();
 
-  if (is_lookahead) {
-    // =========================== lookahead warp ===========================================
+  if (is_inverter) {
+    // =========================== inverter warp ============================================
     const double thr = a.boost_thr, rthr = 1.0 / a.boost_thr;
     int nboost = 0;
-    double2 x = make_double2(0.0, 0.0);   // D_{s-1}^-1
-    // step 1 works on raw tiles: fetch them before anybody can overwrite them with factors
-    const double2 p1 = ld_tile(1, 0), a1 = ld_tile(1, 1);
-    const double2 ut1 = cfrag_transpose(ld_tile(0, 1), g, tq), at1 = cfrag_transpose(a1, g, tq);
+    double2 x;
     for (int s = 0; s < T; ++s) {
       LU_TR(8);
       double2 d, dt;
       if (s == 0) {
         d = ld_pair(tptr(0, 0));
         dt = cfrag_transpose(d, g, tq);
-      } else {
-        double2 pc, uct;
-        if (s == 1) {
-          pc = p1; uct = ut1; d = a1; dt = at1;
-        } else {        // final after update(s-2): handed over by their owners early in that update
-          named_bar_sync(LU_BAR_TILES + (s & 1), 96);
-          pc = *reinterpret_cast<const double2*>(&S.tP[s & 1][2 * lane]);
-          uct = *reinterpret_cast<const double2*>(&S.tUt[s & 1][2 * lane]);
-          d = *reinterpret_cast<const double2*>(&S.tA[s & 1][2 * lane]);
-          dt = *reinterpret_cast<const double2*>(&S.tAt[s & 1][2 * lane]);
-        }
-        LU_TRV(9, d.x);
-        // Ub^T = U^T X^T ;  D = A - P Ub ;  D^T = A^T - Ub^T P^T     (X = D_{s-1}^-1)
-        double2 ubt = make_double2(0.0, 0.0);
-        dmma_cc(ubt, uct, x);
-        dmma_cc(d, neg2(pc), ubt);
-        dmma_cc(dt, neg2(ubt), pc);
+      } else {   // D_s: the first tile the owner of column s updated in step s-1, handed over at once
+        named_bar_sync(LU_BAR_TILES + ((s - 1) & 1), 64);
+        d = *reinterpret_cast<const double2*>(&S.tD[(s - 1) & 1][2 * lane]);
+        dt = *reinterpret_cast<const double2*>(&S.tDt[(s - 1) & 1][2 * lane]);
       }
+      LU_TRV(9, d.x);
       LU_TRV(10, d.x);
       // pivot-block inverse on the tensor cores: Newton-Schulz from (1) the entry-wise Jacobi iterate (diagonally
       // dominant blocks: no elimination at all), else from (2) an FP32 Gauss-Jordan without pivoting on the
@@ -291,18 +273,12 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     }
     if (warp == 0) LU_TR(2);
     // ---------------- trailing update of the column: A~(s+i, c) -= A~(s+i, s) Ub(s, c) ----------------
-    const bool give = (s + 2 < T);
-    // tiles of update(s) the lookahead warp needs for D_{s+2}: t1 = row s+1, t2 = row s+2 of this column
-    auto hand_over = [&](const double2& t1, const double2& t2) {
-      if (jrel == 1) {
-        stT_s(S.tP[s & 1], t2);
-        named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
-      } else if (jrel == (KT > 2 ? 2 : 0)) {
-        stTr_s(S.tUt[s & 1], t1);
-        stTr_s(S.tAt[s & 1], t2);
-        stT_s(S.tA[s & 1], t2);
-        named_bar_arrive(LU_BAR_TILES + (s & 1), 96);
-      }
+    // the owner of the next pivot column hands the next pivot block D_{s+1} (row s+1 of its column, the first
+    // tile it updates) to the inverting warp the moment it is final
+    auto give_d = [&](const double2& t1) {
+      stT_s(S.tD[s & 1], t1);
+      stTr_s(S.tDt[s & 1], t1);
+      named_bar_arrive(LU_BAR_TILES + (s & 1), 64);
     };
     // row s+i of column s+1 goes into package(s+1) as tile i-2 (row s+1 is the next pivot block itself);
     // every tile has its own mbarrier, so the consumers of package(s+1) trail this warp by a tile or two
@@ -352,11 +328,10 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
       dmma884(LU_TILE(i).x, LU_TILE(i).y, af.y, w.y);
       if (i < KT) dmma884(LU_TILE(i + 1).x, LU_TILE(i + 1).y, afn.x, w.x);
       // tile i-1 is final by now (its last DMMA was issued an iteration ago)
-      if (i == 3 && give) hand_over(LU_TILE(1), LU_TILE(2));   // the moment they are final
+      if (i == 1 && own_next) give_d(LU_TILE(1));
       if (i >= 2) pub(i - 1, LU_TILE(i - 1));
       af = afn;
     }
-    if (KT == 2 && give) hand_over(LU_TILE(1), LU_TILE(2));
     pub(KT, fT);
 #undef LU_TILE
     __syncwarp();
@@ -403,12 +378,6 @@ static int launch_lu_kt(spk_ctx* c, int grid, int first_part) {
 template <bool REV>
 static int launch_lu(spk_ctx* c, int grid, int first_part) {
   if (!REV && c->lu_trace && c->L.kt == 13) return launch_lu_kt<13, false, true>(c, grid, first_part);  // tools/lu_trace.py
-  // experimental variant with two window columns per warp (lu2.cu: half the shared-memory traffic per DMMA,
-  // but half the warps to hide latency -- measured slower at KT = 13, see profiles/r01_summary.md)
-  if (c->L.kt >= 8 && getenv("SPK_LU_TWOCOL")) {
-    const int rc = spk_launch_lu2(c, REV, grid, first_part);
-    if (rc != -1) return rc;
-  }
   switch (c->L.kt) {
 #define CASE(K_) case K_: return launch_lu_kt<K_, REV, false>(c, grid, first_part);
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)

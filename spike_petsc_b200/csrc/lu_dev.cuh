@@ -1,5 +1,5 @@
-// lu_dev.cuh -- device helpers shared by the band-LU kernels (lu.cu: one window column per warp,
-// lu2.cu: two window columns per warp): fragment algebra on 8x8 tiles, pivot-block inverses, kernel arguments.
+// lu_dev.cuh -- device helpers shared by the band-LU kernel (lu.cu) and the spike-tip kernels (tips.cu):
+// fragment algebra on 8x8 tiles, pivot-block inverses on the tensor cores, kernel arguments.
 #pragma once
 #include "common.cuh"
 #include <cstdlib>
@@ -9,13 +9,13 @@
 #define LU_NSM_WIDE 0
 #endif
 #define LU_TRACE_STEPS 64
-// optional clock64 trace of CTA 0 (tools/lu_trace.py): [step-100][16]; 0..7 column warp 0, 8..15 lookahead warp
+// optional clock64 trace of CTA 0 (tools/lu_trace.py): [step-100][16]; 0..7 column warp 0, 8..15 inverter warp
 // LU_TRV: stamp once a register value has been produced
 #define LU_TRV(slot, val) do { if (TRACE && blockIdx.x == 0 && s >= 100 && s < 100 + LU_TRACE_STEPS) { double e_; asm volatile("add.f64 %0, %1, %1;" : "=d"(e_) : "d"(val)); if (lane == 0) a.trace[(s - 100) * 16 + (slot)] = clock64() + (e_ == 1.2345e300 ? 1 : 0); } } while (0)
 #define LU_TR(slot) do { if (TRACE && blockIdx.x == 0 && lane == 0 && s >= 100 && s < 100 + LU_TRACE_STEPS) a.trace[(s - 100) * 16 + (slot)] = clock64(); } while (0)
 
 // named barriers 4,5: "the three tiles of update(u) are in shared memory", u even/odd
-// (two producer warps arrive, the lookahead warp syncs)
+// (two producer warps arrive, the inverter warp syncs)
 #define LU_BAR_TILES 4
 
 struct LuArgs {

@@ -56,7 +56,7 @@ __device__ void dense_solve_tiles(const TipSmem& T, int kt, int ktx, const int* 
   const int g = lane >> 2, tq = lane & 3;
   const int l0 = 16 * tq + g;
   const double rthr = 1.0 / thr;
-  // Dv[k & 1] = inverse of the pivot tile of step k.  Warp 0 is the lookahead warp: in step k it first updates
+  // Dv[k & 1] = inverse of the pivot tile of step k.  Warp 0 works one block step ahead: in step k it first updates
   // the NEXT pivot tile M(k+1,k+1) and inverts it while the other warps eliminate the rest of block column k.
   if (warp == 0) {
     const double2 d = *reinterpret_cast<const double2*>(T.M + 2 * lane);
@@ -107,7 +107,7 @@ __device__ void dense_solve_tiles(const TipSmem& T, int kt, int ktx, const int* 
         const int J = ism ? k + 1 + it_ : it_ - nm;
         if (!ism && xfirst && xfirst[J] > k) return false;
         const int I = ri_ < k ? ri_ : ri_ + 1;
-        if (look && ism && I == k + 1 && J == k + 1) return false;           // the lookahead warp's tile
+        if (look && ism && I == k + 1 && J == k + 1) return false;           // warp 0's tile
         return true;
       };
       auto item_tile = [&](int ri_, int it_) -> double* {

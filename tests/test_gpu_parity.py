@@ -197,21 +197,6 @@ def test_pivot_block_inverse_tiers(spk, oracle, kind):
     S.close()
 
 
-@pytest.mark.parametrize("n,k,P,tip", [(40_000, 100, 8, 0), (30_000, 64, 6, -1), (30_001, 117, 5, -1), (20_000, 128, 4, 0)])
-def test_two_column_lu_variant(spk, oracle, monkeypatch, n, k, P, tip):
-    """csrc/lu2.cu (two window columns per warp, opt-in through SPK_LU_TWOCOL) computes the same factorisation."""
-    monkeypatch.setenv("SPK_LU_TWOCOL", "1")
-    a = oracle.gen_band(n, k)
-    lu, _ = oracle.band_lu(a)
-    S = spk.Spike(partitions=P, tip_tiles=tip)
-    S.set_band_dense(a, k)
-    S.factor()
-    u = oracle.gen_vec(n, 3)
-    b = oracle.band_mult(a, u)
-    assert relerr(S.solve(b), oracle.band_solve(lu, b)) < RTOL
-    S.close()
-
-
 def test_error_paths(spk, oracle):
     S = spk.Spike()
     with pytest.raises(spk.SpikeError):

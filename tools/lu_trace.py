@@ -16,12 +16,12 @@ print("cycles/step (col warp 0 S1-enter to S1-enter): mean %.0f min %.0f max %.0
 def seg(a, b): return (t[:, b] - t[:, a]).astype(float)
 print("col warp0:  wait full %.0f | Ub = X U %.0f | update %.0f | publish/load (1 step in KT) %.0f | loop top %.0f" % (
     seg(0, 1).mean(), seg(1, 2).mean(), seg(2, 4).mean(), seg(4, 5).mean(), (t[1:, 0] - t[:-1, 5]).astype(float).mean()))
-print("lookahead:  fp32 GJ %.0f | Newton-Schulz %.0f" % (seg(10, 14).mean(), seg(14, 13).mean()))
-print("lookahead:  wait tiles %.0f | D_s = A - (P X) U %.0f | Gauss-Jordan %.0f | to B fragment + publish %.0f | arrive+store+stage %.0f | iteration %.0f" % (
+print("inverter:   Jacobi start %.0f | Newton-Schulz %.0f" % (seg(10, 14).mean(), seg(14, 13).mean()))
+print("inverter:   wait for D_s %.0f | - %.0f | inverse %.0f | publish %.0f | arrive+store %.0f | iteration %.0f" % (
     seg(8, 9).mean(), seg(9, 10).mean(), seg(10, 13).mean(), seg(13, 11).mean(), seg(11, 12).mean(), np.diff(t[:, 8]).astype(float).mean()))
-print("lookahead lead: D_s^-1 published %.0f cycles before the column warps enter S1(s)" % ((t[:, 0] - t[:, 11]).astype(float).mean()))
+print("D_s^-1 published %.0f cycles before column warp 0 starts waiting for it" % ((t[:, 0] - t[:, 11]).astype(float).mean()))
 if len(sys.argv) > 4:
-    print("step | col warp0: S0 wait  Ub  update  pub  top || lookahead: wait D gj32 ns pub rest")
+    print("step | col warp0: wait  Ub  update  pub  top || inverter: wait - jacobi ns pub rest")
     for i in range(0, 40):
         r = t[i]
         nxt = t[i + 1]
