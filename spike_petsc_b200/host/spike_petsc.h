@@ -22,6 +22,14 @@ PetscErrorCode PCBandedSetMaxHalfBandwith(PC pc, PetscInt kmax);   /* (sic) refe
 PetscErrorCode PCBandedSetNormFraction(PC pc, PetscReal frac);
 PetscErrorCode PCBandedGetInfo(PC pc, PetscInt *k, PetscReal *f, PetscInt *partitions, long long *boosted);
 PetscErrorCode KSPCreate_Reorder(KSP ksp);
+/* on-disk formats of the reference's drivers (matio.c): PETSc binary Mat/Vec (MatLoad, src/testbed2.c:93-96),
+ * MatrixMarket export (src/wbm.c:520-523).  0-based CSR, arrays malloc'd for the caller (SpkFree). */
+int SpkMatLoadBinary(const char *path, int *rows, int *cols, int **ia, int **ja, double **a);
+int SpkMatWriteBinary(const char *path, int rows, int cols, const int *ia, const int *ja, const double *a);
+int SpkVecLoadBinary(const char *path, int *n, double **v);
+int SpkVecWriteBinary(const char *path, int n, const double *v);
+int SpkMatWriteMatrixMarket(const char *path, int rows, int cols, const int *ia, const int *ja, const double *a, int digits);
+void SpkFree(void *p);
 #ifdef __cplusplus
 }
 #endif

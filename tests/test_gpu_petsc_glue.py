@@ -187,3 +187,35 @@ def test_kspreorder_testbed2_flow(glue, oracle, ordering, ksp_type):
     buf = C.create_string_buffer(1024); L.KSPView(ksp, buf, 1024)
     assert buf.value.decode().startswith(f"  reordering type = {ordering}\n")
     L.KSPDestroy(C.byref(ksp))
+
+
+def test_testbed2_from_petsc_binary_file(glue, tmp_path):
+    """src/testbed2.c:93-128 with the matrix coming from a PETSc binary file (MatLoad): file -> CSR -> KSPREORDER +
+    PCBANDED on the GPU -> ||x - u|| (matio.c reads the drivers' on-disk format)."""
+    L = glue
+    ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    L.SpkMatLoadBinary.argtypes = [C.c_char_p, ip, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(dp)]
+    L.SpkMatWriteBinary.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    n, k = 3000, 6
+    A = _problem(n, k, 11); A.sort_indices()
+    path = str(tmp_path / "A.bin").encode()
+    ia0, ja0, a0 = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+    assert L.SpkMatWriteBinary(path, n, n, ia0.ctypes.data, ja0.ctypes.data, a0.ctypes.data) == 0
+    m_, n_ = C.c_int(), C.c_int()
+    ia, ja, a = ip(), ip(), dp()
+    assert L.SpkMatLoadBinary(path, C.byref(m_), C.byref(n_), C.byref(ia), C.byref(ja), C.byref(a)) == 0
+    assert m_.value == n and n_.value == n
+    mat = C.c_void_p()
+    assert L.MatCreateSeqAIJWithArrays(n, ia, ja, a, C.byref(mat)) == 0
+    L.PetscOptionsClear()
+    for name, val in [("-mat_ordering_type", "natural"), ("-reorder_ksp_type", "gmres"), ("-reorder_pc_type", "banded"),
+                      ("-reorder_ksp_rtol", "1e-10"), ("-reorder_pc_banded_kmax", "20"), ("-reorder_pc_banded_frac", "1.0")]:
+        L.PetscOptionsSetValue(name.encode(), val.encode())
+    ksp = C.c_void_p(); L.KSPCreate(C.byref(ksp)); L.KSPCreate_Reorder(ksp)
+    L.KSPSetOperators(ksp, mat, mat)
+    assert L.KSPSetFromOptions(ksp) == 0, L.PetscLastErrorMessage()
+    u = np.ones(n); b = np.ascontiguousarray(A @ u); x = np.zeros(n)
+    vb, vx = _vec(L, b), _vec(L, x)
+    assert L.KSPSolve(ksp, vb, vx) == 0, L.PetscLastErrorMessage()
+    assert np.linalg.norm(x - u) / np.linalg.norm(u) < 1e-8
+    L.KSPDestroy(C.byref(ksp))
