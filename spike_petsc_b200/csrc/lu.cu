@@ -48,13 +48,13 @@
 
 template <int KT>
 struct LuSmem {
-  double PK[LU_R][KT][64];   // package of step s (slot s % LU_R): -A~(s+1+i, s), i = 0..KT-1, row-major
+  double PK[LU_R][KT][64];   // package of step s (slot s % LU_R): A~(s+1+i, s), i = 0..KT-1, row-major (the last one a raw copy)
   double XC[LU_R][64];       // D_s^-1, row-major
   double LT[KT][2][64];      // per column warp: optional shared-memory tail of its column (LU_NSM_WIDE rows)
   double tD[2][64];          // next pivot block D_{u+1} = A~(u+1, u+1), handed over early in update(u), buffer u & 1
   double tDt[2][64];         // its transpose
   unsigned long long xfull[LU_R];       // 1 arrival: the inverter warp has published D_s^-1
-  unsigned long long tfull[LU_R][KT];   // 1 arrival each: package tile j of the slot has been published
+  unsigned long long tfull[LU_R][KT];   // 1 arrival each: group g of package tiles (LU_PUBG tiles) published; [KT-1]: the band-edge tile
   unsigned long long empty[LU_R];   // KT arrivals: every column warp is done with the slot
 };
 
@@ -232,11 +232,11 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
 #pragma unroll
     for (int i = 1; i < KT; ++i) {
       const double2 t = (i < NR) ? accT[i < NR ? i : 0] : *reinterpret_cast<const double2*>(lt + (i < NR ? 0 : i - NR) * 64);
-      stT_s(pk0 + (i - 1) * 64, neg2(t));
+      stT_s(pk0 + (i - 1) * 64, t);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    if (lane < KT) mbar_arrive(tfull_bar(0, lane));
+    if (lane < KT) mbar_arrive(tfull_bar(0, lane));   // (all group barriers and the band-edge one; unused indices are harmless)
     reload_entering(0);
   }
 
@@ -264,12 +264,13 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     // package tiles come through volatile shared-memory loads, one tile ahead of the tensor pipe (the compiler
     // must not hoist a batch of them: the accumulators need the registers)
     const uint32_t pk = smem_u32(&S.PK[slot][0][0] + 2 * lane);
-    double2 afn = lds_v2(pk);   // package tile 0 = -A~(s+1, s)
+    double2 afn = lds_v2(pk);   // package tile 0 = A~(s+1, s)
     double2 w = make_double2(0.0, 0.0);
     {
       const double2 xc = *reinterpret_cast<const double2*>(&S.XC[slot][2 * lane]);
       dmma_cc(w, ut, xc);                        // Ub^T = U^T X^T
       if (!REV && s + cj < T) stT(pf - KT * RS, cfrag_transpose(w, g, tq));   // Ub, the stored factor
+      w = neg2(w);                               // the update subtracts: A~ += A~(.,s) (-Ub); the package holds +A~(.,s)
     }
     if (warp == 0) LU_TR(2);
     // ---------------- trailing update of the column: A~(s+i, c) -= A~(s+i, s) Ub(s, c) ----------------
@@ -284,9 +285,14 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     // every tile has its own mbarrier, so the consumers of package(s+1) trail this warp by a tile or two
     auto pub = [&](int i, const double2& t) {
       if (i >= 2 && own_next) {
-        stT_s(pkn + (i - 2) * 64, neg2(t));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tfull_bar(s + 1, i - 2));
+        stT_s(pkn + (i - 2) * 64, t);
+        if (!REV && s + i < T) stT(pf - (KT - i) * RS, t);   // factor output of the new pivot column
+        // tiles are announced in groups of LU_PUBG (one mbarrier per group: fewer warp syncs + arrivals on the
+        // producer's in-order stream, which everybody else's next step hangs on)
+        if ((i - 2) % LU_PUBG == LU_PUBG - 1 || i - 2 == KT - 2) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tfull_bar(s + 1, (i - 2) / LU_PUBG));
+        }
       }
     };
     // One skewed loop over the 13 tiles of the column (rows s+1 .. s+KT): the second k-chunk of tile i and the
@@ -309,11 +315,12 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
       }
     };
     auto load_operand = [&](int i) -> double2 {   // -A~(s+i, s): package tile i-1; the last one is the raw band-edge copy
-      mbar_wait(tfull_bar(s, i - 1), par);
+      if (i == KT) mbar_wait(tfull_bar(s, KT - 1), par);                                  // the raw band-edge tile
+      else if ((i - 1) % LU_PUBG == 0) mbar_wait(tfull_bar(s, (i - 1) / LU_PUBG), par);   // first tile of a group
       if (i < KT) return lds_v2(pk + (i - 1) * 512);
       double2 ae = lds_v2(smem_u32(&S.PK[slot][KT - 1][REV ? 62 - 2 * lane : 2 * lane]));
       if (REV) ae = make_double2(ae.y, ae.x);
-      return neg2(ae);
+      return ae;
     };
     constexpr int FD = (KT > 6) ? 6 : 2;   // the entering tile is requested FD iterations before its first use
     fetch_tail(1); fetch_tail(2);
@@ -336,14 +343,6 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
 #undef LU_TILE
     __syncwarp();
     if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&S.empty[slot]));   // this warp no longer reads the slot of step s
-    if (!REV && own_next) {   // factor output of the new pivot column, off the critical path
-#pragma unroll
-      for (int i = 2; i < KT; ++i) {
-        const double2 t = (i < NR) ? accT[i < NR ? i : 0] : tl[i < NR ? 0 : i - NR];
-        if (s + i < T) stT(pf - (KT - i) * RS, t);
-      }
-      if (s + KT < T) stT(pf, fT);
-    }
     // window slide
 #pragma unroll
     for (int i = 1; i < NR; ++i) accT[i - 1] = accT[i];

@@ -5,6 +5,9 @@
 #include <cstdlib>
 
 #define LU_R 4            // ring depth of the step packages
+#ifndef LU_PUBG
+#define LU_PUBG 6         // package tiles announced per mbarrier
+#endif
 #ifndef LU_NSM_WIDE
 #define LU_NSM_WIDE 0
 #endif

@@ -27,3 +27,12 @@ if len(sys.argv) > 4:
         nxt = t[i + 1]
         print("%3d | %5d %5d %5d %5d %5d || %5d %5d %5d %5d %5d %5d" % (i, r[1] - r[0], r[2] - r[1], r[4] - r[2], r[5] - r[4], nxt[0] - r[5],
               r[9] - r[8], r[10] - r[9], r[14] - r[10], r[13] - r[14], r[11] - r[13], nxt[8] - r[11]))
+if len(sys.argv) > 4 and sys.argv[4] == "roles":
+    # column warp 0 owns column 0 at step 0: (column - s) mod 13 = (-s) mod 13; it is the next-column owner when that is 1.
+    # trace rows are steps 100..163
+    print("role(jrel) | ready-before-X (wait) | Ub | update | end-of-step work | X_s published relative to warp-0 ready | D_{s+1} at inverter rel. to X_s published")
+    for i in range(0, 60):
+        s = 100 + i
+        jr = (-s) % 13
+        r = t[i]
+        print("%3d jrel=%2d | %5d %5d %5d %5d | %6d | %6d" % (s, jr, r[1] - r[0], r[2] - r[1], r[4] - r[2], r[5] - r[4], r[11] - r[0], t[i + 1][9] - r[11]))
