@@ -288,6 +288,187 @@ __global__ void __launch_bounds__(TIPS_THREADS) k_reduced_factor(const RedArgs a
   }
 }
 
+// ============================================================================================
+// Register-resident variant for kt <= GJ_MAX_KT (the common case; K = 100 -> kt = 13): the same dataflow as the
+// band LU (lu.cu).  One warp per tile COLUMN of the augmented matrix [M | X] keeps its kt tiles in registers as
+// DMMA accumulators for the whole elimination (2*kt warps), one more warp inverts pivot tiles one step ahead.
+// Per block step k the only shared-memory traffic is the broadcast of column k (kt tiles, written once by its
+// owner, read by every live column warp as the left DMMA operand) and of D_k^-1; there are no index loops:
+// the step loop is unrolled, every tile index is a compile-time constant.
+//   live columns at step k:  M columns J > k (J <= k are unit columns by then),  X columns with xfirst <= k
+//   t = D_k^-1 Aug(k,J) (DMMA pair on the register-transposed tile), Aug(I,J) -= Aug(I,k) t for I != k.
+// The owner of column k+1 updates row k+1 first and hands that tile (the next pivot block) to the inverting
+// warp at once, then publishes its finished column for step k+1; one CTA-wide barrier per step.
+#define GJ_MAX_KT 13
+#define GJ_BAR_ALL 1
+#define GJ_BAR_D 4        // named barriers 4,5: pivot tile D_k handed to the inverting warp
+template <int KT>
+struct GjSmem {
+  double PK[2][KT][64];   // column k of the augmented matrix as its owner holds it (tile I = Aug(I,k))
+  double XC[2][64];       // D_k^-1
+  double tD[2][64];       // D_k
+};
+
+// the inverting warp (index 2*KT; it never holds a column: called before any accumulator exists)
+template <int KT>
+__device__ __noinline__ void gj_invert_loop(GjSmem<KT>& S, double thr) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  const double rthr = 1.0 / thr;
+  for (int k = 0; k < KT; ++k) {
+    named_bar_sync(GJ_BAR_D + (k & 1), 64);
+    const double2 d = *reinterpret_cast<const double2*>(&S.tD[k & 1][2 * lane]);
+    *reinterpret_cast<double2*>(&S.XC[k & 1][2 * lane]) = tip_invert8(d, g, tq, thr, rthr);
+    named_bar_sync(GJ_BAR_ALL, (2 * KT + 1) * 32);   // barrier #k
+  }
+}
+
+template <int KT>
+__device__ __forceinline__ void gj_eliminate(GjSmem<KT>& S, double2 (&acc)[KT], int col, int xfirst) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  constexpr int NTHR = (2 * KT + 1) * 32;
+  auto give_d = [&](int k, const double2& t) {
+    *reinterpret_cast<double2*>(&S.tD[k & 1][2 * lane]) = t;
+    named_bar_arrive(GJ_BAR_D + (k & 1), 64);
+  };
+  if (col == 0) {
+    give_d(0, acc[0]);
+#pragma unroll
+    for (int I = 1; I < KT; ++I) *reinterpret_cast<double2*>(&S.PK[0][I][2 * lane]) = acc[I];
+  }
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    named_bar_sync(GJ_BAR_ALL, NTHR);     // barrier #k: column k and D_k^-1 are in shared memory
+    const bool live = (col < KT) ? (col > k) : (k >= xfirst);
+    if (live) {
+      const double2 xc = *reinterpret_cast<const double2*>(&S.XC[k & 1][2 * lane]);
+      const double2 ut = cfrag_transpose(acc[k], g, tq);
+      double2 w = make_double2(0.0, 0.0);
+      dmma_cc(w, ut, xc);                                   // t^T = Aug(k,J)^T D^-T
+      acc[k] = cfrag_transpose(w, g, tq);                   // row k of the column becomes t
+      w = neg2(w);
+      const bool next_owner = (k + 1 < KT) && (col == k + 1);
+      // operand tiles through volatile loads, one tile ahead of the tensor pipe (a hoisted batch would spill)
+      const uint32_t pk = smem_u32(&S.PK[k & 1][0][2 * lane]);
+      double2 avn = lds_v2(pk + ((k + 1) % KT) * 512);
+#pragma unroll
+      for (int ii = 1; ii < KT; ++ii) {
+        const int I = (k + ii) % KT;                        // compile-time after unrolling; row k+1 first
+        const double2 av = avn;
+        if (ii + 1 < KT) avn = lds_v2(pk + ((k + ii + 1) % KT) * 512);
+        dmma_cc(acc[I], av, w);                             // Aug(I,J) -= Aug(I,k) t
+        if (ii == 1 && next_owner) give_d(k + 1, acc[I]);   // the next pivot block is final
+      }
+      if (next_owner) {
+#pragma unroll
+        for (int I = 0; I < KT; ++I)
+          if (I != k + 1) *reinterpret_cast<double2*>(&S.PK[(k + 1) & 1][I][2 * lane]) = acc[I];
+      }
+    }
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__((2 * KT + 1) * 32, 1) k_spike_tip_gj(const TipArgs a) {
+  __shared__ __align__(16) GjSmem<KT> S;
+  const int col = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  constexpr int kp = KT * 8;
+  const int p = blockIdx.x + a.first_part;
+  const double* Sg = a.S + (size_t)p * kp * kp;
+  double* out = a.out + (size_t)p * kp * kp;
+  const int64_t tb = (a.which == 0) ? a.pstart[p + 1] : a.pstart[p];
+  if (col == 2 * KT) { gj_invert_loop<KT>(S, a.thr); return; }
+  double2 acc[KT];
+  int xfirst = 0;
+  const int J = col < KT ? col : col - KT;
+  if (col < KT) {
+#pragma unroll
+    for (int I = 0; I < KT; ++I) acc[I] = *reinterpret_cast<const double2*>(Sg + (size_t)(8 * I + g) * kp + 8 * J + 2 * tq);
+  } else {
+    // right-hand side block straight from the (never overwritten) coupling tiles of the band (see k_spike_tip)
+#pragma unroll
+    for (int I = 0; I < KT; ++I) {
+      double2 v = make_double2(0.0, 0.0);
+      if (a.which == 0) { if (J <= I) v = *reinterpret_cast<const double2*>(a.band + a.L.tile_off(tb - KT + I, tb + J) + 2 * lane); }
+      else              { if (J >= I) v = *reinterpret_cast<const double2*>(a.band + a.L.tile_off(tb + I, tb - KT + J) + 2 * lane); }
+      acc[I] = v;
+    }
+    xfirst = (a.which == 0) ? J : 0;
+  }
+  gj_eliminate<KT>(S, acc, col, xfirst);
+  if (col >= KT) {
+#pragma unroll
+    for (int I = 0; I < KT; ++I) *reinterpret_cast<double2*>(out + (size_t)(8 * I + g) * kp + 8 * J + 2 * tq) = acc[I];
+  }
+}
+
+// Rinv[i] = (I - Wt[i+1] Vb[i])^-1: the M-column warps form their column of I - W V in registers (W staged
+// tile-major in shared memory, the warp's V column transposed in registers), the X-column warps start from the
+// identity (column J lives from block step J on).
+template <int KT>
+__global__ void __launch_bounds__((2 * KT + 1) * 32, 1) k_reduced_factor_gj(const RedArgs a) {
+  extern __shared__ __align__(128) double sm[];
+  GjSmem<KT>& S = *reinterpret_cast<GjSmem<KT>*>(sm);
+  double* Ws = sm + sizeof(GjSmem<KT>) / sizeof(double);
+  const int col = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  constexpr int kp = KT * 8;
+  const int i = blockIdx.x + a.first_iface;
+  const double* V = a.Vb + (size_t)i * kp * kp;
+  const double* W = (i == a.remote_iface) ? a.remoteWt : a.Wt + (size_t)(i + a.wt_part_offset) * kp * kp;
+  double* out = a.Rinv + (size_t)i * kp * kp;
+  load_tiles(Ws, KT, W, kp, KT, 0, KT);
+  named_bar_sync(GJ_BAR_ALL, (2 * KT + 1) * 32);
+  if (col == 2 * KT) { gj_invert_loop<KT>(S, a.thr); return; }
+  double2 acc[KT];
+  const int J = col < KT ? col : col - KT;
+#pragma unroll
+  for (int I = 0; I < KT; ++I) acc[I] = make_double2((I == J && g == 2 * tq) ? 1.0 : 0.0, (I == J && g == 2 * tq + 1) ? 1.0 : 0.0);
+  if (col < KT) {
+#pragma unroll 1
+    for (int q = 0; q < KT; ++q) {
+      const double2 vq = neg2(cfrag_transpose(*reinterpret_cast<const double2*>(V + (size_t)(8 * q + g) * kp + 8 * J + 2 * tq), g, tq));
+#pragma unroll
+      for (int I = 0; I < KT; ++I) dmma_cc(acc[I], *reinterpret_cast<const double2*>(Ws + ((size_t)I * KT + q) * 64 + 2 * lane), vq);
+    }
+  }
+  gj_eliminate<KT>(S, acc, col, col < KT ? 0 : J);
+  if (col >= KT) {
+#pragma unroll
+    for (int I = 0; I < KT; ++I) *reinterpret_cast<double2*>(out + (size_t)(8 * I + g) * kp + 8 * J + 2 * tq) = acc[I];
+  }
+}
+
+template <int KT>
+static void launch_tip_gj(spk_ctx* c, int grid, const TipArgs& t) {
+  k_spike_tip_gj<KT><<<grid, (2 * KT + 1) * 32, 0, c->stream>>>(t);
+}
+template <int KT>
+static cudaError_t launch_red_gj(spk_ctx* c, int grid, const RedArgs& r) {
+  const size_t smem = sizeof(GjSmem<KT>) + sizeof(double) * 64 * KT * KT;
+  cudaError_t e = cudaFuncSetAttribute(k_reduced_factor_gj<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_reduced_factor_gj<KT><<<grid, (2 * KT + 1) * 32, smem, c->stream>>>(r);
+  return cudaSuccess;
+}
+#define GJ_CASES CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+static bool tip_launch(spk_ctx* c, int grid, const TipArgs& t, size_t smem_generic) {
+  switch (c->L.kt) {
+#define CASE(K_) case K_: launch_tip_gj<K_>(c, grid, t); return true;
+    GJ_CASES
+#undef CASE
+    default: k_spike_tip<<<grid, TIPS_THREADS, smem_generic, c->stream>>>(t); return true;
+  }
+}
+static cudaError_t red_launch(spk_ctx* c, int grid, const RedArgs& r, size_t smem_generic) {
+  switch (c->L.kt) {
+#define CASE(K_) case K_: return launch_red_gj<K_>(c, grid, r);
+    GJ_CASES
+#undef CASE
+    default: k_reduced_factor<<<grid, TIPS_THREADS, smem_generic, c->stream>>>(r); return cudaSuccess;
+  }
+}
+
 // Spike tips for this rank.  Interface i couples partition i (bottom) with partition i+1 (top);
 // interface P-1 is the boundary with the right-neighbour rank (its W^(t) arrives in c->remoteWt).
 //   what = 0: every local tip and local reduced block
@@ -308,7 +489,7 @@ int spk_launch_tips(spk_ctx* c, int what, int unused) {
   if (what == 1) {
     if (!has_right) return SPK_OK;
     r.first_iface = P - 1; r.remote_iface = P - 1;
-    k_reduced_factor<<<1, TIPS_THREADS, smem, c->stream>>>(r);
+    SPK_CUDA(c, red_launch(c, 1, r, smem));
     SPK_KERNEL_CHECK(c);
     return SPK_OK;
   }
@@ -317,7 +498,7 @@ int spk_launch_tips(spk_ctx* c, int what, int unused) {
   if (what == 2) {
     if (!has_left) return SPK_OK;
     t.S = c->St; t.out = c->Wt; t.first_part = 0; t.which = 1;
-    k_spike_tip<<<1, TIPS_THREADS, smem, c->stream>>>(t);
+    tip_launch(c, 1, t, smem);
     SPK_KERNEL_CHECK(c);
     return SPK_OK;
   }
@@ -325,20 +506,20 @@ int spk_launch_tips(spk_ctx* c, int what, int unused) {
   const int nvb = (P - 1) + (has_right ? 1 : 0);
   if (nvb > 0) {
     t.S = c->Sb; t.out = c->Vb; t.first_part = 0; t.which = 0;
-    k_spike_tip<<<nvb, TIPS_THREADS, smem, c->stream>>>(t);
+    tip_launch(c, nvb, t, smem);
     SPK_KERNEL_CHECK(c);
   }
   // W^(t) of partitions 1..P-1 (+ 0 when a left neighbour exists)
   const int wfirst = has_left ? 0 : 1;
   if (P - wfirst > 0) {
     t.S = c->St; t.out = c->Wt; t.first_part = wfirst; t.which = 1;
-    k_spike_tip<<<P - wfirst, TIPS_THREADS, smem, c->stream>>>(t);
+    tip_launch(c, P - wfirst, t, smem);
     SPK_KERNEL_CHECK(c);
   }
   const int nred = (P - 1) + ((what == 3 && has_right) ? 1 : 0);   // interface P-1 = boundary with the right rank
   if (nred > 0) {
     r.first_iface = 0; r.remote_iface = (what == 3 && has_right) ? P - 1 : -1;
-    k_reduced_factor<<<nred, TIPS_THREADS, smem, c->stream>>>(r);
+    SPK_CUDA(c, red_launch(c, nred, r, smem));
     SPK_KERNEL_CHECK(c);
   }
   return SPK_OK;
