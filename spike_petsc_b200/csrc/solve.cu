@@ -56,7 +56,7 @@ struct SweepSmem {
 // constant, the loop is straight-line code (4-5 x {tile LDS, y LDS, 2 FMA}) and two shuffles.
 template <int KT, int DIR, int FW>
 __device__ __forceinline__ double far_partial(const double* stage_row, const double* ybase, int lane, int tq) {
-  double acc = 0.0;
+  double acc = 0.0, acc1 = 0.0;   // two accumulation chains
 #pragma unroll
   for (int t = FW; t < KT - 1; t += 3) {
     // forward: stage tile tt (d = tt-KT) multiplies the block solved KT-tt iterations before the target row;
@@ -66,8 +66,9 @@ __device__ __forceinline__ double far_partial(const double* stage_row, const dou
     const double2 tv = *reinterpret_cast<const double2*>(stage_row + tt * 64 + 2 * lane);
     const double2 yp = *reinterpret_cast<const double2*>(ybase - dist * 8 + 2 * tq);
     acc = fma(tv.x, yp.x, acc);
-    acc = fma(tv.y, yp.y, acc);
+    acc1 = fma(tv.y, yp.y, acc1);
   }
+  acc += acc1;
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
   return acc;
@@ -112,24 +113,24 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
   if (threadIdx.x == SW_COPY_THREAD) {
     for (int it = 0; it < SW_NST && it < nrows; ++it) issue(it);
   }
-  int slot = 0;   // ring slot of the current iteration (it % RING)
-  for (int it = 0; it < nrows; ++it) {
-    const unsigned gi = ib + (unsigned)it;
-    if (warp == 0) {
-      // -------- near warp: finish the tile row of this iteration
-      // (the far warps already waited for this stage one iteration ago; only iteration 0 is unseen)
-      const int st = (int)(gi % SW_NST);
-      if (it == 0) mbar_wait(reinterpret_cast<uint64_t*>(&S.full[st]), (gi / SW_NST) & 1u);
+  // iterations for which the right-hand side block came with the bulk copy: [bulk_lo, bulk_hi)
+  // Every role runs its own loop (one CTA barrier per iteration closes all of them).
+  if (warp == 0) {
+    // -------- near warp: finishes the tile row of every iteration; the block solved one iteration ago never
+    // leaves its registers (two shuffles issued before the barrier hand every lane its two entries)
+    mbar_wait(reinterpret_cast<uint64_t*>(&S.full[ib % SW_NST]), (ib / SW_NST) & 1u);   // (the far warps wait for all later stages)
+    int slot = 0;
+    unsigned st = ib % SW_NST;
+    double2 yp = make_double2(0.0, 0.0);
+    for (int it = 0; it < nrows; ++it) {
       const int par = it & 1;
       const int64_t I = rstart + (int64_t)DIR * it;
       double rhs;
       if (rhs_bulk_ok(it)) rhs = S.stage[st][KT + 1][g];
       else rhs = (I * 8 + g < nvalid) ? vin[I * 8 + g] : 0.0;
       const double cg = rhs - (S.farpart[par][0][g] + S.farpart[par][1][g] + S.farpart[par][2][g]);
-      // adjacent tile: forward Lb(I,I-1) is stage tile KT-1 (d=-1); backward Ub(I,I+1) is stage tile 0 (d=+1);
-      // the block solved one iteration ago sits at ring position slot+RING-1 (zero at iteration 0)
+      // adjacent tile: forward Lb(I,I-1) is stage tile KT-1 (d=-1); backward Ub(I,I+1) is stage tile 0 (d=+1)
       const double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 0][2 * lane]);
-      const double2 yp = *reinterpret_cast<const double2*>(&S.ybuf[slot + RING - 1][2 * tq]);
       double part = fma(t.x, yp.x, t.y * yp.y);
       part += __shfl_xor_sync(0xffffffffu, part, 1);
       part += __shfl_xor_sync(0xffffffffu, part, 2);
@@ -143,29 +144,39 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
         yv += __shfl_xor_sync(0xffffffffu, yv, 1);
         yv += __shfl_xor_sync(0xffffffffu, yv, 2);
       }
-      if (tq == 0) { S.ybuf[slot][g] = yv; S.ybuf[slot + RING][g] = yv; sink(I, g, yv); }
-    } else if (warp <= 3) {
-      // -------- far warps: partial sums for the NEXT iteration from blocks solved >= 2 iterations before it
-      const int itn = it + 1;
-      if (itn < nrows) {
-        const unsigned gn = gi + 1u;
-        const int stn = (int)(gn % SW_NST);
+      if (tq == 0) { S.ybuf[slot][g] = yv; S.ybuf[slot + RING][g] = yv; }
+      yp.x = __shfl_sync(0xffffffffu, yv, 8 * tq);
+      yp.y = __shfl_sync(0xffffffffu, yv, 8 * tq + 4);
+      __syncthreads();
+      if (tq == 0) sink(I, g, yv);
+      slot = slot + 1 == RING ? 0 : slot + 1;
+      st = (st + 1) % SW_NST;
+    }
+  } else if (warp <= 3) {
+    // -------- far warps: partial sums for the NEXT iteration from blocks solved >= 2 iterations before it
+    int sn = 1 == RING ? 0 : 1;            // ring slot of iteration it+1
+    unsigned gn = ib + 1u;
+    for (int it = 0; it < nrows; ++it, ++gn) {
+      if (it + 1 < nrows) {
+        const unsigned stn = gn % SW_NST;
         mbar_wait(reinterpret_cast<uint64_t*>(&S.full[stn]), (gn / SW_NST) & 1u);
-        const int sn = slot + 1 == RING ? 0 : slot + 1;   // ring slot of iteration itn
         const double* srow = &S.stage[stn][0][0];
         const double* ybase = &S.ybuf[sn + RING][0];
         double acc;
         if (warp == 1) acc = far_partial<KT, DIR, 0>(srow, ybase, lane, tq);
         else if (warp == 2) acc = far_partial<KT, DIR, 1>(srow, ybase, lane, tq);
         else acc = far_partial<KT, DIR, 2>(srow, ybase, lane, tq);
-        if (tq == 0) S.farpart[itn & 1][warp - 1][g] = acc;
+        if (tq == 0) S.farpart[(it + 1) & 1][warp - 1][g] = acc;
       }
-    } else {
-      // -------- copy warp: refill the stage the near warp finished one iteration ago
-      if (threadIdx.x == SW_COPY_THREAD && it >= 1 && it - 1 + SW_NST < nrows) issue(it - 1 + SW_NST);
+      __syncthreads();
+      sn = sn + 1 == RING ? 0 : sn + 1;
     }
-    __syncthreads();
-    slot = slot + 1 == RING ? 0 : slot + 1;
+  } else {
+    // -------- copy warp: refill the stage the near warp finished one iteration ago
+    for (int it = 0; it < nrows; ++it) {
+      if (threadIdx.x == SW_COPY_THREAD && it >= 1 && it - 1 + SW_NST < nrows) issue(it - 1 + SW_NST);
+      __syncthreads();
+    }
   }
 }
 
