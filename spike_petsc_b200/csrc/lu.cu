@@ -19,10 +19,12 @@
 //   * per 8-pivot step s a column warp scales ITS OWN pivot-row tile, Ub(s,J) = D_s^-1 A~(s,J)
 //     (2 DMMAs), then updates its column A~(I,J) -= A~(I,s) Ub(s,J) (2 DMMAs per tile, issued skewed so
 //     that two accumulation chains are in flight).  The left operands come from the step PACKAGE: the
-//     pivot-column tiles -A~(s+1.., s), published to shared memory by the warp that owns column s
-//     WHILE it updates them during step s-1, one mbarrier per tile: the consumers of package(s) trail
-//     their producer by a tile or two instead of waiting for its whole column.  Packages live in a
-//     4-deep ring; an `empty` mbarrier per slot tells the producer when all column warps have left it.
+//     pivot-column tiles A~(s+1.., s) (the scaled pivot row is negated instead, once per step), published to
+//     shared memory by the warp that owns column s WHILE it updates them during step s-1 and announced in
+//     groups of LU_PUBG tiles (one mbarrier per group): the consumers of package(s) trail their producer by
+//     a few tiles instead of waiting for its whole column.  That owner's update is the critical path of every
+//     step; it also writes the new pivot column's factor tiles as it goes.  Packages live in a 4-deep ring; an
+//     `empty` mbarrier per slot tells the producer when all column warps have left it.
 //   * operand layouts: a DMMA contracts over k, so the SAME permutation of k may be applied to both
 //     operands.  With k = 2*(lane%4)+h for k-chunk h, the left operand of M1*M2 is the accumulator
 //     ("C") fragment of M1 itself and the right operand is the C fragment of M2^T.  Tiles are row-major
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
   int jrel = warp;                   // (column owned) - s, taken mod KT
   double* pf = tptr(KT, warp);       // running pointer: tile (s+KT, c)
 
-  // Package of pivot column sn: tiles 0..KT-2 = -A~(sn+1+j, sn) (logical row-major), tile KT-1 = the band-edge
+  // Package of pivot column sn: tiles 0..KT-2 = A~(sn+1+j, sn) (logical row-major), tile KT-1 = the band-edge
   // tile (sn+KT, sn), which no update ever touched: a RAW copy (stored orientation, not negated) made by cp.async.
   auto stage_edge = [&](int sn, const double* src) {
     double* dst = &S.PK[sn % LU_R][KT - 1][2 * lane];
@@ -282,7 +284,6 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
       named_bar_arrive(LU_BAR_TILES + (s & 1), 64);
     };
     // row s+i of column s+1 goes into package(s+1) as tile i-2 (row s+1 is the next pivot block itself);
-    // every tile has its own mbarrier, so the consumers of package(s+1) trail this warp by a tile or two
     auto pub = [&](int i, const double2& t) {
       if (i >= 2 && own_next) {
         stT_s(pkn + (i - 2) * 64, t);
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
         }
       }
     };
-    auto load_operand = [&](int i) -> double2 {   // -A~(s+i, s): package tile i-1; the last one is the raw band-edge copy
+    auto load_operand = [&](int i) -> double2 {   // A~(s+i, s): package tile i-1; the last one is the raw band-edge copy
       if (i == KT) mbar_wait(tfull_bar(s, KT - 1), par);                                  // the raw band-edge tile
       else if ((i - 1) % LU_PUBG == 0) mbar_wait(tfull_bar(s, (i - 1) / LU_PUBG), par);   // first tile of a group
       if (i < KT) return lds_v2(pk + (i - 1) * 512);
