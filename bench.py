@@ -207,6 +207,7 @@ def run_ours(args):
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        local_ms = ms.item()
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         if it >= args.warmup:
@@ -214,6 +215,15 @@ def run_ours(args):
             stage = eng.view()["stage_ms"]
             lu_ms.append(stage[1])
     clocks = sampler.stop() if rank == 0 else None
+    per_rank = None
+    if world > 1:   # last step, every rank: its own event time, factor / solve split and stage times (where the ranks wait)
+        iv = eng.view()
+        mine = torch.tensor([local_ms, iv["factor_ms"], iv["solve_ms"]] + list(stage[:6]), dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(v, 4) for v in t.tolist()] for t in allr]
+    S.check()                                      # a timed-out mailbox spin would have left garbage in x
+    exchange = "NVLink peer mailboxes (kernel stores + flags, csrc/peer.cu)" if getattr(S, "_peer", False) else "NCCL p2p"
     err = ((x - u).norm() ** 2)
     cnt = torch.tensor([float(n_loc)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -263,7 +273,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "synthetic diagonally dominant band N=10M K=100 fp64, in-place SPIKE factor + solve of b=A*1",
                        "seed": SEED, "delta": DELTA, "partitions_per_gpu": info["partitions"], "tip_tiles": info["tip_tiles"],
-                       "parallelism": f"row-block x{world}, spike-tip exchange over NCCL p2p",
+                       "parallelism": f"row-block x{world}, spike-tip exchange over {exchange}" if world > 1 else "row-block x1",
                        "l2": "inputs (16 GB band) exceed the 126 MB L2; band restored from a pristine copy between steps (untimed)"},
             "rel_err_vs_exact_u": relerr,
             "stage_ms": {"tip_windows": stage[0], "band_lu": stage[1], "spike_tips": stage[2], "sweeps": stage[3],
@@ -273,7 +283,9 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": lu_bytes,
                          "whole_step_frac": (2 * band_alg + band_alg + 32.0 * N_ROWS) / world / (ms * 1e-3) / 1e9 / peak,
                          "fp64_tflops": N_ROWS * (2.0 * K_HALF * K_HALF + K_HALF) / world / (lu * 1e-3) / 1e12},
-            "gpu_launches": info["kernel_launches"] if world == 1 else 8 + 1,
+            "gpu_launches": info["kernel_launches"],
+            "per_rank_ms": {"columns": ["step", "factor", "solve", "tip_windows", "band_lu", "spike_tips", "sweeps", "reduced", "corrections"],
+                            "rows": per_rank} if per_rank else None,
             "clocks": clocks,
             "e2e": e2e if e2e is not None else {"value": None, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                                                 "note": "host-buffer path measured at N=1 only"},

@@ -139,6 +139,26 @@ enum {
 int spk_factor_phase(spk_ctx *ctx, int phase);
 int spk_solve_phase(spk_ctx *ctx, int phase, const double *b, double *x, int nrhs);
 
+/* ---- the same exchanges through NVLink peer memory instead of host-driven NCCL send/recv (csrc/peer.cu).
+ * Every rank owns a mailbox in device memory; neighbours map it with CUDA IPC (the 64-byte handle travels
+ * once, over any host channel), a producer's kernel stores the item straight into the consumer's mailbox and
+ * releases a sequence flag, the consumer's kernel acquires it, moves the item where spk_set_boundary would
+ * have put it and acknowledges.  spk_peer_post(which) replaces spk_get_boundary(which) + send,
+ * spk_peer_wait(which) replaces recv + spk_set_boundary(which); both only enqueue a kernel on the context's
+ * stream (no host synchronisation), so the phase order above is unchanged and the W^(t) exchange overlaps the
+ * band LU by construction.  Replaces, like the hooks above, the VecScatter / MatGetSubMatrices traffic PETSc
+ * would issue for a distributed Mat on this path (src/matbanded.c:141-150 runs the reference on one rank only).
+ *   spk_peer_mailbox_create : allocate my mailbox (after the band is set); handle64 <- cudaIpcMemHandle_t,
+ *                             dev_ptr <- its device address (either may be NULL)
+ *   spk_peer_mailbox_attach : side 0 = left neighbour, 1 = right; pass the neighbour's handle, or its device
+ *                             address when it lives in the same process
+ *   spk_peer_check          : synchronise the stream; SPK_ERR_STATE if a bounded spin (~2 s) expired */
+int spk_peer_mailbox_create(spk_ctx *ctx, void *handle64, void **dev_ptr);
+int spk_peer_mailbox_attach(spk_ctx *ctx, int side, const void *handle64, void *direct_ptr);
+int spk_peer_post(spk_ctx *ctx, int which);   /* which: SPK_BND_WT_FIRST, SPK_BND_G_TOP, SPK_BND_X_BOT */
+int spk_peer_wait(spk_ctx *ctx, int which);   /* which: SPK_BND_REMOTE_WT, SPK_BND_REMOTE_G_TOP, SPK_BND_REMOTE_X_BOT */
+int spk_peer_check(spk_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,11 @@ def lib():
         L.spk_set_boundary.argtypes = [vp, C.c_int, vp]
         L.spk_factor_phase.argtypes = [vp, C.c_int]
         L.spk_solve_phase.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+        L.spk_peer_mailbox_create.argtypes = [vp, vp, C.POINTER(vp)]
+        L.spk_peer_mailbox_attach.argtypes = [vp, C.c_int, vp, vp]
+        L.spk_peer_post.argtypes = [vp, C.c_int]
+        L.spk_peer_wait.argtypes = [vp, C.c_int]
+        L.spk_peer_check.argtypes = [vp]
         _LIB = L
     return _LIB
 
@@ -238,6 +243,29 @@ class Spike:
 
     def set_boundary(self, which: int, buf):
         self._ck(lib().spk_set_boundary(self._h, which, _addr(buf)), f"spk_set_boundary({which})")
+
+    # ---- the same exchanges through NVLink peer memory (csrc/peer.cu)
+    peer_capable = True
+
+    def peer_create(self):
+        """-> (64-byte CUDA IPC handle, device address) of this rank's mailbox."""
+        h = C.create_string_buffer(64)
+        p = C.c_void_p(0)
+        self._ck(lib().spk_peer_mailbox_create(self._h, h, C.byref(p)), "spk_peer_mailbox_create")
+        return bytes(h.raw), p.value
+
+    def peer_attach(self, side: int, handle: bytes = None, ptr: int = None):
+        hb = C.create_string_buffer(handle, 64) if handle is not None else None
+        self._ck(lib().spk_peer_mailbox_attach(self._h, side, hb, C.c_void_p(ptr) if ptr else None), f"spk_peer_mailbox_attach({side})")
+
+    def peer_post(self, which: int):
+        self._ck(lib().spk_peer_post(self._h, which), f"spk_peer_post({which})")
+
+    def peer_wait(self, which: int):
+        self._ck(lib().spk_peer_wait(self._h, which), f"spk_peer_wait({which})")
+
+    def peer_check(self):
+        self._ck(lib().spk_peer_check(self._h), "spk_peer_check")
 
     def view(self) -> dict:
         info = Info()

@@ -31,6 +31,7 @@ static void free_band(spk_ctx* c) {
   F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->xtopRemote); F(c->xbBoundary); F(c->haloL); F(c->haloR);
   F(c->opA.ia); F(c->opA.ja); F(c->opA.a);
   free(c->h_pstart); c->h_pstart = nullptr;
+  spk_peer_release(c);   // the mailbox layout depends on kp
   c->have_band = c->factored = 0;
 }
 
@@ -560,7 +561,7 @@ extern "C" int spk_view(spk_ctx* c, spk_info* info) {
 
 // ---- multi-GPU boundary hooks: buffers follow opts.mem (device pointers in sharded runs) --------
 extern "C" int spk_tip_size(spk_ctx* c, int* kp) { if (!c || !kp) return SPK_ERR_ARG; *kp = c->kp; return SPK_OK; }
-static int bnd_desc(spk_ctx* c, int which, double** ptr, size_t* count, int* is_out) {
+int spk_bnd_desc(spk_ctx* c, int which, double** ptr, size_t* count, int* is_out) {
   const size_t kk = (size_t)c->kp * c->kp, k1 = (size_t)c->kp;
   switch (which) {
     case SPK_BND_WT_FIRST:     *ptr = c->Wt;          *count = kk; *is_out = 1; return 0;  // W^(t) of my partition 0
@@ -577,7 +578,7 @@ static int bnd_desc(spk_ctx* c, int which, double** ptr, size_t* count, int* is_
 extern "C" int spk_get_boundary(spk_ctx* c, int which, double* buf) {
   if (!c || !buf || !c->have_band) return SPK_ERR_ARG;
   double* p; size_t n; int out;
-  if (bnd_desc(c, which, &p, &n, &out) || !out) { SPK_SET_ERR(c, "spk_get_boundary: bad or unavailable item %d", which); return SPK_ERR_ARG; }
+  if (spk_bnd_desc(c, which, &p, &n, &out) || !out) { SPK_SET_ERR(c, "spk_get_boundary: bad or unavailable item %d", which); return SPK_ERR_ARG; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   SPK_CUDA(c, cudaMemcpyAsync(buf, p, sizeof(double) * n, c->opts.mem == SPK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
   if (c->opts.mem != SPK_MEM_DEVICE) SPK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -586,7 +587,7 @@ extern "C" int spk_get_boundary(spk_ctx* c, int which, double* buf) {
 extern "C" int spk_set_boundary(spk_ctx* c, int which, const double* buf) {
   if (!c || !buf || !c->have_band) return SPK_ERR_ARG;
   double* p; size_t n; int out;
-  if (bnd_desc(c, which, &p, &n, &out) || out) { SPK_SET_ERR(c, "spk_set_boundary: bad item %d", which); return SPK_ERR_ARG; }
+  if (spk_bnd_desc(c, which, &p, &n, &out) || out) { SPK_SET_ERR(c, "spk_set_boundary: bad item %d", which); return SPK_ERR_ARG; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   SPK_CUDA(c, cudaMemcpyAsync(p, buf, sizeof(double) * n, c->opts.mem == SPK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   if (c->opts.mem != SPK_MEM_DEVICE) SPK_CUDA(c, cudaStreamSynchronize(c->stream));

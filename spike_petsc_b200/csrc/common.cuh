@@ -71,6 +71,10 @@ struct spk_ctx {
   double *cur_x;       // output vector of the solve in progress (split-phase)
   int have_remote_wt;  // the right neighbour's W^(t) has been set for the factorisation in progress
   int boundary_done;   // the boundary reduced block has been factored
+  // NVLink peer mailboxes (peer.cu): mine, the neighbours' (0 left, 1 right), per-channel sequence numbers
+  double *mbox, *peer_mbox[2];
+  int peer_ipc[2];
+  unsigned long long peer_seq_out[3], peer_seq_in[3];
   // operator for Krylov
   CsrDev opA;
   // bookkeeping
@@ -88,6 +92,9 @@ struct spk_ctx {
   void* lu_trace;           // debug: device buffer for clock64 stamps of the LU kernel (tools only)
   char err[512];
 };
+
+void spk_peer_release(spk_ctx* c);   // peer.cu
+int spk_bnd_desc(spk_ctx* c, int which, double** ptr, size_t* count, int* is_out);   // capi.cu
 
 #define SPK_SET_ERR(ctx, ...) do { if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); } while (0)
 #define SPK_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \

@@ -5,10 +5,16 @@ the same factor / solve kernels on it.  Only the data of the partition interface
 ranks crosses NVLink: one kp x kp spike tip W^(t) per boundary at factor time and two kp-vectors per
 boundary per solve (kp = 8*ceil(K/8)); this replaces the PETSc MPI scatter a distributed Mat/Vec
 would do on that path.  The exchanges are point-to-point `torch.distributed` operations, i.e.
-ncclSend / ncclRecv over NVLink 5 when the backend is NCCL.  The engine argument exists so the
-exchange protocol can be exercised on CPU (gloo) with a reference engine (tests/test_sharded_cpu.py).
+ncclSend / ncclRecv over NVLink 5 when the backend is NCCL -- or, when the engine supports it (the CUDA
+engine does: csrc/peer.cu), stores into the neighbour's mailbox in NVLink peer memory issued by the engine's own
+kernels, with no host round per exchange (the NCCL path stays as the fallback when CUDA IPC is unavailable and
+for SPIKE_B200_PEER=0).  The engine argument exists so the exchange protocol can be exercised on CPU (gloo)
+with a reference engine (tests/test_sharded_cpu.py).
 """
 from __future__ import annotations
+
+import os
+import sys
 
 from . import capi
 
@@ -27,6 +33,56 @@ class ShardedSpike:
         get_boundary, set_boundary, tip_size) created for this rank's row block."""
         self.e, self.rank, self.world, self.dist = engine, rank, world, dist
         self._bufs = None
+        self._peer = None        # None: not decided yet; True: NVLink mailboxes; False: NCCL send/recv
+        self._peer_verified = False
+
+    # ---- NVLink peer mailboxes: every rank creates one, the CUDA IPC handles travel once over the process group
+    def _peer_setup(self):
+        if self._peer is not None:
+            return self._peer
+        self._peer = False
+        if self.world == 1 or not getattr(self.e, "peer_capable", False) or os.environ.get("SPIKE_B200_PEER", "1") == "0":
+            return False
+        td = self.dist
+        if td is None:
+            import torch.distributed as td
+        ok, handle = 1, b""
+        try:
+            handle, _ = self.e.peer_create()
+        except Exception as exc:   # noqa: BLE001 -- any failure means "use NCCL", decided collectively below
+            ok = 0
+            print(f"[spike_b200] rank {self.rank}: no peer mailbox ({exc}); NCCL exchange", file=sys.stderr)
+        got = [None] * self.world
+        td.all_gather_object(got, (ok, handle))
+        if all(g[0] for g in got):
+            try:
+                if self.rank > 0:
+                    self.e.peer_attach(0, handle=got[self.rank - 1][1])
+                if self.rank + 1 < self.world:
+                    self.e.peer_attach(1, handle=got[self.rank + 1][1])
+            except Exception as exc:   # noqa: BLE001
+                ok = 0
+                print(f"[spike_b200] rank {self.rank}: cannot map the neighbour's mailbox ({exc}); NCCL exchange", file=sys.stderr)
+        else:
+            ok = 0
+        agreed = [None] * self.world
+        td.all_gather_object(agreed, ok)
+        self._peer = all(agreed)
+        return self._peer
+
+    def attach_local_peers(self, left_ptr=None, right_ptr=None):
+        """Neighbour shards living in this process (several shards on one GPU): use their mailboxes directly."""
+        self.e.peer_create()
+        if left_ptr:
+            self.e.peer_attach(0, ptr=left_ptr)
+        if right_ptr:
+            self.e.peer_attach(1, ptr=right_ptr)
+        self._peer = True
+
+    def check(self):
+        """Synchronise and raise if a mailbox spin timed out (peer protocol only)."""
+        if self._peer:
+            self.e.peer_check()
 
     # ---- neighbour exchange: send `out` to rank+dir_, receive the matching buffer from rank-dir_
     def _shift(self, send_buf, recv_buf, direction: int):
@@ -73,6 +129,19 @@ class ShardedSpike:
             self._alloc(like)
         b = self._bufs
         has_left, has_right = self.rank > 0, self.rank + 1 < self.world
+        if self.world > 1 and self._peer_setup():
+            # NVLink mailboxes: W^(t) of my first partition is stored into the left neighbour's memory by a kernel
+            # queued before the band LU; the kernel that picks up the right neighbour's W^(t) is queued after it
+            self.e.factor_phase(10)
+            if has_left:
+                self.e.peer_post(capi.BND_WT_FIRST)
+            self.e.factor_phase(11)
+            if has_right:
+                self.e.peer_wait(capi.BND_REMOTE_WT)
+            self.e.factor_phase(1)
+            if has_right:
+                self.e.factor_phase(2)
+            return
         if self.world == 1 or not getattr(self.e, "overlapped_factor", False):
             self.e.factor_phase(0)
             self.e.factor_phase(1)
@@ -106,6 +175,22 @@ class ShardedSpike:
             self._alloc(bvec)
         b = self._bufs
         has_left, has_right = self.rank > 0, self.rank + 1 < self.world
+        if self.world > 1 and self._peer_setup():
+            self.e.solve_phase(0, self._ptr(bvec), self._ptr(xvec))
+            if has_left:
+                self.e.peer_post(capi.BND_G_TOP)
+            if has_right:
+                self.e.peer_wait(capi.BND_REMOTE_G_TOP)
+            self.e.solve_phase(1)
+            if has_right:
+                self.e.peer_post(capi.BND_X_BOT)
+            if has_left:
+                self.e.peer_wait(capi.BND_REMOTE_X_BOT)
+            self.e.solve_phase(2)
+            if not self._peer_verified:   # the first exchange proves the mapping works; later checks are the caller's
+                self.e.peer_check()
+                self._peer_verified = True
+            return xvec
         self.e.solve_phase(0, self._ptr(bvec), self._ptr(xvec))
         if self.world > 1:
             if has_left:

@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(spk, oracle, n, k, R, parts, tip, delta=1.2, overlapped=False):
+def _run(spk, oracle, n, k, R, parts, tip, delta=1.2, overlapped=False, mailbox=False):
     import torch
     from spike_petsc_b200 import capi
     bounds = spk.shard_rows(n, R)
@@ -35,7 +35,28 @@ def _run(spk, oracle, n, k, R, parts, tip, delta=1.2, overlapped=False):
     assert np.linalg.norm(y - bfull) / np.linalg.norm(bfull) < 1e-14
     # ---- factor with the W^(t) exchange
     wt = [torch.zeros(kp * kp, dtype=torch.float64, device=dev) for _ in range(R)]
-    if not overlapped:
+    if mailbox:
+        # NVLink peer mailboxes (csrc/peer.cu); the shards share one stream here, so every post is queued before
+        # the wait that consumes it -- the order the kernels of R processes would reach by spinning
+        ptrs = [e.peer_create()[1] for e in E]
+        for r in range(R):
+            if r > 0:
+                E[r].peer_attach(0, ptr=ptrs[r - 1])
+            if r + 1 < R:
+                E[r].peer_attach(1, ptr=ptrs[r + 1])
+        for e in E:
+            e.factor_phase(10)
+        for r in range(1, R):
+            E[r].peer_post(capi.BND_WT_FIRST)
+        for e in E:
+            e.factor_phase(11)
+        for r in range(R):
+            if r + 1 < R:
+                E[r].peer_wait(capi.BND_REMOTE_WT)
+            E[r].factor_phase(1)
+            if r + 1 < R:
+                E[r].factor_phase(2)
+    elif not overlapped:
         for e in E:
             e.factor_phase(0); e.factor_phase(1)
         for r in range(1, R):
@@ -60,20 +81,39 @@ def _run(spk, oracle, n, k, R, parts, tip, delta=1.2, overlapped=False):
     bs = [torch.from_numpy(bfull[bounds[r]:bounds[r + 1]].copy()).to(dev) for r in range(R)]
     xo = [torch.empty_like(b) for b in bs]
     v = [torch.zeros(kp, dtype=torch.float64, device=dev) for _ in range(R)]
-    for r in range(R):
+    for rep in range(3 if mailbox else 0):   # three solves: both slots of every channel and the ack back-pressure
+        for r in range(R):
+            xo[r].zero_()
+            E[r].solve_phase(0, bs[r].data_ptr(), xo[r].data_ptr())
+        for r in range(1, R):
+            E[r].peer_post(capi.BND_G_TOP)
+        for r in range(R - 1):
+            E[r].peer_wait(capi.BND_REMOTE_G_TOP)
+        for r in range(R):
+            E[r].solve_phase(1)
+        for r in range(R - 1):
+            E[r].peer_post(capi.BND_X_BOT)
+        for r in range(1, R):
+            E[r].peer_wait(capi.BND_REMOTE_X_BOT)
+        for r in range(R):
+            E[r].solve_phase(2)
+        for e in E:
+            e.peer_check()
+    for r in range(R if not mailbox else 0):
         E[r].solve_phase(0, bs[r].data_ptr(), xo[r].data_ptr())
-    for r in range(1, R):
-        E[r].get_boundary(capi.BND_G_TOP, v[r].data_ptr())
-    for r in range(R - 1):
-        E[r].set_boundary(capi.BND_REMOTE_G_TOP, v[r + 1].data_ptr())
-    for r in range(R):
-        E[r].solve_phase(1)
-    for r in range(R - 1):
-        E[r].get_boundary(capi.BND_X_BOT, v[r].data_ptr())
-    for r in range(1, R):
-        E[r].set_boundary(capi.BND_REMOTE_X_BOT, v[r - 1].data_ptr())
-    for r in range(R):
-        E[r].solve_phase(2)
+    if not mailbox:
+        for r in range(1, R):
+            E[r].get_boundary(capi.BND_G_TOP, v[r].data_ptr())
+        for r in range(R - 1):
+            E[r].set_boundary(capi.BND_REMOTE_G_TOP, v[r + 1].data_ptr())
+        for r in range(R):
+            E[r].solve_phase(1)
+        for r in range(R - 1):
+            E[r].get_boundary(capi.BND_X_BOT, v[r].data_ptr())
+        for r in range(1, R):
+            E[r].set_boundary(capi.BND_REMOTE_X_BOT, v[r - 1].data_ptr())
+        for r in range(R):
+            E[r].solve_phase(2)
     torch.cuda.synchronize()
     x = np.concatenate([t.cpu().numpy() for t in xo])
     lu, _ = oracle.band_lu(a)
@@ -93,3 +133,27 @@ def test_sharded_matches_reference_cpu_path(spk, oracle, n, k, R, parts, tip):
 def test_sharded_overlapped_factor_protocol(spk, oracle, n, k, R, parts, tip):
     """factor phases 10/11: the W^(t) exchange overlaps the band LU, the boundary block rides with the local ones."""
     assert _run(spk, oracle, n, k, R, parts, tip, overlapped=True) < 1e-10
+
+
+@pytest.mark.parametrize("n,k,R,parts,tip", [(64_000, 100, 4, 3, 0), (30_008, 37, 3, 1, -1), (200_000, 50, 8, 2, 0)])
+def test_sharded_peer_mailbox_protocol(spk, oracle, n, k, R, parts, tip):
+    """spk_peer_post / spk_peer_wait: the boundary items travel through the neighbours' mailboxes (flag + ack words)."""
+    assert _run(spk, oracle, n, k, R, parts, tip, mailbox=True) < 1e-10
+
+
+def test_peer_mailbox_spin_is_bounded(spk):
+    """A wait whose item never arrives gives up after ~2 s and spk_peer_check reports it (no hung GPU)."""
+    from spike_petsc_b200 import capi
+    E = [spk.Spike(partitions=2, mem=spk.MEM_DEVICE, rank=r, nranks=2, row_offset=r * 8000, n_global=16000) for r in range(2)]
+    for e in E:
+        e.set_band_synthetic(8000, 10)
+    ptrs = [e.peer_create()[1] for e in E]
+    E[0].peer_attach(1, ptr=ptrs[1])
+    E[1].peer_attach(0, ptr=ptrs[0])
+    with pytest.raises(RuntimeError):
+        E[0].peer_post(capi.BND_REMOTE_WT)          # not an "out" item
+    E[0].peer_wait(capi.BND_REMOTE_WT)              # nobody posted
+    with pytest.raises(RuntimeError, match="timed out"):
+        E[0].peer_check()
+    for e in E:
+        e.close()
