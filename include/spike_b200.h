@@ -130,7 +130,7 @@ enum {
 };
 /* split-phase factor/solve for nranks > 1 (the host performs the NCCL exchanges between phases):
  *   factor: phase 0 (tip windows + LU), phase 1 (local tips), [WT_FIRST -> left's REMOTE_WT], phase 2
- *      or, overlapping the exchange with the LU: phase 10 (tip windows + my first W^(t)), start
+ *      or, overlapping the exchange with the LU: phase 10 (tip windows + every W^(t)), start
  *      [WT_FIRST -> left's REMOTE_WT], phase 11 (band LU), finish the exchange, phase 1 (local tips and,
  *      REMOTE_WT being set, the boundary block in the same launch), phase 2 (no-op then)
  *   solve : phase 0 (sweeps), [G_TOP -> left's REMOTE_G_TOP], phase 1 (reduced systems),

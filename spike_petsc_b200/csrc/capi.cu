@@ -331,7 +331,7 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
   int rc = SPK_OK;
   if (phase == 0) {
     if (c->factored) { SPK_SET_ERR(c, "band already factored (factorisation is in place)"); return SPK_ERR_STATE; }
-    c->launches = 0; c->have_remote_wt = 0; c->boundary_done = 0;
+    c->launches = 0; c->have_remote_wt = 0; c->boundary_done = 0; c->wt_done = 0;
     SPK_CUDA(c, cudaMemsetAsync(c->d_boost, 0, sizeof(int64_t), c->stream));
     SPK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     // W^(t) needs the unfactored top windows: UL pass first (read only), then the in-place LU
@@ -340,14 +340,14 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
     if (rc) return rc;
     return SPK_OK;
   }
-  if (phase == 10) {   // overlapped protocol, step 1: tip windows and -- if a left neighbour exists -- my first W^(t)
+  if (phase == 10) {   // overlapped protocol, step 1: tip windows and every W^(t) (the first one travels to the left neighbour)
     if (c->factored) { SPK_SET_ERR(c, "band already factored (factorisation is in place)"); return SPK_ERR_STATE; }
-    c->launches = 0; c->have_remote_wt = 0; c->boundary_done = 0;
+    c->launches = 0; c->have_remote_wt = 0; c->boundary_done = 0; c->wt_done = 0;
     SPK_CUDA(c, cudaMemsetAsync(c->d_boost, 0, sizeof(int64_t), c->stream));
     SPK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     STAGE_BEGIN(c, 0);
     rc = spk_launch_ul_tips(c);
-    if (rc == SPK_OK && c->opts.rank > 0) rc = spk_launch_tips(c, 2, 0);
+    if (rc == SPK_OK) rc = spk_launch_tips(c, 4, 0);   // all W^(t) now (one launch; no single-CTA kernel for the first one)
     STAGE_END(c, 0);
     return rc;
   }

@@ -71,6 +71,7 @@ struct spk_ctx {
   double *cur_x;       // output vector of the solve in progress (split-phase)
   int have_remote_wt;  // the right neighbour's W^(t) has been set for the factorisation in progress
   int boundary_done;   // the boundary reduced block has been factored
+  int wt_done;         // every W^(t) of the factorisation in progress has been computed (factor phase 10)
   // NVLink peer mailboxes (peer.cu): mine, the neighbours' (0 left, 1 right), per-channel sequence numbers
   double *mbox, *peer_mbox[2];
   int peer_ipc[2];

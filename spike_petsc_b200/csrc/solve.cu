@@ -14,10 +14,12 @@
 //                    with 8x8 tiles spread over the lanes and warp-shuffle reductions;
 //   warps 1-3 ("far") accumulate the part of the dot products that only needs y_{<=I-2} for the
 //                    NEXT tile row (warp-shuffle reductions over the 4 lanes of a row);
-//   warp 4 keeps SW_NST tile rows in flight with bulk async copies (mbarrier tx-count).
+//   warp 4 keeps SW_NST_MAIN / SW_NST_CORR tile rows in flight with bulk async copies (mbarrier tx-count).
 #include "common.cuh"
+#include <algorithm>
 
-#define SW_NST 8
+#define SW_NST_MAIN 8         // stage ring depth of the partition sweeps (2 CTAs/SM resident)
+#define SW_NST_CORR 6         // ... of the window corrections: 46 KB of shared memory, 4 CTAs/SM = all 2P jobs resident
 #define SW_THREADS 160          // near warp, three far warps, one copy warp
 #define SW_COPY_THREAD 128
 
@@ -37,7 +39,7 @@ struct SweepArgs {
   int64_t n;           // rows of the user vectors (padded rows are neither read nor written)
 };
 
-template <int KT>
+template <int KT, int SW_NST>
 struct SweepSmem {
   // forward : [0..KT-1] = Lb tiles d=-KT..-1, [KT] = D^-1 (diagonal slot), [KT+1] = right-hand-side block (8 doubles)
   // backward: [0..KT-1] = Ub tiles d=1..KT (unit block diagonal),         [KT+1] = right-hand-side block
@@ -74,8 +76,8 @@ __device__ __forceinline__ double far_partial(const double* stage_row, const dou
   return acc;
 }
 
-template <int KT, int DIR, class Sink>
-__device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, unsigned& itbase, int64_t r0, int64_t r1,
+template <int KT, int SW_NST, int DIR, class Sink>
+__device__ __forceinline__ void sweep_dir(SweepSmem<KT, SW_NST>& S, const SweepArgs& a, unsigned& itbase, int64_t r0, int64_t r1,
                                           const double* vin, int64_t nvalid, Sink sink) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
@@ -180,10 +182,10 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT>& S, const SweepArgs& a, 
   }
 }
 
-template <int KT>
-__global__ void __launch_bounds__(SW_THREADS, 3) k_sweep(const SweepArgs a) {
+template <int KT, int SW_NST>
+__global__ void __launch_bounds__(SW_THREADS, SW_NST > 6 ? 3 : 4) k_sweep(const SweepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SweepSmem<KT>& S = *reinterpret_cast<SweepSmem<KT>*>(smem_raw);
+  SweepSmem<KT, SW_NST>& S = *reinterpret_cast<SweepSmem<KT, SW_NST>*>(smem_raw);
   const int kp = KT * 8;
   if (threadIdx.x == 0) {
     for (int i = 0; i < SW_NST; ++i) mbar_init(reinterpret_cast<uint64_t*>(&S.full[i]), 1);
@@ -197,8 +199,8 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep(const SweepArgs a) {
     const int64_t t0 = a.pstart[p], t1 = a.pstart[p + 1];
     double* x = a.x;
     auto store_x = [&](int64_t I, int g, double v) { if (I * 8 + g < n) x[I * 8 + g] = v; };
-    sweep_dir<KT, +1>(S, a, itbase, t0, t1, a.in, n, store_x);
-    sweep_dir<KT, -1>(S, a, itbase, t0, t1, x, n, store_x);
+    sweep_dir<KT, SW_NST, +1>(S, a, itbase, t0, t1, a.in, n, store_x);
+    sweep_dir<KT, SW_NST, -1>(S, a, itbase, t0, t1, x, n, store_x);
     return;
   }
   // ---- corrections: blockIdx = 2*p + side (0 top, 1 bottom); when the window covers more than half
@@ -236,24 +238,24 @@ __global__ void __launch_bounds__(SW_THREADS, 3) k_sweep(const SweepArgs a) {
     if (use_bot && I >= t1 - KT) v += rb[e - (t1 - KT) * 8];
     w[e] = v;
   }
-  sweep_dir<KT, +1>(S, a, itbase, flo, hi, w, npad, store_w);
-  sweep_dir<KT, -1>(S, a, itbase, lo, hi, w, npad, store_w);
+  sweep_dir<KT, SW_NST, +1>(S, a, itbase, flo, hi, w, npad, store_w);
+  sweep_dir<KT, SW_NST, -1>(S, a, itbase, lo, hi, w, npad, store_w);
   __syncthreads();
   for (int64_t e = lo * 8 + threadIdx.x; e < hi * 8; e += blockDim.x)
     if (e < n) x[e] -= w[e];
 }
 
-template <int KT>
+template <int KT, int NST>
 static int launch_sweep_kt(spk_ctx* c, const SweepArgs& a, int grid) {
-  const size_t smem = sizeof(SweepSmem<KT>);
-  SPK_CUDA(c, cudaFuncSetAttribute(k_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_sweep<KT><<<grid, SW_THREADS, smem, c->stream>>>(a);
+  const size_t smem = sizeof(SweepSmem<KT, NST>);
+  SPK_CUDA(c, cudaFuncSetAttribute(k_sweep<KT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_sweep<KT, NST><<<grid, SW_THREADS, smem, c->stream>>>(a);
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }
 static int launch_sweep_any(spk_ctx* c, const SweepArgs& a, int grid) {
   switch (c->L.kt) {
-#define CASE(K_) case K_: return launch_sweep_kt<K_>(c, a, grid);
+#define CASE(K_) case K_: return a.mode == SWEEP_MAIN ? launch_sweep_kt<K_, SW_NST_MAIN>(c, a, grid) : launch_sweep_kt<K_, SW_NST_CORR>(c, a, grid);
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
 #undef CASE
     default: SPK_SET_ERR(c, "unsupported kt=%d", c->L.kt); return SPK_ERR_UNSUPPORTED;
@@ -286,7 +288,7 @@ int spk_launch_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld) {
 }
 
 // --------------------------------------------------------------------------------------------
-// reduced system solve + coupling right-hand sides, one CTA (4 warps) per interface
+// reduced system solve + coupling right-hand sides, one CTA (32 warps: the loads of a whole block mat-vec in flight at once) per interface
 // --------------------------------------------------------------------------------------------
 struct RedSolveArgs {
   const double* band; BandLayout L; const int64_t* pstart;
@@ -332,7 +334,7 @@ __device__ __forceinline__ void block_matvec(const double* __restrict__ M, const
     }
   }
 }
-__global__ void __launch_bounds__(256) k_reduced_solve(const RedSolveArgs a) {
+__global__ void __launch_bounds__(1024) k_reduced_solve(const RedSolveArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int kp = a.L.kt * 8, KT = a.L.kt;
   double* gb = sm; double* gt = gb + kp; double* tv = gt + kp; double* xt = tv + kp; double* xb = xt + kp;
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(256) k_reduced_solve(const RedSolveArgs a) {
   block_matvec(V, xt, gb, xb, kp, true);      // x_b = g_b - V x_t
   __syncthreads();
   // r_top of partition i+1: C_{i+1} x_b ;  r_bot of partition i: B_i x_t
-  for (int r = warp; r < kp; r += 8) {
+  for (int r = warp; r < kp; r += (int)(blockDim.x >> 5)) {
     double s1 = 0.0, s2 = 0.0;
     for (int c = lane; c < kp; c += 32) {
       if (!bnd && (c >> 3) >= (r >> 3)) s1 = fma(a.band[a.L.elem_off(tb * 8 + r, (tb - KT) * 8 + c)], xb[c], s1);
@@ -370,10 +372,10 @@ __global__ void __launch_bounds__(256) k_reduced_solve(const RedSolveArgs a) {
 }
 
 // r_top of partition 0 from the left neighbour's x_b:  r = C_0 x_b,  C_0(r,c) = A(r, c - kp)
-__global__ void __launch_bounds__(128) k_rtop_left(const double* __restrict__ band, BandLayout L, const double* __restrict__ xb, double* rtop) {
+__global__ void __launch_bounds__(1024) k_rtop_left(const double* __restrict__ band, BandLayout L, const double* __restrict__ xb, double* rtop) {
   const int kp = L.kt * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < kp; r += 4) {
+  for (int r = warp; r < kp; r += (int)(blockDim.x >> 5)) {
     double s1 = 0.0;
     for (int c = lane; c < kp; c += 32)
       if ((c >> 3) >= (r >> 3)) s1 = fma(band[L.elem_off(r, (int64_t)c - kp)], xb[c], s1);
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(128) k_rtop_left(const double* __restrict__ ba
   }
 }
 int spk_launch_rtop_left(spk_ctx* c) {
-  k_rtop_left<<<1, 128, 0, c->stream>>>(c->band, c->L, c->remoteXbot, c->gtip);
+  k_rtop_left<<<1, 1024, 0, c->stream>>>(c->band, c->L, c->remoteXbot, c->gtip);
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }
@@ -401,7 +403,11 @@ int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int if
     a.first_iface = iface_lo;
     a.boundary_iface = has_right ? c->P - 1 : -1;
     a.remoteWt = c->remoteWt; a.remoteGtop = c->remoteGtop; a.xbBoundary = c->xbBoundary; a.n = c->L.n;
-    k_reduced_solve<<<n, 256, sizeof(double) * 5 * c->kp, c->stream>>>(a);
+    // as many warps per CTA as keep every interface resident at once (2048 threads per SM): 32 warps = one pass per
+    // block mat-vec when there are at most two interfaces per SM
+    const int per_sm = (n + c->sm_count - 1) / c->sm_count;
+    const int threads = std::max(256, std::min(1024, (2048 / std::max(per_sm, 1)) / 32 * 32));
+    k_reduced_solve<<<n, threads, sizeof(double) * 5 * c->kp, c->stream>>>(a);
     SPK_KERNEL_CHECK(c);
   }
   return SPK_OK;

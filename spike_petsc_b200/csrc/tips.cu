@@ -476,6 +476,7 @@ static cudaError_t red_launch(spk_ctx* c, int grid, const RedArgs& r, size_t sme
 //   what = 2: only W^(t) of my first partition (needs the tip windows, not the band LU: sent to the left
 //             neighbour while the LU runs)
 //   what = 3: like 0, and the boundary reduced block in the same launch (remoteWt already set)
+//   what = 4: every W^(t) of this rank (they need the tip windows only; what = 0 / 3 then skip them)
 int spk_launch_tips(spk_ctx* c, int what, int unused) {
   (void)unused;
   const int kp = c->kp, P = c->P;
@@ -504,18 +505,19 @@ int spk_launch_tips(spk_ctx* c, int what, int unused) {
   }
   // V^(b) of partitions 0..P-2 (+ P-1 when a right neighbour exists)
   const int nvb = (P - 1) + (has_right ? 1 : 0);
-  if (nvb > 0) {
+  if (nvb > 0 && what != 4) {
     t.S = c->Sb; t.out = c->Vb; t.first_part = 0; t.which = 0;
     tip_launch(c, nvb, t, smem);
     SPK_KERNEL_CHECK(c);
   }
   // W^(t) of partitions 1..P-1 (+ 0 when a left neighbour exists)
   const int wfirst = has_left ? 0 : 1;
-  if (P - wfirst > 0) {
+  if (P - wfirst > 0 && !c->wt_done) {
     t.S = c->St; t.out = c->Wt; t.first_part = wfirst; t.which = 1;
     tip_launch(c, P - wfirst, t, smem);
     SPK_KERNEL_CHECK(c);
   }
+  if (what == 4) { c->wt_done = 1; return SPK_OK; }
   const int nred = (P - 1) + ((what == 3 && has_right) ? 1 : 0);   // interface P-1 = boundary with the right rank
   if (nred > 0) {
     r.first_iface = 0; r.remote_iface = (what == 3 && has_right) ? P - 1 : -1;
