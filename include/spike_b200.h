@@ -110,6 +110,13 @@ int spk_set_operator_csr(spk_ctx *ctx, int n, const int *ia, const int *ja, cons
 int spk_krylov(spk_ctx *ctx, int method, int restart, double rtol, int maxit, const double *b,
                double *x, int *its, double *rnorm, int *converged);
 
+/* Equilibration: band <- diag(rscale) band diag(cscale) in place, after spk_set_band_* and before
+ * spk_factor; spk_solve and the spk_krylov preconditioner then apply diag(c) (scaled band)^-1 diag(r), i.e. the
+ * inverse of the ORIGINAL band.  rscale = exp(u), cscale = exp(v) of MC64 job 5 are the scalings the reference
+ * computes and discards (src/petsc_mat_wbm.c:56; AWBM: src/petsc_mat_awbm.c:208-223).  n entries each, memory
+ * space per opts.mem.  spk_mult keeps using the unscaled original.  Single-rank contexts only. */
+int spk_set_scaling(spk_ctx *ctx, const double *rscale, const double *cscale);
+
 /* PCView_Banded (src/matbanded.c:196-211) */
 int spk_view(spk_ctx *ctx, spk_info *info);
 

@@ -71,6 +71,7 @@ def lib():
         L.spk_solve.argtypes = [vp, vp, vp, C.c_int]
         L.spk_mult.argtypes = [vp, vp, vp]
         L.spk_keep_original.argtypes = [vp, C.c_int]
+        L.spk_set_scaling.argtypes = [vp, vp, vp]
         L.spk_permute.argtypes = [vp, vp, C.c_int, vp, C.c_int64]
         L.spk_set_operator_csr.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
         L.spk_krylov.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, ip, dp, ip]
@@ -171,6 +172,13 @@ class Spike:
         cp = None if colperm is None else np.ascontiguousarray(colperm, dtype=np.int32)
         self._ck(lib().spk_set_operator_csr(self._h, len(ia) - 1, _addr(ia), _addr(ja), _addr(a), _addr(rp), _addr(cp)),
                  "spk_set_operator_csr")
+
+    def set_scaling(self, rscale, cscale):
+        """band <- diag(r) band diag(c) before factor(); solve() still returns the solution of the original system."""
+        if self.mem == MEM_HOST:
+            rscale = np.ascontiguousarray(rscale, dtype=np.float64)
+            cscale = np.ascontiguousarray(cscale, dtype=np.float64)
+        self._ck(lib().spk_set_scaling(self._h, _addr(rscale), _addr(cscale)), "spk_set_scaling")
 
     def keep_original(self, keep=True):
         self._ck(lib().spk_keep_original(self._h, int(keep)), "spk_keep_original")

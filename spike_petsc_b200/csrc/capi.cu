@@ -29,7 +29,7 @@ static void free_band(spk_ctx* c) {
   F(c->band); F(c->orig); F(c->dinv); F(c->d_pstart); F(c->Sb); F(c->St); F(c->Vb); F(c->Wt); F(c->Red);
   F(c->RedPiv); F(c->work); F(c->gtip); F(c->xtip); F(c->xb); F(c->xt); F(c->corr);
   F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->xtopRemote); F(c->xbBoundary); F(c->haloL); F(c->haloR);
-  F(c->opA.ia); F(c->opA.ja); F(c->opA.a);
+  F(c->opA.ia); F(c->opA.ja); F(c->opA.a); F(c->rscale); F(c->cscale);
   free(c->h_pstart); c->h_pstart = nullptr;
   spk_peer_release(c);   // the mailbox layout depends on kp
   c->have_band = c->factored = 0;
@@ -160,6 +160,33 @@ static int finish_band(spk_ctx* c) {
     SPK_CUDA(c, cudaMalloc(&c->orig, sizeof(double) * (size_t)c->L.elems()));
     SPK_CUDA(c, cudaMemcpyAsync(c->orig, c->band, sizeof(double) * (size_t)c->L.elems(), cudaMemcpyDeviceToDevice, c->stream));
   }
+  return SPK_OK;
+}
+
+// Equilibration of the band before the factorisation: band <- diag(r) band diag(c) in place, and
+// spk_solve / the Krylov preconditioner apply x = diag(c) (diag(r) A diag(c))^-1 diag(r) b -- the same operator
+// A^-1 in exact arithmetic, but the no-pivot LU and its boosting rule (|pivot| < boost_rel * max|a|) then see
+// entries of comparable size.  With r = exp(u), c = exp(v) of MC64 job 5 (the vector the reference computes and
+// discards, src/petsc_mat_wbm.c:56) every entry is <= 1 in magnitude and the matched ones are 1.
+// The kept original (spk_mult, the Krylov operator) stays unscaled.
+extern "C" int spk_set_scaling(spk_ctx* c, const double* rscale, const double* cscale) {
+  if (!c || !rscale || !cscale) return SPK_ERR_ARG;
+  if (!c->have_band || c->factored) { SPK_SET_ERR(c, "spk_set_scaling: set the band first and scale it before spk_factor"); return SPK_ERR_STATE; }
+  if (c->opts.nranks > 1) { SPK_SET_ERR(c, "spk_set_scaling: not available for sharded contexts yet (the halo columns need the neighbours' scales)"); return SPK_ERR_UNSUPPORTED; }
+  if (c->rscale) { SPK_SET_ERR(c, "spk_set_scaling: the band is already scaled"); return SPK_ERR_STATE; }
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  const size_t bytes = sizeof(double) * (size_t)c->L.n;
+  const cudaMemcpyKind kind = c->opts.mem == SPK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  SPK_CUDA(c, cudaMalloc(&c->rscale, bytes));
+  SPK_CUDA(c, cudaMalloc(&c->cscale, bytes));
+  SPK_CUDA(c, cudaMemcpyAsync(c->rscale, rscale, bytes, kind, c->stream));
+  SPK_CUDA(c, cudaMemcpyAsync(c->cscale, cscale, bytes, kind, c->stream));
+  int rc = spk_launch_scale_band(c, c->rscale, c->cscale);
+  if (rc) return rc;
+  rc = spk_launch_absmax(c, c->band, c->d_scalar);   // the boosting threshold follows the scaled band
+  if (rc) return rc;
+  SPK_CUDA(c, cudaMemcpyAsync(&c->anorm_max, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SPK_CUDA(c, cudaStreamSynchronize(c->stream));
   return SPK_OK;
 }
 
@@ -393,8 +420,14 @@ extern "C" int spk_factor(spk_ctx* c) {
 // solve (device pointers, one right-hand side)
 // ---------------------------------------------------------------------------------------------
 int spk_solve_dev(spk_ctx* c, const double* b, double* x) {
+  int rc = SPK_OK;
+  if (c->rscale) {   // equilibrated band: x = diag(c) B~^-1 diag(r) b  (the sweeps run in place on x)
+    rc = spk_launch_vec_scale(c, x, b, c->rscale, c->L.n);
+    if (rc) return rc;
+    b = x;
+  }
   STAGE_BEGIN(c, 3);
-  int rc = spk_launch_sweep(c, b, x, 1, c->L.n);
+  rc = spk_launch_sweep(c, b, x, 1, c->L.n);
   STAGE_END(c, 3);
   if (rc) return rc;
   if (c->P > 1) {
@@ -406,6 +439,7 @@ int spk_solve_dev(spk_ctx* c, const double* b, double* x) {
     rc = spk_launch_corrections(c, x, 1, c->L.n);
     STAGE_END(c, 5);
   }
+  if (rc == SPK_OK && c->cscale) rc = spk_launch_vec_scale(c, x, x, c->cscale, c->L.n);
   return rc;
 }
 

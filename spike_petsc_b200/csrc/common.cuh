@@ -76,6 +76,7 @@ struct spk_ctx {
   double *mbox, *peer_mbox[2];
   int peer_ipc[2];
   unsigned long long peer_seq_out[3], peer_seq_in[3];
+  double *rscale, *cscale;   // optional equilibration (spk_set_scaling): the factored band is diag(r) A diag(c)
   // operator for Krylov
   CsrDev opA;
   // bookkeeping
@@ -157,6 +158,8 @@ int spk_launch_pack_dense(spk_ctx* c, const double* src_dev, int layout);
 int spk_launch_pack_csr(spk_ctx* c, const CsrDev& A, const int* rowperm_dev, const int* icolperm_dev);
 int spk_launch_unpack_rows(spk_ctx* c, const double* band, double* rows_dev);
 int spk_launch_absmax(spk_ctx* c, const double* band, double* out_dev);
+int spk_launch_scale_band(spk_ctx* c, const double* rs_dev, const double* cs_dev);
+int spk_launch_vec_scale(spk_ctx* c, double* out, const double* in, const double* s, int64_t n);
 int spk_launch_matmult(spk_ctx* c, const double* band, const double* x, double* y);
 int spk_launch_lu(spk_ctx* c);            // per-partition LU (+ S_b capture, dinv)
 int spk_launch_ul_tips(spk_ctx* c);       // UL window -> S_t

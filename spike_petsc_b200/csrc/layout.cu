@@ -71,6 +71,43 @@ int spk_launch_pack_dense(spk_ctx* c, const double* src_dev, int layout) {
   return SPK_OK;
 }
 
+// --------------------------------------------------------------------------------------------
+// equilibration  band(i,j) <- r_i * band(i,j) * c_j  in place (MC64-style scalings exp(u_i), exp(v_j):
+// the reference computes them and throws them away, src/petsc_mat_wbm.c:56).
+// One thread per entry pair of a tile: coalesced 16 B accesses, the scale vectors stay in L1/L2.
+// --------------------------------------------------------------------------------------------
+__global__ void k_scale_band(double* __restrict__ band, BandLayout L, const double* __restrict__ rs, const double* __restrict__ cs) {
+  const int64_t npairs = L.nt * (int64_t)L.tpr * 32;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < npairs; e += (int64_t)gridDim.x * blockDim.x) {
+    const int pr = (int)(e & 31);
+    const int64_t t = e >> 5;
+    const int64_t I = t / L.tpr;
+    const int slot = (int)(t - I * L.tpr);
+    const int64_t J = I + slot - L.kt;
+    const int64_t i = I * 8 + (pr >> 2), j = J * 8 + (pr & 3) * 2;
+    if (J < 0 || J >= L.nt || i >= L.n) continue;
+    double2* p = reinterpret_cast<double2*>(band + t * SPK_TILE_ELEMS) + pr;
+    double2 v = *p;
+    const double r = rs[i];
+    v.x = (j < L.n) ? r * v.x * cs[j] : v.x;
+    v.y = (j + 1 < L.n) ? r * v.y * cs[j + 1] : v.y;
+    *p = v;
+  }
+}
+int spk_launch_scale_band(spk_ctx* c, const double* rs_dev, const double* cs_dev) {
+  k_scale_band<<<c->sm_count * 8, 256, 0, c->stream>>>(c->band, c->L, rs_dev, cs_dev);
+  SPK_KERNEL_CHECK(c);
+  return SPK_OK;
+}
+__global__ void k_vec_scale(double* __restrict__ out, const double* __restrict__ in, const double* __restrict__ s, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) out[e] = in[e] * s[e];
+}
+int spk_launch_vec_scale(spk_ctx* c, double* out, const double* in, const double* s, int64_t n) {
+  k_vec_scale<<<c->sm_count * 4, 256, 0, c->stream>>>(out, in, s, n);
+  SPK_KERNEL_CHECK(c);
+  return SPK_OK;
+}
+
 // tile-major band -> ROWS layout (test/debug hook)
 __global__ void k_unpack_rows(const double* __restrict__ band, double* __restrict__ dst, BandLayout L) {
   const int64_t bw = 2 * (int64_t)L.k + 1;

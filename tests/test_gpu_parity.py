@@ -288,6 +288,66 @@ def test_wbm_3x3_permutation_applied_on_gpu(spk, oracle):
     S.close()
 
 
+# ------------------------------------------------------------------ equilibration
+@pytest.mark.parametrize("scales", ["ideal", "mc64"])
+def test_equilibration_removes_spurious_boosts(spk, oracle, scales):
+    """A = D1 T D2 with T diagonally dominant and row scales over sixteen decades: the boosting rule
+    (|pivot| < boost_rel * max|a|) mistakes the small rows for singular ones (on the GPU only where the
+    tensor-core pivot-block inverse falls back to the scalar elimination).  With the band equilibrated by
+    spk_set_scaling -- by 1/D1, 1/D2, or by exp(u), exp(v) of the reference's own MC64 job 5, the vector
+    src/petsc_mat_wbm.c:56 throws away -- no pivot is boosted and spk_solve returns the exact band solve of the
+    ORIGINAL system."""
+    if scales == "mc64" and not oracle.have_mc64():
+        pytest.skip("reference MC64 not built (oracle/_ref)")
+    n, k = 6000, 12
+    t = oracle.gen_band(n, k)
+    rng = np.random.default_rng(7)
+    d1, d2 = 10.0 ** rng.uniform(-8, 8, n), 10.0 ** rng.uniform(-0.5, 0.5, n)   # (wide column scales would make x itself ill-determined)
+    a = np.zeros_like(t)
+    rows, cols, vals = [], [], []
+    for d in range(-k, k + 1):
+        lo, hi = max(0, -d), min(n, n - d)
+        a[lo:hi, d + k] = d1[lo:hi] * t[lo:hi, d + k] * d2[lo + d:hi + d]
+        rows.append(np.arange(lo, hi)); cols.append(np.arange(lo, hi) + d); vals.append(a[lo:hi, d + k])
+    u = oracle.gen_vec(n, 5)
+    b = oracle.band_mult(a, u)
+    lu, _ = oracle.band_lu(a)
+    xref = oracle.band_solve(lu, b)
+    # the scalar rule restated by the oracle boosts hundreds of healthy pivots of the small rows ...
+    assert oracle.band_lu(a, boost=1e-13 * np.abs(a).max())[1] > 100
+    if scales == "ideal":
+        r, c = 1.0 / d1, 1.0 / d2
+    else:
+        m = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+        m.sort_indices()
+        _, col_is, num, dw = oracle.wbm(m.indptr, m.indices, m.data)
+        assert num == n and np.array_equal(col_is, np.arange(n))          # the dominant diagonal is the matching
+        # the wrapper hands CSR to MC64 as CSC (src/petsc_mat_wbm.c:29,52): MC64 sees A^T, so its row scaling u
+        # (dw[0:n]) scales the COLUMNS of A and its column scaling v (dw[n:2n]) the rows
+        r, c = np.exp(dw[n:2 * n]), np.exp(dw[:n])
+        sc = sp.diags(r) @ m @ sp.diags(c)
+        assert abs(sc).max() <= 1.0 + 1e-10 and np.allclose(abs(sc.diagonal()), 1.0, rtol=1e-10)
+    # ... and none once the band is equilibrated
+    a_sc = np.zeros_like(a)
+    for d in range(-k, k + 1):
+        lo, hi = max(0, -d), min(n, n - d)
+        a_sc[lo:hi, d + k] = r[lo:hi] * a[lo:hi, d + k] * c[lo + d:hi + d]
+    assert oracle.band_lu(a_sc, boost=1e-13 * np.abs(a_sc).max())[1] == 0
+    S = spk.Spike(partitions=4)
+    S.keep_original(True)
+    S.set_band_dense(a, k)
+    S.set_scaling(r, c)
+    with pytest.raises(spk.SpikeError):
+        S.set_scaling(r, c)                                                # once per band
+    S.factor()
+    info = S.view()
+    assert info["boosted_pivots"] == 0 and info["anorm_max"] <= 1.0 + 1e-10 if scales == "mc64" else info["boosted_pivots"] == 0
+    x = S.solve(b)
+    assert relerr(x, xref) < RTOL and relerr(x, u) < 1e-9
+    assert relerr(S.mult(u), b) < 1e-14                                    # the kept original is the unscaled band
+    S.close()
+
+
 # ------------------------------------------------------------------ Krylov iteration parity (+-1)
 @pytest.mark.parametrize("method", ["gmres", "bcgs"])
 def test_krylov_iteration_parity(spk, oracle, method):
