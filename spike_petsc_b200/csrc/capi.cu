@@ -201,12 +201,51 @@ extern "C" int spk_keep_original(spk_ctx* c, int keep) {
   return SPK_OK;
 }
 
+// rows per upload chunk of spk_set_band_dense(host, ROWS); 0 = 256 MB worth.  Debug hook for the tests (not public).
+static int64_t g_pack_chunk_rows = 0;
+extern "C" int spk_debug_set_pack_chunk_rows(int64_t rows) { g_pack_chunk_rows = rows > 0 ? ((rows + 7) & ~7ll) : 0; return SPK_OK; }
+
 extern "C" int spk_set_band_dense(spk_ctx* c, int64_t n, int k, const double* band, int layout, int mem) {
   if (!c || !band) return SPK_ERR_ARG;
   if (layout != SPK_LAYOUT_ROWS && layout != SPK_LAYOUT_DIAGS) { SPK_SET_ERR(c, "bad layout %d", layout); return SPK_ERR_ARG; }
   int rc = plan(c, n, k);
   if (rc) return rc;
   const size_t bytes = sizeof(double) * (size_t)n * (2 * (size_t)k + 1);
+  if (mem == SPK_MEM_HOST && layout == SPK_LAYOUT_ROWS) {
+    // Host rows -> device tiles as a two-buffer pipeline: chunk i+1 crosses PCIe on a copy stream while chunk i is
+    // packed; no device copy of the whole input (16 GB at N = 10M, K = 100) is ever allocated.
+    const int64_t bw = 2 * (int64_t)k + 1;
+    int64_t chunk = g_pack_chunk_rows > 0 ? g_pack_chunk_rows : std::max<int64_t>(8, ((int64_t)(256u << 20) / (bw * 8)) & ~7ll);
+    chunk = std::min<int64_t>(chunk, n);
+    double* buf[2] = {nullptr, nullptr};
+    cudaStream_t cs = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
+    cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
+      e = cudaMalloc(&buf[s], sizeof(double) * (size_t)chunk * bw);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&packed[s], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->band, 0, sizeof(double) * (size_t)c->L.elems(), c->stream);
+    int64_t i = 0;
+    for (int64_t r0 = 0; r0 < n && e == cudaSuccess && rc == SPK_OK; r0 += chunk, ++i) {
+      const int s = (int)(i & 1);
+      const int64_t nr = std::min(chunk, n - r0);
+      if (i >= 2) e = cudaStreamWaitEvent(cs, packed[s], 0);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(buf[s], band + r0 * bw, sizeof(double) * (size_t)nr * bw, cudaMemcpyHostToDevice, cs);
+      if (e == cudaSuccess) e = cudaEventRecord(copied[s], cs);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, copied[s], 0);
+      if (e == cudaSuccess) rc = spk_launch_pack_rows_chunk(c, buf[s], r0, nr);
+      if (e == cudaSuccess && rc == SPK_OK) e = cudaEventRecord(packed[s], c->stream);
+    }
+    if (e == cudaSuccess && rc == SPK_OK) rc = spk_launch_pack_finish(c);
+    if (e == cudaSuccess && rc == SPK_OK) rc = finish_band(c);
+    cudaStreamSynchronize(c->stream);
+    if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
+    for (int s = 0; s < 2; ++s) { if (buf[s]) cudaFree(buf[s]); if (copied[s]) cudaEventDestroy(copied[s]); if (packed[s]) cudaEventDestroy(packed[s]); }
+    if (e != cudaSuccess) { SPK_SET_ERR(c, "chunked band upload failed: %s", cudaGetErrorString(e)); return SPK_ERR_CUDA; }
+    return rc;
+  }
   const double* src = band;
   double* tmp = nullptr;
   if (mem == SPK_MEM_HOST) {

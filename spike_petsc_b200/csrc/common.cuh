@@ -155,6 +155,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ---- kernels' host launchers (defined in the .cu files) ---------------------------------------
 int spk_launch_generate(spk_ctx* c, uint64_t seed, double delta);
 int spk_launch_pack_dense(spk_ctx* c, const double* src_dev, int layout);
+int spk_launch_pack_rows_chunk(spk_ctx* c, const double* src_dev, int64_t row0, int64_t nrows);
+int spk_launch_pack_finish(spk_ctx* c);
 int spk_launch_pack_csr(spk_ctx* c, const CsrDev& A, const int* rowperm_dev, const int* icolperm_dev);
 int spk_launch_unpack_rows(spk_ctx* c, const double* band, double* rows_dev);
 int spk_launch_absmax(spk_ctx* c, const double* band, double* out_dev);

@@ -62,6 +62,27 @@ __global__ void k_pad_identity(double* __restrict__ band, BandLayout L) {
   const int64_t i = L.n + threadIdx.x;
   if (i < L.nt * SPK_TILE) band[L.elem_off(i, i)] = 1.0;
 }
+// rows [row0, row0+nrows) of a ROWS-layout band, src pointing at the first of them (chunked host upload)
+__global__ void k_pack_rows_chunk(const double* __restrict__ src, double* __restrict__ band, BandLayout L, int64_t row0, int64_t nrows) {
+  const int64_t bw = 2 * (int64_t)L.k + 1;
+  const int64_t total = nrows * bw;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t il = e / bw, dk = e - il * bw;
+    const int64_t i = row0 + il, j = i + dk - L.k;
+    if (j < 0 || j >= L.n) continue;
+    band[L.elem_off(i, j)] = src[e];
+  }
+}
+int spk_launch_pack_rows_chunk(spk_ctx* c, const double* src_dev, int64_t row0, int64_t nrows) {
+  k_pack_rows_chunk<<<c->sm_count * 8, 256, 0, c->stream>>>(src_dev, c->band, c->L, row0, nrows);
+  SPK_KERNEL_CHECK(c);
+  return SPK_OK;
+}
+int spk_launch_pack_finish(spk_ctx* c) {   // identity on the padded rows of the last tile row
+  const BandLayout& L = c->L;
+  if (L.nt * SPK_TILE > L.n) { k_pad_identity<<<1, 8, 0, c->stream>>>(c->band, L); SPK_KERNEL_CHECK(c); }
+  return SPK_OK;
+}
 int spk_launch_pack_dense(spk_ctx* c, const double* src_dev, int layout) {
   const BandLayout& L = c->L;
   SPK_CUDA(c, cudaMemsetAsync(c->band, 0, sizeof(double) * (size_t)L.elems(), c->stream));

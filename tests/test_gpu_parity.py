@@ -53,6 +53,27 @@ def test_dense_pack_round_trip_bit_exact(spk, oracle, layout):
     S.close()
 
 
+def test_host_rows_upload_is_chunked_and_bit_exact(spk, oracle):
+    """spk_set_band_dense(host, ROWS) streams the band through two chunk buffers (copy stream + pack kernel);
+    with 64-row chunks a 1237-row band takes 20 of them, the last one ragged."""
+    import ctypes as C
+    L = spk.lib()
+    L.spk_debug_set_pack_chunk_rows.argtypes = [C.c_int64]
+    n, k = 1237, 21
+    a = oracle.gen_band(n, k, seed=3)
+    try:
+        L.spk_debug_set_pack_chunk_rows(64)
+        S = spk.Spike()
+        S.set_band_dense(a, k, spk.LAYOUT_ROWS)
+        np.testing.assert_array_equal(S.get_band_rows(), a)
+        S.factor()
+        b = oracle.band_mult(a, np.ones(n))
+        assert relerr(S.solve(b), np.ones(n)) < 1e-12
+        S.close()
+    finally:
+        L.spk_debug_set_pack_chunk_rows(0)
+
+
 # ------------------------------------------------------------------ MatMult
 @pytest.mark.parametrize("n,k", [(100, 3), (5000, 10), (20000, 50), (9999, 100)])
 def test_matmult_vs_oracle(spk, oracle, n, k):
