@@ -90,8 +90,9 @@ int spk_get_band_rows(spk_ctx *ctx, double *band_rows_host);
 /* PCSetUp(b->pc) at src/matbanded.c:178 (and MatLUFactor of a MATBANDED): per-partition banded LU
  * (no pivoting, diagonal boosting), spike tips V^(b)/W^(t), reduced-system factorisation. In place. */
 int spk_factor(spk_ctx *ctx);
-/* PCApply(b->pc,x,y) at src/matbanded.c:190 (and MatSolve): x = B^{-1} b for nrhs vectors of
- * leading dimension n.  b and x may alias. */
+/* PCApply(b->pc,x,y) at src/matbanded.c:190 (and MatSolve / MatMatSolve): x = B^{-1} b for nrhs vectors of
+ * leading dimension n.  b and x may alias.  nrhs >= 2 takes the block path: sweeps and window corrections run for
+ * 8 columns per warp as tile products on the FP64 tensor cores and read the band once per 32 columns. */
 int spk_solve(spk_ctx *ctx, const double *b, double *x, int nrhs);
 /* MatMult (src/testbed2.c:122 and inside the inner KSP) with the UNFACTORED band kept by
  * spk_keep_original(ctx,1) or, before spk_factor, with the band itself. */

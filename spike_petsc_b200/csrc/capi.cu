@@ -29,7 +29,7 @@ static void free_band(spk_ctx* c) {
   F(c->band); F(c->orig); F(c->dinv); F(c->d_pstart); F(c->Sb); F(c->St); F(c->Vb); F(c->Wt); F(c->Red);
   F(c->RedPiv); F(c->work); F(c->gtip); F(c->xtip); F(c->xb); F(c->xt); F(c->corr);
   F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->xtopRemote); F(c->xbBoundary); F(c->haloL); F(c->haloR);
-  F(c->opA.ia); F(c->opA.ja); F(c->opA.a); F(c->rscale); F(c->cscale);
+  F(c->opA.ia); F(c->opA.ja); F(c->opA.a); F(c->rscale); F(c->cscale); F(c->tips_mr); F(c->work_mr); c->nrhs_mr = 0;
   free(c->h_pstart); c->h_pstart = nullptr;
   spk_peer_release(c);   // the mailbox layout depends on kp
   c->have_band = c->factored = 0;
@@ -482,6 +482,42 @@ int spk_solve_dev(spk_ctx* c, const double* b, double* x) {
   return rc;
 }
 
+// Several right-hand sides (device pointers, column r at b + r*n): the partition sweeps run for all columns at
+// once on the tensor cores (msweep.cu: the band is read once per 32 columns), the O(P kp^2) reduced solves and the
+// window corrections are per column.
+static int solve_multi_dev(spk_ctx* c, const double* b, double* x, int nrhs) {
+  const int64_t n = c->L.n;
+  int rc = SPK_OK;
+  if (c->rscale) {
+    for (int r = 0; r < nrhs && rc == SPK_OK; ++r) rc = spk_launch_vec_scale(c, x + (size_t)r * n, b + (size_t)r * n, c->rscale, n);
+    if (rc) return rc;
+    b = x;
+  }
+  STAGE_BEGIN(c, 3);
+  rc = spk_launch_msweep(c, b, x, nrhs, n);
+  STAGE_END(c, 3);
+  if (rc) return rc;
+  if (c->P > 1) {
+    // scratch for all columns: coupling right-hand sides (2*P*kp each) and the forward results of the window sweeps
+    const int64_t npad = c->L.nt * 8;
+    if (c->nrhs_mr < nrhs) {
+      if (c->tips_mr) { cudaFree(c->tips_mr); c->tips_mr = nullptr; }
+      if (c->work_mr) { cudaFree(c->work_mr); c->work_mr = nullptr; }
+      c->nrhs_mr = 0;
+      SPK_CUDA(c, cudaMalloc(&c->tips_mr, sizeof(double) * 2 * (size_t)c->P * c->kp * nrhs));
+      SPK_CUDA(c, cudaMalloc(&c->work_mr, sizeof(double) * (size_t)npad * nrhs));
+      c->nrhs_mr = nrhs;
+    }
+    SPK_CUDA(c, cudaMemsetAsync(c->tips_mr, 0, sizeof(double) * 2 * (size_t)c->P * c->kp * nrhs, c->stream));
+    STAGE_BEGIN(c, 4); rc = spk_launch_reduced_solve_multi(c, x, nrhs, n, c->tips_mr); STAGE_END(c, 4);
+    if (rc) return rc;
+    STAGE_BEGIN(c, 5); rc = spk_launch_mcorrections(c, x, nrhs, n, c->tips_mr, c->work_mr, npad); STAGE_END(c, 5);
+    if (rc) return rc;
+  }
+  for (int r = 0; r < nrhs && rc == SPK_OK && c->cscale; ++r) rc = spk_launch_vec_scale(c, x + (size_t)r * n, x + (size_t)r * n, c->cscale, n);
+  return rc;
+}
+
 // split-phase solve for a sharded context (device pointers, one right-hand side):
 //   phase 0: g = D^-1 b                      -> exchange SPK_BND_G_TOP (to the left rank)
 //   phase 1: reduced systems (incl. boundary) -> exchange SPK_BND_X_BOT (to the right rank)
@@ -533,7 +569,8 @@ extern "C" int spk_solve(spk_ctx* c, const double* b, double* x, int nrhs) {
   const int launches0 = c->launches;
   SPK_CUDA(c, cudaEventRecord(c->evs0, c->stream));
   int rc = SPK_OK;
-  for (int r = 0; r < nrhs && rc == SPK_OK; ++r) rc = spk_solve_dev(c, bd + (size_t)r * n, xd + (size_t)r * n);
+  if (nrhs >= 2) rc = solve_multi_dev(c, bd, xd, nrhs);
+  else rc = spk_solve_dev(c, bd, xd);
   if (rc == SPK_OK) {
     cudaError_t e = cudaEventRecord(c->evs1, c->stream);
     c->timed_solve = 1;

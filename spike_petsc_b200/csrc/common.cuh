@@ -76,6 +76,7 @@ struct spk_ctx {
   double *mbox, *peer_mbox[2];
   int peer_ipc[2];
   unsigned long long peer_seq_out[3], peer_seq_in[3];
+  double *tips_mr, *work_mr; int nrhs_mr;   // multi-right-hand-side scratch (grow-only): coupling right-hand sides, sweep results
   double *rscale, *cscale;   // optional equilibration (spk_set_scaling): the factored band is diag(r) A diag(c)
   // operator for Krylov
   CsrDev opA;
@@ -168,7 +169,10 @@ int spk_launch_ul_tips(spk_ctx* c);       // UL window -> S_t
 int spk_launch_tips(spk_ctx* c, int what, int unused);  // 0: local tips + reduced blocks, 1: boundary reduced block
 int spk_launch_rtop_left(spk_ctx* c);
 int spk_launch_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld);   // g = D^-1 b
+int spk_launch_msweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld);   // g = D^-1 b, nrhs columns at once (msweep.cu)
 int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int iface_lo, int iface_hi);
 int spk_launch_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld);
+int spk_launch_reduced_solve_multi(spk_ctx* c, double* x, int nrhs, int64_t ld, double* tips);
+int spk_launch_mcorrections(spk_ctx* c, double* x, int nrhs, int64_t ld, const double* tips, double* work, int64_t ld_work);
 int spk_launch_gather(spk_ctx* c, const int* idx_dev, int inverse, const double* in, double* out, int64_t n);
 int spk_launch_csr_mult(spk_ctx* c, const CsrDev& A, const double* x, double* y);

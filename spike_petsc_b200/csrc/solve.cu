@@ -299,6 +299,7 @@ struct RedSolveArgs {
   int boundary_iface;          // interface index served with remote data (-1: none)
   const double* remoteWt; const double* remoteGtop; double* xbBoundary;
   int64_t n;
+  int64_t x_stride; size_t tip_stride;   // several right-hand sides: blockIdx.y selects x + y*x_stride, rtop/rbot + y*tip_stride
 };
 // out[r] = base[r] - sum_c M[r*kp+c] v[c] (or just the product when base == nullptr).  8 warps; each warp
 // takes 4 rows per pass and issues all their loads before the shuffle reductions (memory-level
@@ -342,9 +343,12 @@ __global__ void __launch_bounds__(1024) k_reduced_solve(const RedSolveArgs a) {
   const bool bnd = (i == a.boundary_iface);
   const int64_t tb = a.pstart[i + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double* xg = a.x + (size_t)blockIdx.y * a.x_stride;
+  double* const rtop_o = a.rtop + (size_t)blockIdx.y * a.tip_stride;
+  double* const rbot_o = a.rbot + (size_t)blockIdx.y * a.tip_stride;
   for (int e = threadIdx.x; e < kp; e += blockDim.x) {
-    gb[e] = a.x[(tb - KT) * 8 + e];
-    gt[e] = bnd ? a.remoteGtop[e] : ((tb * 8 + e < a.n) ? a.x[tb * 8 + e] : 0.0);
+    gb[e] = xg[(tb - KT) * 8 + e];
+    gt[e] = bnd ? a.remoteGtop[e] : ((tb * 8 + e < a.n) ? xg[tb * 8 + e] : 0.0);
   }
   __syncthreads();
   const double* W = bnd ? a.remoteWt : a.Wt + (size_t)(i + 1) * kp * kp;
@@ -365,8 +369,8 @@ __global__ void __launch_bounds__(1024) k_reduced_solve(const RedSolveArgs a) {
     }
     for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
     if (lane == 0) {
-      if (!bnd) a.rtop[(size_t)(i + 1) * kp + r] = s1; else a.xbBoundary[r] = xb[r];
-      a.rbot[(size_t)i * kp + r] = s2;
+      if (!bnd) rtop_o[(size_t)(i + 1) * kp + r] = s1; else a.xbBoundary[r] = xb[r];
+      rbot_o[(size_t)i * kp + r] = s2;
     }
   }
 }
@@ -403,11 +407,35 @@ int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int if
     a.first_iface = iface_lo;
     a.boundary_iface = has_right ? c->P - 1 : -1;
     a.remoteWt = c->remoteWt; a.remoteGtop = c->remoteGtop; a.xbBoundary = c->xbBoundary; a.n = c->L.n;
+    a.x_stride = 0; a.tip_stride = 0;
     // as many warps per CTA as keep every interface resident at once (2048 threads per SM): 32 warps = one pass per
     // block mat-vec when there are at most two interfaces per SM
     const int per_sm = (n + c->sm_count - 1) / c->sm_count;
     const int threads = std::max(256, std::min(1024, (2048 / std::max(per_sm, 1)) / 32 * 32));
     k_reduced_solve<<<n, threads, sizeof(double) * 5 * c->kp, c->stream>>>(a);
+    SPK_KERNEL_CHECK(c);
+  }
+  return SPK_OK;
+}
+
+// All right-hand sides in one launch (grid.y = column): tips[r] = rtop | rbot of column r, 2*P*kp doubles each.
+// Single-rank contexts (no boundary interface).
+int spk_launch_reduced_solve_multi(spk_ctx* c, double* x, int nrhs, int64_t ld, double* tips) {
+  const int n = c->P - 1;
+  if (n <= 0) return SPK_OK;
+  RedSolveArgs a;
+  a.band = c->band; a.L = c->L; a.pstart = c->d_pstart; a.Vb = c->Vb; a.Wt = c->Wt; a.Rinv = c->Red;
+  a.x = x; a.rtop = tips; a.rbot = tips + (size_t)c->P * c->kp;
+  a.first_iface = 0; a.boundary_iface = -1;
+  a.remoteWt = c->remoteWt; a.remoteGtop = c->remoteGtop; a.xbBoundary = c->xbBoundary; a.n = c->L.n;
+  a.x_stride = ld; a.tip_stride = 2 * (size_t)c->P * c->kp;
+  for (int r0 = 0; r0 < nrhs; r0 += 65535) {
+    const int nr = std::min(nrhs - r0, 65535);
+    const int per_sm = (int)(((int64_t)n * nr + c->sm_count - 1) / c->sm_count);
+    const int threads = std::max(256, std::min(1024, (2048 / std::max(per_sm, 1)) / 32 * 32));
+    RedSolveArgs b = a;
+    b.x = x + (size_t)r0 * ld; b.rtop = a.rtop + (size_t)r0 * a.tip_stride; b.rbot = a.rbot + (size_t)r0 * a.tip_stride;
+    k_reduced_solve<<<dim3(n, nr), threads, sizeof(double) * 5 * c->kp, c->stream>>>(b);
     SPK_KERNEL_CHECK(c);
   }
   return SPK_OK;
