@@ -97,6 +97,10 @@ int spk_solve(spk_ctx *ctx, const double *b, double *x, int nrhs);
 /* MatMult (src/testbed2.c:122 and inside the inner KSP) with the UNFACTORED band kept by
  * spk_keep_original(ctx,1) or, before spk_factor, with the band itself. */
 int spk_mult(spk_ctx *ctx, const double *x, double *y);
+/* keep != 0: keep a copy of the unfactored band (call before the band is set, or before spk_factor).  spk_factor
+ * then reads that copy and writes the factors into the working band (out of place, same traffic), so it can be
+ * called again -- PCSetUp after PCReset with an unchanged operator -- without setting the band anew.  Without it
+ * the factorisation is in place and a second spk_factor is an error. */
 int spk_keep_original(spk_ctx *ctx, int keep);
 
 /* VecPermute (src/kspreorder.c:122-127): inverse=0: v[i] <- v[idx[i]];  inverse=1: v[idx[i]] <- v[i].

@@ -396,7 +396,8 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   int rc = SPK_OK;
   if (phase == 0) {
-    if (c->factored) { SPK_SET_ERR(c, "band already factored (factorisation is in place)"); return SPK_ERR_STATE; }
+    if (c->factored && spk_lu_source(c) == c->band) { SPK_SET_ERR(c, "band already factored (the factorisation is in place unless spk_keep_original(ctx,1) kept the unfactored band)"); return SPK_ERR_STATE; }
+    c->factored = 0;
     c->launches = 0; c->have_remote_wt = 0; c->boundary_done = 0; c->wt_done = 0;
     SPK_CUDA(c, cudaMemsetAsync(c->d_boost, 0, sizeof(int64_t), c->stream));
     SPK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -407,7 +408,8 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
     return SPK_OK;
   }
   if (phase == 10) {   // overlapped protocol, step 1: tip windows and every W^(t) (the first one travels to the left neighbour)
-    if (c->factored) { SPK_SET_ERR(c, "band already factored (factorisation is in place)"); return SPK_ERR_STATE; }
+    if (c->factored && spk_lu_source(c) == c->band) { SPK_SET_ERR(c, "band already factored (the factorisation is in place unless spk_keep_original(ctx,1) kept the unfactored band)"); return SPK_ERR_STATE; }
+    c->factored = 0;
     c->launches = 0; c->have_remote_wt = 0; c->boundary_done = 0; c->wt_done = 0;
     SPK_CUDA(c, cudaMemsetAsync(c->d_boost, 0, sizeof(int64_t), c->stream));
     SPK_CUDA(c, cudaEventRecord(c->ev0, c->stream));

@@ -97,6 +97,8 @@ struct spk_ctx {
 };
 
 void spk_peer_release(spk_ctx* c);   // peer.cu
+// band the LU and the tip windows read: the kept original if there is one that still equals the unfactored band
+static inline double* spk_lu_source(spk_ctx* c) { return (c->orig && !c->rscale) ? c->orig : c->band; }
 int spk_bnd_desc(spk_ctx* c, int which, double** ptr, size_t* count, int* is_out);   // capi.cu
 
 #define SPK_SET_ERR(ctx, ...) do { if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); } while (0)

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
       LU_TRV(11, x.x);
       __syncwarp();
       if (lane == 0) mbar_arrive(xfull_bar(s));   // D_s^-1 is published
-      if (!REV) *reinterpret_cast<double2*>(tptr(s, s) + 2 * lane) = x;  // factor output
+      if (!REV) *reinterpret_cast<double2*>(tptr(s, s) + a.dst_off + 2 * lane) = x;  // factor output
       LU_TR(12);
     }
     if (lane == 0 && nboost) atomicAdd((unsigned long long*)a.boost_count, (unsigned long long)nboost);
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     {
       const double2 xc = *reinterpret_cast<const double2*>(&S.XC[slot][2 * lane]);
       dmma_cc(w, ut, xc);                        // Ub^T = U^T X^T
-      if (!REV && s + cj < T) stT(pf - KT * RS, cfrag_transpose(w, g, tq));   // Ub, the stored factor
+      if (!REV && s + cj < T) stT(pf + a.dst_off - KT * RS, cfrag_transpose(w, g, tq));   // Ub, the stored factor
       w = neg2(w);                               // the update subtracts: A~ += A~(.,s) (-Ub); the package holds +A~(.,s)
     }
     if (warp == 0) LU_TR(2);
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     auto pub = [&](int i, const double2& t) {
       if (i >= 2 && own_next) {
         stT_s(pkn + (i - 2) * 64, t);
-        if (!REV && s + i < T) stT(pf - (KT - i) * RS, t);   // factor output of the new pivot column
+        if (!REV && s + i < T) stT(pf + a.dst_off - (KT - i) * RS, t);   // factor output of the new pivot column
         // tiles are announced in groups of LU_PUBG (one mbarrier per group: fewer warp syncs + arrivals on the
         // producer's in-order stream, which everybody else's next step hangs on)
         if ((i - 2) % LU_PUBG == LU_PUBG - 1 || i - 2 == KT - 2) {
@@ -364,7 +364,11 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
 template <int KT, bool REV, bool TRACE>
 static int launch_lu_kt(spk_ctx* c, int grid, int first_part) {
   LuArgs a;
-  a.band = c->band; a.schur = REV ? c->St : c->Sb; a.pstart = c->d_pstart;
+  // out of place when the unfactored band is kept (and not equilibrated in place afterwards): read the original,
+  // write the factors -- the same 2B of traffic, and the factorisation can be repeated without restoring anything
+  double* src = spk_lu_source(c);
+  a.band = src; a.dst_off = (long long)(c->band - src);
+  a.schur = REV ? c->St : c->Sb; a.pstart = c->d_pstart;
   a.boost_count = (long long*)c->d_boost; a.tpr = c->L.tpr; a.tipT = c->tipT; a.first_part = first_part;
   a.boost_thr = c->opts.boost_rel * c->anorm_max;
   a.trace = (long long*)c->lu_trace;

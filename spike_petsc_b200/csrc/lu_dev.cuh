@@ -22,7 +22,9 @@
 #define LU_BAR_TILES 4
 
 struct LuArgs {
-  double* band;
+  double* band;           // the band the tiles are READ from (the kept original when there is one, else = destination)
+  long long dst_off;      // destination band - source band, in doubles: factor tiles are written to band + dst_off
+                          // (tiles the elimination never rewrites -- band-edge tiles, coupling blocks -- are equal in both)
   double* schur;          // P * kp*kp : S_b (FWD) or S_t (REV)
   const int64_t* pstart;  // P+1 tile-row boundaries
   long long* boost_count;

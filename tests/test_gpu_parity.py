@@ -174,6 +174,26 @@ def test_multi_rhs_tensor_core_sweeps(spk, oracle, n, k, P, nrhs):
     S.close()
 
 
+def test_refactor_reads_the_kept_original(spk, oracle):
+    """With spk_keep_original(ctx,1) the LU reads the kept unfactored band and writes the factors into the working band,
+    so spk_factor can be repeated (PCSetUp after a reset) and gives bit-identical factors and solutions."""
+    n, k = 20_000, 40
+    a = oracle.gen_band(n, k)
+    b = oracle.band_mult(a, np.ones(n))
+    S = spk.Spike(partitions=5)
+    S.keep_original(True)
+    S.set_band_dense(a, k)
+    S.factor()
+    f1, x1 = S.get_band_rows().copy(), S.solve(b).copy()
+    S.factor()
+    S.factor()
+    np.testing.assert_array_equal(S.get_band_rows(), f1)
+    np.testing.assert_array_equal(S.solve(b), x1)
+    assert relerr(x1, np.ones(n)) < 1e-12
+    assert relerr(S.mult(np.ones(n)), b) < 1e-14
+    S.close()
+
+
 def test_gpu_tips_match_oracle_tips(spk, oracle):
     """Same partitioning on CPU and GPU -> identical truncated-SPIKE answer (not only the exact one)."""
     n, k, P = 24_000, 40, 6
