@@ -290,15 +290,14 @@ __global__ void __launch_bounds__(TIPS_THREADS) k_reduced_factor(const RedArgs a
 
 // ============================================================================================
 // Register-resident variant for kt <= GJ_MAX_KT (the common case; K = 100 -> kt = 13): the same dataflow as the
-// band LU (lu.cu).  One warp per tile COLUMN of the augmented matrix [M | X] keeps its kt tiles in registers as
-// DMMA accumulators for the whole elimination (2*kt warps), one more warp inverts pivot tiles one step ahead.
-// Per block step k the only shared-memory traffic is the broadcast of column k (kt tiles, written once by its
-// owner, read by every live column warp as the left DMMA operand) and of D_k^-1; there are no index loops:
-// the step loop is unrolled, every tile index is a compile-time constant.
-//   live columns at step k:  M columns J > k (J <= k are unit columns by then),  X columns with xfirst <= k
+// band LU (lu.cu).  One warp per tile COLUMN keeps its kt tiles in registers as DMMA accumulators for the whole
+// elimination, one more warp inverts pivot tiles one step ahead.  Per block step k the only shared-memory traffic is
+// the broadcast of column k (kt tiles, written once by its owner, read by every column warp as the left DMMA
+// operand) and of D_k^-1; there are no index loops: the step loop is unrolled, every tile index is a compile-time
+// constant.
 //   t = D_k^-1 Aug(k,J) (DMMA pair on the register-transposed tile), Aug(I,J) -= Aug(I,k) t for I != k.
-// The owner of column k+1 updates row k+1 first and hands that tile (the next pivot block) to the inverting
-// warp at once, then publishes its finished column for step k+1; one CTA-wide barrier per step.
+// The owner of the next pivot column updates the next pivot row first and hands that tile (the next pivot block) to
+// the inverting warp at once, then publishes its finished column for the next step; one CTA-wide barrier per step.
 #define GJ_MAX_KT 13
 #define GJ_BAR_ALL 1
 #define GJ_BAR_D 4        // named barriers 4,5: pivot tile D_k handed to the inverting warp
@@ -310,7 +309,7 @@ struct GjSmem {
 };
 
 // the inverting warp (index 2*KT; it never holds a column: called before any accumulator exists)
-template <int KT>
+template <int KT, int NTHR>
 __device__ __noinline__ void gj_invert_loop(GjSmem<KT>& S, double thr) {
   const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
   const double rthr = 1.0 / thr;
@@ -318,95 +317,107 @@ __device__ __noinline__ void gj_invert_loop(GjSmem<KT>& S, double thr) {
     named_bar_sync(GJ_BAR_D + (k & 1), 64);
     const double2 d = *reinterpret_cast<const double2*>(&S.tD[k & 1][2 * lane]);
     *reinterpret_cast<double2*>(&S.XC[k & 1][2 * lane]) = tip_invert8(d, g, tq, thr, rthr);
-    named_bar_sync(GJ_BAR_ALL, (2 * KT + 1) * 32);   // barrier #k
+    named_bar_sync(GJ_BAR_ALL, NTHR);   // barrier #k
   }
 }
 
-template <int KT>
-__device__ __forceinline__ void gj_eliminate(GjSmem<KT>& S, double2 (&acc)[KT], int col, int xfirst) {
+// ---- column j of M and column j of X share one warp ------------------------------------------------------
+// When the right-hand side block is block triangular (B: X(I,J) = 0 for I < J; C: for I > J; identity) and the
+// pivots are taken in the matching order (top-down for B and the identity, bottom-up for C -- the order the UL
+// window itself eliminates in), column J of X is untouched until pivot step J, which is exactly the step at which
+// column J of M has been published as the pivot column and is never needed again.  The warp that owned M(:,J) then
+// loads X(:,J) into the same registers and carries it to the end.  KT column warps + the inverting warp = 448
+// threads at 72 registers for kt = 13: two solves per SM, all 295 interfaces of a 296-partition GPU resident at
+// once, and every warp has work in every step.
+template <int KT, bool REV, class XInit>
+__device__ __forceinline__ void gj_eliminate_shared(GjSmem<KT>& S, double2 (&acc)[KT], int col, XInit xinit) {
   const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
-  constexpr int NTHR = (2 * KT + 1) * 32;
-  auto give_d = [&](int k, const double2& t) {
-    *reinterpret_cast<double2*>(&S.tD[k & 1][2 * lane]) = t;
-    named_bar_arrive(GJ_BAR_D + (k & 1), 64);
+  constexpr int NTHR = (KT + 1) * 32;
+  auto give_d = [&](int st, const double2& t) {
+    *reinterpret_cast<double2*>(&S.tD[st & 1][2 * lane]) = t;
+    named_bar_arrive(GJ_BAR_D + (st & 1), 64);
   };
-  if (col == 0) {
-    give_d(0, acc[0]);
+  constexpr int P0 = REV ? KT - 1 : 0;
+  if (col == P0) {
+    give_d(0, acc[P0]);
 #pragma unroll
-    for (int I = 1; I < KT; ++I) *reinterpret_cast<double2*>(&S.PK[0][I][2 * lane]) = acc[I];
+    for (int I = 0; I < KT; ++I)
+      if (I != P0) *reinterpret_cast<double2*>(&S.PK[0][I][2 * lane]) = acc[I];
   }
 #pragma unroll
-  for (int k = 0; k < KT; ++k) {
-    named_bar_sync(GJ_BAR_ALL, NTHR);     // barrier #k: column k and D_k^-1 are in shared memory
-    const bool live = (col < KT) ? (col > k) : (k >= xfirst);
-    if (live) {
-      const double2 xc = *reinterpret_cast<const double2*>(&S.XC[k & 1][2 * lane]);
-      const double2 ut = cfrag_transpose(acc[k], g, tq);
-      double2 w = make_double2(0.0, 0.0);
-      dmma_cc(w, ut, xc);                                   // t^T = Aug(k,J)^T D^-T
-      acc[k] = cfrag_transpose(w, g, tq);                   // row k of the column becomes t
-      w = neg2(w);
-      const bool next_owner = (k + 1 < KT) && (col == k + 1);
-      // operand tiles through volatile loads, one tile ahead of the tensor pipe (a hoisted batch would spill)
-      const uint32_t pk = smem_u32(&S.PK[k & 1][0][2 * lane]);
-      double2 avn = lds_v2(pk + ((k + 1) % KT) * 512);
+  for (int st = 0; st < KT; ++st) {
+    const int k = REV ? KT - 1 - st : st;          // pivot block of this step (compile-time after unrolling)
+    const int kn = REV ? k - 1 : k + 1;            // the next one
+    named_bar_sync(GJ_BAR_ALL, NTHR);              // column k of M and D_k^-1 are in shared memory
+    if (col == k) xinit(acc, k);                   // my M column is the published pivot column: switch to X(:,k)
+    const double2 xc = *reinterpret_cast<const double2*>(&S.XC[st & 1][2 * lane]);
+    const double2 ut = cfrag_transpose(acc[k], g, tq);
+    double2 w = make_double2(0.0, 0.0);
+    dmma_cc(w, ut, xc);                            // t^T = Aug(k,J)^T D^-T
+    acc[k] = cfrag_transpose(w, g, tq);
+    w = neg2(w);
+    const bool next_owner = (st + 1 < KT) && (col == kn);
+    const uint32_t pk = smem_u32(&S.PK[st & 1][0][2 * lane]);
+    double2 avn = lds_v2(pk + (REV ? (k - 1 + KT) % KT : (k + 1) % KT) * 512);
 #pragma unroll
-      for (int ii = 1; ii < KT; ++ii) {
-        const int I = (k + ii) % KT;                        // compile-time after unrolling; row k+1 first
-        const double2 av = avn;
-        if (ii + 1 < KT) avn = lds_v2(pk + ((k + ii + 1) % KT) * 512);
-        dmma_cc(acc[I], av, w);                             // Aug(I,J) -= Aug(I,k) t
-        if (ii == 1 && next_owner) give_d(k + 1, acc[I]);   // the next pivot block is final
-      }
-      if (next_owner) {
+    for (int ii = 1; ii < KT; ++ii) {
+      const int I = REV ? (k - ii + KT) % KT : (k + ii) % KT;      // the next pivot row first
+      const double2 av = avn;
+      if (ii + 1 < KT) avn = lds_v2(pk + (REV ? (k - ii - 1 + 2 * KT) % KT : (k + ii + 1) % KT) * 512);
+      dmma_cc(acc[I], av, w);
+      if (ii == 1 && next_owner) give_d(st + 1, acc[I]);
+    }
+    if (next_owner) {
 #pragma unroll
-        for (int I = 0; I < KT; ++I)
-          if (I != k + 1) *reinterpret_cast<double2*>(&S.PK[(k + 1) & 1][I][2 * lane]) = acc[I];
-      }
+      for (int I = 0; I < KT; ++I)
+        if (I != kn) *reinterpret_cast<double2*>(&S.PK[(st + 1) & 1][I][2 * lane]) = acc[I];
     }
   }
 }
 
-template <int KT>
-__global__ void __launch_bounds__((2 * KT + 1) * 32, 1) k_spike_tip_gj(const TipArgs a) {
-  __shared__ __align__(16) GjSmem<KT> S;
+// WHICH = 0: V^(b) = S_b^-1 B (top-down), WHICH = 1: W^(t) = S_t^-1 C (bottom-up)
+template <int KT, int WHICH>
+__global__ void __launch_bounds__((KT + 1) * 32, 2) k_spike_tip_gj2(const TipArgs a) {
+  extern __shared__ __align__(128) double sm[];
+  GjSmem<KT>& S = *reinterpret_cast<GjSmem<KT>*>(sm);
+  double* Xs = sm + sizeof(GjSmem<KT>) / sizeof(double);          // X(:,j) staged by warp j: tile (I,j) at (j*KT+I)*64
   const int col = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   constexpr int kp = KT * 8;
   const int p = blockIdx.x + a.first_part;
+  if (col == KT) { gj_invert_loop<KT, (KT + 1) * 32>(S, a.thr); return; }
   const double* Sg = a.S + (size_t)p * kp * kp;
   double* out = a.out + (size_t)p * kp * kp;
-  const int64_t tb = (a.which == 0) ? a.pstart[p + 1] : a.pstart[p];
-  if (col == 2 * KT) { gj_invert_loop<KT>(S, a.thr); return; }
-  double2 acc[KT];
-  int xfirst = 0;
-  const int J = col < KT ? col : col - KT;
-  if (col < KT) {
+  const int64_t tb = (WHICH == 0) ? a.pstart[p + 1] : a.pstart[p];
+  // my column of the coupling block goes to shared memory now (cp.async), into registers at my pivot step
 #pragma unroll
-    for (int I = 0; I < KT; ++I) acc[I] = *reinterpret_cast<const double2*>(Sg + (size_t)(8 * I + g) * kp + 8 * J + 2 * tq);
-  } else {
-    // right-hand side block straight from the (never overwritten) coupling tiles of the band (see k_spike_tip)
+  for (int I = 0; I < KT; ++I) {
+    const bool nz = (WHICH == 0) ? (col <= I) : (col >= I);
+    if (nz) {
+      const double* src = a.band + ((WHICH == 0) ? a.L.tile_off(tb - KT + I, tb + col) : a.L.tile_off(tb + I, tb - KT + col)) + 2 * lane;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(Xs + ((size_t)col * KT + I) * 64 + 2 * lane)), "l"(src) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  double2 acc[KT];
+#pragma unroll
+  for (int I = 0; I < KT; ++I) acc[I] = *reinterpret_cast<const double2*>(Sg + (size_t)(8 * I + g) * kp + 8 * col + 2 * tq);
+  auto xinit = [&](double2 (&x)[KT], int k) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
 #pragma unroll
     for (int I = 0; I < KT; ++I) {
-      double2 v = make_double2(0.0, 0.0);
-      if (a.which == 0) { if (J <= I) v = *reinterpret_cast<const double2*>(a.band + a.L.tile_off(tb - KT + I, tb + J) + 2 * lane); }
-      else              { if (J >= I) v = *reinterpret_cast<const double2*>(a.band + a.L.tile_off(tb + I, tb - KT + J) + 2 * lane); }
-      acc[I] = v;
+      const bool nz = (WHICH == 0) ? (k <= I) : (k >= I);
+      x[I] = nz ? *reinterpret_cast<const double2*>(Xs + ((size_t)k * KT + I) * 64 + 2 * lane) : make_double2(0.0, 0.0);
     }
-    xfirst = (a.which == 0) ? J : 0;
-  }
-  gj_eliminate<KT>(S, acc, col, xfirst);
-  if (col >= KT) {
+  };
+  gj_eliminate_shared<KT, WHICH == 1>(S, acc, col, xinit);
 #pragma unroll
-    for (int I = 0; I < KT; ++I) *reinterpret_cast<double2*>(out + (size_t)(8 * I + g) * kp + 8 * J + 2 * tq) = acc[I];
-  }
+  for (int I = 0; I < KT; ++I) *reinterpret_cast<double2*>(out + (size_t)(8 * I + g) * kp + 8 * col + 2 * tq) = acc[I];
 }
 
-// Rinv[i] = (I - Wt[i+1] Vb[i])^-1: the M-column warps form their column of I - W V in registers (W staged
-// tile-major in shared memory, the warp's V column transposed in registers), the X-column warps start from the
-// identity (column J lives from block step J on).
 template <int KT>
-__global__ void __launch_bounds__((2 * KT + 1) * 32, 1) k_reduced_factor_gj(const RedArgs a) {
+__global__ void __launch_bounds__((KT + 1) * 32, 2) k_reduced_factor_gj2(const RedArgs a) {
   extern __shared__ __align__(128) double sm[];
   GjSmem<KT>& S = *reinterpret_cast<GjSmem<KT>*>(sm);
   double* Ws = sm + sizeof(GjSmem<KT>) / sizeof(double);
@@ -418,43 +429,51 @@ __global__ void __launch_bounds__((2 * KT + 1) * 32, 1) k_reduced_factor_gj(cons
   const double* W = (i == a.remote_iface) ? a.remoteWt : a.Wt + (size_t)(i + a.wt_part_offset) * kp * kp;
   double* out = a.Rinv + (size_t)i * kp * kp;
   load_tiles(Ws, KT, W, kp, KT, 0, KT);
-  named_bar_sync(GJ_BAR_ALL, (2 * KT + 1) * 32);
-  if (col == 2 * KT) { gj_invert_loop<KT>(S, a.thr); return; }
-  double2 acc[KT];
-  const int J = col < KT ? col : col - KT;
+  named_bar_sync(GJ_BAR_ALL, (KT + 1) * 32);
+  if (col == KT) { gj_invert_loop<KT, (KT + 1) * 32>(S, a.thr); return; }
+  double2 acc[KT];   // column `col` of I - W V
 #pragma unroll
-  for (int I = 0; I < KT; ++I) acc[I] = make_double2((I == J && g == 2 * tq) ? 1.0 : 0.0, (I == J && g == 2 * tq + 1) ? 1.0 : 0.0);
-  if (col < KT) {
+  for (int I = 0; I < KT; ++I) acc[I] = make_double2((I == col && g == 2 * tq) ? 1.0 : 0.0, (I == col && g == 2 * tq + 1) ? 1.0 : 0.0);
 #pragma unroll 1
-    for (int q = 0; q < KT; ++q) {
-      const double2 vq = neg2(cfrag_transpose(*reinterpret_cast<const double2*>(V + (size_t)(8 * q + g) * kp + 8 * J + 2 * tq), g, tq));
+  for (int q = 0; q < KT; ++q) {
+    const double2 vq = neg2(cfrag_transpose(*reinterpret_cast<const double2*>(V + (size_t)(8 * q + g) * kp + 8 * col + 2 * tq), g, tq));
 #pragma unroll
-      for (int I = 0; I < KT; ++I) dmma_cc(acc[I], *reinterpret_cast<const double2*>(Ws + ((size_t)I * KT + q) * 64 + 2 * lane), vq);
-    }
+    for (int I = 0; I < KT; ++I) dmma_cc(acc[I], *reinterpret_cast<const double2*>(Ws + ((size_t)I * KT + q) * 64 + 2 * lane), vq);
   }
-  gj_eliminate<KT>(S, acc, col, col < KT ? 0 : J);
-  if (col >= KT) {
+  auto xinit = [&](double2 (&x)[KT], int k) {   // column k of the identity
 #pragma unroll
-    for (int I = 0; I < KT; ++I) *reinterpret_cast<double2*>(out + (size_t)(8 * I + g) * kp + 8 * J + 2 * tq) = acc[I];
-  }
+    for (int I = 0; I < KT; ++I) x[I] = make_double2((I == k && g == 2 * tq) ? 1.0 : 0.0, (I == k && g == 2 * tq + 1) ? 1.0 : 0.0);
+  };
+  gj_eliminate_shared<KT, false>(S, acc, col, xinit);
+#pragma unroll
+  for (int I = 0; I < KT; ++I) *reinterpret_cast<double2*>(out + (size_t)(8 * I + g) * kp + 8 * col + 2 * tq) = acc[I];
 }
 
 template <int KT>
-static void launch_tip_gj(spk_ctx* c, int grid, const TipArgs& t) {
-  k_spike_tip_gj<KT><<<grid, (2 * KT + 1) * 32, 0, c->stream>>>(t);
+static cudaError_t launch_tip_gj(spk_ctx* c, int grid, const TipArgs& t) {
+  const size_t smem = sizeof(GjSmem<KT>) + sizeof(double) * 64 * KT * KT;
+  cudaError_t e;
+  if (t.which == 0) {
+    e = cudaFuncSetAttribute(k_spike_tip_gj2<KT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_spike_tip_gj2<KT, 0><<<grid, (KT + 1) * 32, smem, c->stream>>>(t);
+  } else {
+    e = cudaFuncSetAttribute(k_spike_tip_gj2<KT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_spike_tip_gj2<KT, 1><<<grid, (KT + 1) * 32, smem, c->stream>>>(t);
+  }
+  return e;
 }
 template <int KT>
 static cudaError_t launch_red_gj(spk_ctx* c, int grid, const RedArgs& r) {
   const size_t smem = sizeof(GjSmem<KT>) + sizeof(double) * 64 * KT * KT;
-  cudaError_t e = cudaFuncSetAttribute(k_reduced_factor_gj<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_reduced_factor_gj2<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_reduced_factor_gj<KT><<<grid, (2 * KT + 1) * 32, smem, c->stream>>>(r);
+  k_reduced_factor_gj2<KT><<<grid, (KT + 1) * 32, smem, c->stream>>>(r);
   return cudaSuccess;
 }
 #define GJ_CASES CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
 static bool tip_launch(spk_ctx* c, int grid, const TipArgs& t, size_t smem_generic) {
   switch (c->L.kt) {
-#define CASE(K_) case K_: launch_tip_gj<K_>(c, grid, t); return true;
+#define CASE(K_) case K_: return launch_tip_gj<K_>(c, grid, t) == cudaSuccess;
     GJ_CASES
 #undef CASE
     default: k_spike_tip<<<grid, TIPS_THREADS, smem_generic, c->stream>>>(t); return true;
