@@ -79,12 +79,64 @@ class NumpyEngine:
             self.x.copy_(torch.from_numpy(self.g - np.linalg.solve(self.Aloc, r)))
 
 
+class MailboxEngine(NumpyEngine):
+    """The same engine with the peer-mailbox interface of the CUDA context (spk_peer_*): post = non-blocking send of
+    the boundary item to the neighbour, wait = receive + set_boundary.  Exercises ShardedSpike's mailbox protocol
+    (handle all-gather, phase order 10 / post / 11 / wait / 1 / 2, solve posts and waits) without a GPU."""
+    peer_capable = True
+    overlapped_factor = True
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self.peers, self.pending = {}, []
+
+    def factor_phase(self, ph):
+        if ph == 10:
+            super().factor_phase(1)          # W^(t) (and V^(b)) exist before the "LU" phase, as on the GPU
+        elif ph in (11, 1):
+            pass
+        else:
+            super().factor_phase(ph)
+
+    def peer_create(self):
+        return str(self.rank).encode().ljust(64, b" "), None
+
+    def peer_attach(self, side, handle=None, ptr=None):
+        self.peers[side] = int(handle.decode())
+
+    def _item(self, which):
+        from spike_petsc_b200 import capi
+        return {capi.BND_WT_FIRST: (0, self.k * self.k), capi.BND_G_TOP: (0, self.k), capi.BND_X_BOT: (1, self.k),
+                capi.BND_REMOTE_WT: (1, self.k * self.k), capi.BND_REMOTE_G_TOP: (1, self.k),
+                capi.BND_REMOTE_X_BOT: (0, self.k)}[which]
+
+    def peer_post(self, which):
+        side, n = self._item(which)
+        buf = torch.zeros(n, dtype=torch.float64)
+        self.get_boundary(which, buf)
+        self.pending.append((dist.isend(buf, self.peers[side], tag=which), buf))
+
+    def peer_wait(self, which):
+        from spike_petsc_b200 import capi
+        side, n = self._item(which)
+        buf = torch.zeros(n, dtype=torch.float64)
+        src_tag = {capi.BND_REMOTE_WT: capi.BND_WT_FIRST, capi.BND_REMOTE_G_TOP: capi.BND_G_TOP,
+                   capi.BND_REMOTE_X_BOT: capi.BND_X_BOT}[which]
+        dist.recv(buf, self.peers[side], tag=src_tag)
+        self.set_boundary(which, buf)
+
+    def peer_check(self):
+        for req, _ in self.pending:
+            req.wait()
+        self.pending = []
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
     return p
 
 
-def _worker(rank, world, port, n, k, out):
+def _worker(rank, world, port, n, k, out, mailbox=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -103,12 +155,17 @@ def _worker(rank, world, port, n, k, out):
         bfull = A @ u
         bounds = shard_rows(n, world)
         lo, hi = bounds[rank], bounds[rank + 1]
-        eng = NumpyEngine(A, lo, hi, k, rank, world)
+        eng = (MailboxEngine if mailbox else NumpyEngine)(A, lo, hi, k, rank, world)
         S = ShardedSpike(eng, rank, world)
         b = torch.from_numpy(bfull[lo:hi].copy())
         x = torch.zeros_like(b)
         S.factor(b)
         S.solve(b, x)
+        if mailbox:
+            assert S._peer is True
+            x.zero_()
+            S.solve(b, x)                    # a second solve on the same factorisation
+            S.check()
         err = float(np.abs(x.numpy() - u[lo:hi]).max())
         res = torch.tensor([err], dtype=torch.float64)
         dist.all_reduce(res, op=dist.ReduceOp.MAX)
@@ -118,12 +175,12 @@ def _worker(rank, world, port, n, k, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_exchange_protocol_gloo(world):
+@pytest.mark.parametrize("world,mailbox", [(2, False), (3, False), (2, True), (3, True)])
+def test_sharded_exchange_protocol_gloo(world, mailbox):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 480, 5, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 480, 5, q, mailbox)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
