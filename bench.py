@@ -89,10 +89,18 @@ def run_reference(args):
     reference's PCBANDED + `-banded_pc_type lu` computes it, run partition-parallel (OpenMP SPIKE port)
     on all host cores, on a bounded sample of the workload, scaled linearly in N."""
     import numpy as np
-    from oracle import oracle as O
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm uses every host core
+    if "TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    from oracle import oracle as O
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)))
+    except OSError:
+        pass
     cores = O.num_threads()
     n_s = 1_000_000          # 1/10 of the rows; banded factor/solve cost is linear in N at fixed K
     scale = N_ROWS / n_s
