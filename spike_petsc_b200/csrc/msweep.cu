@@ -108,8 +108,8 @@ __global__ void __launch_bounds__((MS_GROUPS + 1) * 32) k_msweep(const MSweepArg
   const size_t oA = (size_t)cA * (size_t)a.ld, oB = oA + (size_t)a.ld;
   const size_t wA = (size_t)cA * (size_t)a.ld_work, wB = wA + (size_t)a.ld_work;
   const int kp = KT * 8;
-  const double* rtA = a.tips + (size_t)cA * a.tip_stride + (size_t)p * kp;      // r_top of this partition, column cA
-  const double* rtB = rtA + a.tip_stride;
+  const double* rtA = corr ? a.tips + (size_t)cA * a.tip_stride + (size_t)p * kp : nullptr;   // r_top of this partition, column cA
+  const double* rtB = corr ? rtA + a.tip_stride : nullptr;
   const size_t rb_off = (size_t)a.P * kp;                                         // r_bot sits P*kp behind r_top
   // right-hand side block of tile row I for the forward sweep / input block for the backward sweep
   auto ldv = [&](bool fwd, int64_t I) -> double2 {
