@@ -73,6 +73,8 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
   const int64_t t0 = a.pstart[part];
   const int64_t plen = a.pstart[part + 1] - t0;
   const int T = REV ? (int)(plen < a.tipT ? plen : a.tipT) : (int)plen;
+  // steps to run: the tip window only wants the Schur block that is complete once step T-KT-1 has finished
+  const int Tend = REV ? (T > KT ? T - KT : 0) : T;
   const int64_t base = REV ? (t0 + T - 1) : t0;  // actual tile index of logical tile 0
   const int tpr = a.tpr;
 
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     const double thr = a.boost_thr, rthr = 1.0 / a.boost_thr;
     int nboost = 0;
     double2 x;
-    for (int s = 0; s < T; ++s) {
+    for (int s = 0; s < Tend; ++s) {
       LU_TR(8);
       double2 d, dt;
       if (s == 0) {
@@ -242,11 +244,11 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     reload_entering(0);
   }
 
-  for (int s = 0; s < T; ++s) {
+  for (int s = 0; s < Tend; ++s) {
     const int cj = (jrel == 0) ? KT : jrel;
     const int slot = s % LU_R;
     // the warp that owns the NEXT pivot column publishes package(s+1) tile by tile while it updates them
-    const bool own_next = (jrel == 1) && (s + 1 < T);
+    const bool own_next = (jrel == 1) && (s + 1 < Tend);
     double* const pkn = &S.PK[(s + 1) % LU_R][0][0];
     if (own_next) { wait_slot_free(s + 1); stage_edge(s + 1, pf + RS); }
     // ---- independent of the package: the entering row tile lands in shared memory; L2 prefetch two steps ahead
