@@ -68,7 +68,9 @@ int spk_destroy(spk_ctx **ctx);
 
 /* ---- band definition -------------------------------------------------------------------------- */
 /* Dense band in host or device memory.  ROWS: a[i*(2k+1) + (j-i+k)];  DIAGS: a[(j-i+k)*n + i].
- * Replaces holding B as AIJ (PC_Banded.B, src/matbanded.c:114). */
+ * Replaces holding B as AIJ (PC_Banded.B, src/matbanded.c:114).  For a shard (opts.nranks > 1) n is the number of
+ * local rows and j the local column index: entries with j < 0 or j >= n that exist in the global matrix
+ * (opts.row_offset, opts.n_global) are the coupling blocks to the neighbour ranks and are kept. */
 int spk_set_band_dense(spk_ctx *ctx, int64_t n, int k, const double *band, int layout, int mem);
 
 /* MatCreateSubMatrixBanded (src/matbanded.h:5, src/matbanded.c:22-107) fused with the MatPermute of
@@ -119,7 +121,9 @@ int spk_krylov(spk_ctx *ctx, int method, int restart, double rtol, int maxit, co
  * spk_factor; spk_solve and the spk_krylov preconditioner then apply diag(c) (scaled band)^-1 diag(r), i.e. the
  * inverse of the ORIGINAL band.  rscale = exp(u), cscale = exp(v) of MC64 job 5 are the scalings the reference
  * computes and discards (src/petsc_mat_wbm.c:56; AWBM: src/petsc_mat_awbm.c:208-223).  n entries each, memory
- * space per opts.mem.  spk_mult keeps using the unscaled original.  Single-rank contexts only. */
+ * space per opts.mem.  spk_mult keeps using the unscaled original.  Sharded contexts (nranks > 1) pass n + 2*kp
+ * column scales: the left neighbour's last kp, their own n, the right neighbour's first kp (the coupling blocks
+ * live in this rank's halo tiles); entries towards a missing neighbour are ignored. */
 int spk_set_scaling(spk_ctx *ctx, const double *rscale, const double *cscale);
 
 /* PCView_Banded (src/matbanded.c:196-211) */

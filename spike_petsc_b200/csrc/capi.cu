@@ -29,7 +29,7 @@ static void free_band(spk_ctx* c) {
   F(c->band); F(c->orig); F(c->dinv); F(c->d_pstart); F(c->Sb); F(c->St); F(c->Vb); F(c->Wt); F(c->Red);
   F(c->RedPiv); F(c->work); F(c->gtip); F(c->xtip); F(c->xb); F(c->xt); F(c->corr);
   F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->xtopRemote); F(c->xbBoundary); F(c->haloL); F(c->haloR);
-  F(c->opA.ia); F(c->opA.ja); F(c->opA.a); F(c->rscale); F(c->cscale); F(c->tips_mr); F(c->work_mr); c->nrhs_mr = 0;
+  F(c->opA.ia); F(c->opA.ja); F(c->opA.a); F(c->rscale); F(c->cscale_base); c->cscale = nullptr; F(c->tips_mr); F(c->work_mr); c->nrhs_mr = 0;
   free(c->h_pstart); c->h_pstart = nullptr;
   spk_peer_release(c);   // the mailbox layout depends on kp
   c->have_band = c->factored = 0;
@@ -172,15 +172,20 @@ static int finish_band(spk_ctx* c) {
 extern "C" int spk_set_scaling(spk_ctx* c, const double* rscale, const double* cscale) {
   if (!c || !rscale || !cscale) return SPK_ERR_ARG;
   if (!c->have_band || c->factored) { SPK_SET_ERR(c, "spk_set_scaling: set the band first and scale it before spk_factor"); return SPK_ERR_STATE; }
-  if (c->opts.nranks > 1) { SPK_SET_ERR(c, "spk_set_scaling: not available for sharded contexts yet (the halo columns need the neighbours' scales)"); return SPK_ERR_UNSUPPORTED; }
   if (c->rscale) { SPK_SET_ERR(c, "spk_set_scaling: the band is already scaled"); return SPK_ERR_STATE; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   const size_t bytes = sizeof(double) * (size_t)c->L.n;
   const cudaMemcpyKind kind = c->opts.mem == SPK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  // column scales with kp halo entries on either side: a sharded context passes n + 2*kp values (the neighbours'
+  // last / first kp column scales around its own), a single-rank one just its n
+  const size_t kp = (size_t)c->kp;
+  const bool sharded = c->opts.nranks > 1;
   SPK_CUDA(c, cudaMalloc(&c->rscale, bytes));
-  SPK_CUDA(c, cudaMalloc(&c->cscale, bytes));
+  SPK_CUDA(c, cudaMalloc(&c->cscale_base, bytes + 2 * kp * sizeof(double)));
+  c->cscale = c->cscale_base + kp;
   SPK_CUDA(c, cudaMemcpyAsync(c->rscale, rscale, bytes, kind, c->stream));
-  SPK_CUDA(c, cudaMemcpyAsync(c->cscale, cscale, bytes, kind, c->stream));
+  if (sharded) SPK_CUDA(c, cudaMemcpyAsync(c->cscale_base, cscale, bytes + 2 * kp * sizeof(double), kind, c->stream));
+  else SPK_CUDA(c, cudaMemcpyAsync(c->cscale, cscale, bytes, kind, c->stream));
   int rc = spk_launch_scale_band(c, c->rscale, c->cscale);
   if (rc) return rc;
   rc = spk_launch_absmax(c, c->band, c->d_scalar);   // the boosting threshold follows the scaled band
@@ -534,6 +539,11 @@ extern "C" int spk_solve_phase(spk_ctx* c, int phase, const double* b, double* x
     if (!b || !x) return SPK_ERR_ARG;
     c->cur_x = x;
     SPK_CUDA(c, cudaEventRecord(c->evs0, c->stream));
+    if (c->rscale) {   // equilibrated band: the sweeps run in place on diag(r) b
+      rc = spk_launch_vec_scale(c, x, b, c->rscale, c->L.n);
+      if (rc) return rc;
+      b = x;
+    }
     STAGE_BEGIN(c, 3); rc = spk_launch_sweep(c, b, x, 1, c->L.n); STAGE_END(c, 3);
     return rc;
   }
@@ -547,6 +557,7 @@ extern "C" int spk_solve_phase(spk_ctx* c, int phase, const double* b, double* x
     if (c->opts.rank > 0) rc = spk_launch_rtop_left(c);
     if (rc == SPK_OK) rc = spk_launch_corrections(c, c->cur_x, 1, c->L.n);
     STAGE_END(c, 5);
+    if (rc == SPK_OK && c->cscale) rc = spk_launch_vec_scale(c, c->cur_x, c->cur_x, c->cscale, c->L.n);
     SPK_CUDA(c, cudaEventRecord(c->evs1, c->stream));
     c->timed_solve = 1;
     return rc;

@@ -78,6 +78,7 @@ struct spk_ctx {
   unsigned long long peer_seq_out[3], peer_seq_in[3];
   double *tips_mr, *work_mr; int nrhs_mr;   // multi-right-hand-side scratch (grow-only): coupling right-hand sides, sweep results
   double *rscale, *cscale;   // optional equilibration (spk_set_scaling): the factored band is diag(r) A diag(c)
+  double *cscale_base;       // allocation behind cscale: [kp left-halo scales | n local | kp right-halo scales]
   // operator for Krylov
   CsrDev opA;
   // bookkeeping

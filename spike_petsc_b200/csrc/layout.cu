@@ -46,7 +46,9 @@ int spk_launch_generate(spk_ctx* c, uint64_t seed, double delta) {
 // --------------------------------------------------------------------------------------------
 // dense band (ROWS or DIAGS layout, device memory) -> tile-major band
 // --------------------------------------------------------------------------------------------
-__global__ void k_pack_dense(const double* __restrict__ src, double* __restrict__ band, BandLayout L, int layout) {
+// Columns are kept while they exist in the GLOBAL matrix, local columns [jlo, jhi): a shard's rows keep the entries
+// that reach into its neighbours' columns (they land in the halo tiles = the coupling blocks).
+__global__ void k_pack_dense(const double* __restrict__ src, double* __restrict__ band, BandLayout L, int layout, int64_t jlo, int64_t jhi) {
   const int64_t bw = 2 * (int64_t)L.k + 1;
   const int64_t total = L.n * bw;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -54,7 +56,7 @@ __global__ void k_pack_dense(const double* __restrict__ src, double* __restrict_
     if (layout == SPK_LAYOUT_ROWS) { i = e / bw; dk = e - i * bw; }
     else { dk = e / L.n; i = e - dk * L.n; }
     const int64_t j = i + dk - L.k;
-    if (j < 0 || j >= L.n) continue;
+    if (j < jlo || j >= jhi) continue;
     band[L.elem_off(i, j)] = src[e];
   }
 }
@@ -63,18 +65,20 @@ __global__ void k_pad_identity(double* __restrict__ band, BandLayout L) {
   if (i < L.nt * SPK_TILE) band[L.elem_off(i, i)] = 1.0;
 }
 // rows [row0, row0+nrows) of a ROWS-layout band, src pointing at the first of them (chunked host upload)
-__global__ void k_pack_rows_chunk(const double* __restrict__ src, double* __restrict__ band, BandLayout L, int64_t row0, int64_t nrows) {
+__global__ void k_pack_rows_chunk(const double* __restrict__ src, double* __restrict__ band, BandLayout L, int64_t row0, int64_t nrows,
+                                  int64_t jlo, int64_t jhi) {
   const int64_t bw = 2 * (int64_t)L.k + 1;
   const int64_t total = nrows * bw;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t il = e / bw, dk = e - il * bw;
     const int64_t i = row0 + il, j = i + dk - L.k;
-    if (j < 0 || j >= L.n) continue;
+    if (j < jlo || j >= jhi) continue;
     band[L.elem_off(i, j)] = src[e];
   }
 }
 int spk_launch_pack_rows_chunk(spk_ctx* c, const double* src_dev, int64_t row0, int64_t nrows) {
-  k_pack_rows_chunk<<<c->sm_count * 8, 256, 0, c->stream>>>(src_dev, c->band, c->L, row0, nrows);
+  const int64_t ng = c->opts.n_global > 0 ? c->opts.n_global : c->L.n;
+  k_pack_rows_chunk<<<c->sm_count * 8, 256, 0, c->stream>>>(src_dev, c->band, c->L, row0, nrows, -c->opts.row_offset, ng - c->opts.row_offset);
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }
@@ -86,7 +90,8 @@ int spk_launch_pack_finish(spk_ctx* c) {   // identity on the padded rows of the
 int spk_launch_pack_dense(spk_ctx* c, const double* src_dev, int layout) {
   const BandLayout& L = c->L;
   SPK_CUDA(c, cudaMemsetAsync(c->band, 0, sizeof(double) * (size_t)L.elems(), c->stream));
-  k_pack_dense<<<c->sm_count * 8, 256, 0, c->stream>>>(src_dev, c->band, L, layout);
+  const int64_t ng = c->opts.n_global > 0 ? c->opts.n_global : L.n;
+  k_pack_dense<<<c->sm_count * 8, 256, 0, c->stream>>>(src_dev, c->band, L, layout, -c->opts.row_offset, ng - c->opts.row_offset);
   SPK_KERNEL_CHECK(c);
   if (L.nt * SPK_TILE > L.n) { k_pad_identity<<<1, 8, 0, c->stream>>>(c->band, L); SPK_KERNEL_CHECK(c); }
   return SPK_OK;
@@ -97,7 +102,10 @@ int spk_launch_pack_dense(spk_ctx* c, const double* src_dev, int layout) {
 // the reference computes them and throws them away, src/petsc_mat_wbm.c:56).
 // One thread per entry pair of a tile: coalesced 16 B accesses, the scale vectors stay in L1/L2.
 // --------------------------------------------------------------------------------------------
-__global__ void k_scale_band(double* __restrict__ band, BandLayout L, const double* __restrict__ rs, const double* __restrict__ cs) {
+// cs points at the scale of local column 0; columns [clo, chi) are scaled: [0, n) on a single rank, reaching kp
+// entries into the neighbours' columns (the coupling blocks kept in the halo tiles) on a sharded one.
+__global__ void k_scale_band(double* __restrict__ band, BandLayout L, const double* __restrict__ rs, const double* __restrict__ cs,
+                             int64_t clo, int64_t chi) {
   const int64_t npairs = L.nt * (int64_t)L.tpr * 32;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < npairs; e += (int64_t)gridDim.x * blockDim.x) {
     const int pr = (int)(e & 31);
@@ -106,17 +114,19 @@ __global__ void k_scale_band(double* __restrict__ band, BandLayout L, const doub
     const int slot = (int)(t - I * L.tpr);
     const int64_t J = I + slot - L.kt;
     const int64_t i = I * 8 + (pr >> 2), j = J * 8 + (pr & 3) * 2;
-    if (J < 0 || J >= L.nt || i >= L.n) continue;
+    if (i >= L.n || j + 1 < clo || j >= chi) continue;
     double2* p = reinterpret_cast<double2*>(band + t * SPK_TILE_ELEMS) + pr;
     double2 v = *p;
     const double r = rs[i];
-    v.x = (j < L.n) ? r * v.x * cs[j] : v.x;
-    v.y = (j + 1 < L.n) ? r * v.y * cs[j + 1] : v.y;
+    v.x = (j >= clo && j < chi) ? r * v.x * cs[j] : v.x;
+    v.y = (j + 1 >= clo && j + 1 < chi) ? r * v.y * cs[j + 1] : v.y;
     *p = v;
   }
 }
 int spk_launch_scale_band(spk_ctx* c, const double* rs_dev, const double* cs_dev) {
-  k_scale_band<<<c->sm_count * 8, 256, 0, c->stream>>>(c->band, c->L, rs_dev, cs_dev);
+  const int64_t clo = c->opts.rank > 0 ? -(int64_t)c->kp : 0;
+  const int64_t chi = c->L.n + (c->opts.rank + 1 < c->opts.nranks ? (int64_t)c->kp : 0);
+  k_scale_band<<<c->sm_count * 8, 256, 0, c->stream>>>(c->band, c->L, rs_dev, cs_dev, clo, chi);
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }

@@ -210,6 +210,23 @@ class ShardedSpike:
         self.e.solve_phase(2)
         return xvec
 
+    def set_scaling(self, rscale, cscale):
+        """Equilibrate this rank's rows (spk_set_scaling): rscale / cscale are the scales of the rank's own rows and
+        columns (tensors on its device); the kp column scales of either neighbour that the halo tiles need travel
+        over the process group once."""
+        import torch
+        if self._bufs is None:
+            self._alloc(cscale)
+        kp = self.kp
+        from_right = torch.ones(kp, dtype=cscale.dtype, device=cscale.device)
+        from_left = torch.ones(kp, dtype=cscale.dtype, device=cscale.device)
+        if self.world > 1:
+            self._shift(cscale[:kp].contiguous(), from_right, -1)   # my first kp go left; I get the right rank's first kp
+            self._shift(cscale[-kp:].contiguous(), from_left, +1)   # my last kp go right; I get the left rank's last kp
+        ext = torch.cat([from_left, cscale, from_right]).contiguous() if self.world > 1 else cscale.contiguous()
+        self._scales = (rscale.contiguous(), ext)                    # keep them alive until the copy has been enqueued
+        self.e.set_scaling(self._ptr(self._scales[0]), self._ptr(ext))
+
     def mult(self, xvec, yvec):
         """y = A x on this rank's rows with the kp-entry halos of both neighbours."""
         if self._bufs is None:
