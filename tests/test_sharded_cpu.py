@@ -26,6 +26,18 @@ class NumpyEngine:
     def buffer_address(self, t):
         return t
 
+    def set_scaling(self, r, c_ext):
+        """spk_set_scaling of a shard: c_ext = [left neighbour's last k | my columns | right neighbour's first k]."""
+        k = self.k
+        r, c_ext = r.numpy(), c_ext.numpy()
+        c = c_ext[k:-k] if self.world > 1 else c_ext
+        self.Aloc = r[:, None] * self.Aloc * c[None, :]
+        if self.B is not None:
+            self.B = r[-k:, None] * self.B * c_ext[-k:][None, :]
+        if self.C is not None:
+            self.C = r[:k, None] * self.C * c_ext[:k][None, :]
+        self.rs, self.cs = r.copy(), c.copy()
+
     def tip_size(self):
         return self.k
 
@@ -61,7 +73,7 @@ class NumpyEngine:
         k = self.k
         if ph == 0:
             self.x = x
-            self.g = np.linalg.solve(self.Aloc, b.numpy())
+            self.g = np.linalg.solve(self.Aloc, b.numpy() * getattr(self, "rs", 1.0))
             self.rbot = None
         elif ph == 1:
             if self.B is not None:
@@ -76,7 +88,7 @@ class NumpyEngine:
                 r[:k] += self.C @ self.remote["xb"]
             if self.rbot is not None:
                 r[-k:] += self.rbot
-            self.x.copy_(torch.from_numpy(self.g - np.linalg.solve(self.Aloc, r)))
+            self.x.copy_(torch.from_numpy((self.g - np.linalg.solve(self.Aloc, r)) * getattr(self, "cs", 1.0)))
 
 
 class MailboxEngine(NumpyEngine):
@@ -136,7 +148,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, k, out, mailbox=False):
+def _worker(rank, world, port, n, k, out, mailbox=False, scaled=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -151,6 +163,10 @@ def _worker(rank, world, port, n, k, out, mailbox=False):
             for d in range(-k, k + 1):
                 if 0 <= i + d < n:
                     A[i, i + d] = a[i, d + k]
+        if scaled:   # A = D1 T D2; the shards equilibrate with 1/D1, 1/D2 (halo scales exchanged by ShardedSpike)
+            rng = np.random.default_rng(5)
+            d1, d2 = 10.0 ** rng.uniform(-6, 6, n), 10.0 ** rng.uniform(-0.5, 0.5, n)
+            A = d1[:, None] * A * d2[None, :]
         u = O.gen_vec(n, 7)
         bfull = A @ u
         bounds = shard_rows(n, world)
@@ -159,6 +175,8 @@ def _worker(rank, world, port, n, k, out, mailbox=False):
         S = ShardedSpike(eng, rank, world)
         b = torch.from_numpy(bfull[lo:hi].copy())
         x = torch.zeros_like(b)
+        if scaled:
+            S.set_scaling(torch.from_numpy(1.0 / d1[lo:hi]), torch.from_numpy(1.0 / d2[lo:hi]))
         S.factor(b)
         S.solve(b, x)
         if mailbox:
@@ -175,12 +193,13 @@ def _worker(rank, world, port, n, k, out, mailbox=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,mailbox", [(2, False), (3, False), (2, True), (3, True)])
-def test_sharded_exchange_protocol_gloo(world, mailbox):
+@pytest.mark.parametrize("world,mailbox,scaled", [(2, False, False), (3, False, False), (2, True, False), (3, True, False),
+                                                  (3, False, True)])
+def test_sharded_exchange_protocol_gloo(world, mailbox, scaled):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 480, 5, q, mailbox)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 480, 5, q, mailbox, scaled)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
