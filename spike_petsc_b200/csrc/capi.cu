@@ -7,6 +7,9 @@
 #include <vector>
 #include "common.cuh"
 
+int spk_wide_alloc(spk_ctx* c);    // wide.cu
+void spk_wide_free(spk_ctx* c);
+int spk_wide_check(spk_ctx* c);
 int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, const double* b_dev, double* x_dev,
                    int* its, double* rnorm, int* converged);  // krylov.cu
 
@@ -31,6 +34,7 @@ static void free_band(spk_ctx* c) {
   F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->xtopRemote); F(c->xbBoundary); F(c->haloL); F(c->haloR);
   F(c->opA.ia); F(c->opA.ja); F(c->opA.a); F(c->rscale); F(c->cscale_base); c->cscale = nullptr; F(c->tips_mr); F(c->work_mr); c->nrhs_mr = 0;
   free(c->h_pstart); c->h_pstart = nullptr;
+  spk_wide_free(c);
   spk_peer_release(c);   // the mailbox layout depends on kp
   c->have_band = c->factored = 0;
 }
@@ -96,42 +100,76 @@ static int plan(spk_ctx* c, int64_t n, int k) {
   if (n <= 0 || k < 0) { SPK_SET_ERR(c, "bad size n=%lld k=%d", (long long)n, k); return SPK_ERR_ARG; }
   int kt = (k + 7) / 8;
   if (kt < 2) kt = 2;
-  if (kt > SPK_MAX_KT) {
-    SPK_SET_ERR(c, "half-bandwidth %d > %d: the register-resident window kernel does not cover wide bands yet", k, 8 * SPK_MAX_KT);
+  if (k > SPK_MAX_K) {
+    SPK_SET_ERR(c, "half-bandwidth %d > %d is not supported", k, SPK_MAX_K);
     return SPK_ERR_UNSUPPORTED;
   }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   free_band(c);
   BandLayout& L = c->L;
-  L.n = n; L.k = k; L.kt = kt; L.tpr = 2 * kt + 1; L.nt = (n + 7) / 8;
-  c->kp = 8 * kt;
-  // partitions: every partition needs >= 2*kt tile rows (distinct top and bottom tips)
-  const int64_t minlen = std::max<int64_t>(2 * kt, 4);
-  int64_t P = c->opts.partitions > 0 ? c->opts.partitions : 2 * (int64_t)c->sm_count;
-  // keep partitions long enough that the truncation window is a small fraction of them
-  const int64_t want_len = std::max<int64_t>(minlen, 8 * kt);
-  if (c->opts.partitions <= 0) P = std::min<int64_t>(P, std::max<int64_t>(1, L.nt / want_len));
-  P = std::min<int64_t>(P, std::max<int64_t>(1, L.nt / minlen));
-  if (P < 1) P = 1;
-  c->P = (int)P;
-  c->h_pstart = (int64_t*)malloc(sizeof(int64_t) * (P + 1));
-  for (int64_t p = 0; p <= P; ++p) c->h_pstart[p] = L.nt * p / P;
-  int64_t minp = L.nt;
-  for (int64_t p = 0; p < P; ++p) minp = std::min(minp, c->h_pstart[p + 1] - c->h_pstart[p]);
-  int tip = c->opts.tip_tiles;
-  if (tip == 0) tip = 12 * kt;            // auto: 12 bandwidths of decay
-  if (tip < 0 || tip > minp) tip = (int)minp;
-  if (tip < kt) tip = (int)std::min<int64_t>(minp, kt);
-  c->tipT = tip;
-  if (P > 1 && minp < minlen) { SPK_SET_ERR(c, "partition too short (%lld tile rows < %lld)", (long long)minp, (long long)minlen); return SPK_ERR_ARG; }
-  if (L.nt < kt) { SPK_SET_ERR(c, "matrix smaller than one band window (n=%lld, k=%d)", (long long)n, k); return SPK_ERR_UNSUPPORTED; }
+  const bool wide = kt > SPK_MAX_KT;
+  int64_t P;
+  if (!wide) {
+    L.n = n; L.k = k; L.kt = kt; L.kc = kt; L.tpr = 2 * kt + 1; L.nt = (n + 7) / 8;
+    c->kp = 8 * kt;
+    // partitions: every partition needs >= 2*kt tile rows (distinct top and bottom tips)
+    const int64_t minlen = std::max<int64_t>(2 * kt, 4);
+    P = c->opts.partitions > 0 ? c->opts.partitions : 2 * (int64_t)c->sm_count;
+    // keep partitions long enough that the truncation window is a small fraction of them
+    const int64_t want_len = std::max<int64_t>(minlen, 8 * kt);
+    if (c->opts.partitions <= 0) P = std::min<int64_t>(P, std::max<int64_t>(1, L.nt / want_len));
+    P = std::min<int64_t>(P, std::max<int64_t>(1, L.nt / minlen));
+    if (P < 1) P = 1;
+    c->P = (int)P;
+    c->h_pstart = (int64_t*)malloc(sizeof(int64_t) * (P + 1));
+    for (int64_t p = 0; p <= P; ++p) c->h_pstart[p] = L.nt * p / P;
+    int64_t minp = L.nt;
+    for (int64_t p = 0; p < P; ++p) minp = std::min(minp, c->h_pstart[p + 1] - c->h_pstart[p]);
+    int tip = c->opts.tip_tiles;
+    if (tip == 0) tip = 12 * kt;            // auto: 12 bandwidths of decay
+    if (tip < 0 || tip > minp) tip = (int)minp;
+    if (tip < kt) tip = (int)std::min<int64_t>(minp, kt);
+    c->tipT = tip;
+    if (P > 1 && minp < minlen) { SPK_SET_ERR(c, "partition too short (%lld tile rows < %lld)", (long long)minp, (long long)minlen); return SPK_ERR_ARG; }
+    if (L.nt < kt) { SPK_SET_ERR(c, "matrix smaller than one band window (n=%lld, k=%d)", (long long)n, k); return SPK_ERR_UNSUPPORTED; }
+  } else {
+    // wide band (wide.cuh): super-blocks of 8x8 tiles, KB of them per side (even), tile storage 8*KB+7 per side,
+    // rows padded to whole super-blocks, partitions of whole super-block rows
+    int kb = (k + 63) / 64;
+    kb += kb & 1;
+    c->wide = 1; c->kb = kb;
+    L.n = n; L.k = k; L.kt = 8 * kb + 7; L.kc = 8 * kb; L.tpr = 2 * L.kt + 1; L.nt = ((n + 63) / 64) * 8;
+    c->kp = 64 * kb;
+    const int64_t nsb = L.nt / 8;
+    const int64_t minlen = 2 * kb;                                   // super-block rows
+    const int64_t groups = std::max<int64_t>(1, c->sm_count / (kb + 1));
+    P = c->opts.partitions > 0 ? c->opts.partitions : 4 * groups;
+    if (c->opts.partitions <= 0) P = std::min<int64_t>(P, std::max<int64_t>(1, nsb / (12 * kb)));
+    P = std::min<int64_t>(P, std::max<int64_t>(1, nsb / minlen));
+    if (P < 1) P = 1;
+    c->P = (int)P;
+    c->h_pstart = (int64_t*)malloc(sizeof(int64_t) * (P + 1));
+    for (int64_t p = 0; p <= P; ++p) c->h_pstart[p] = 8 * (nsb * p / P);
+    int64_t minp = L.nt;
+    for (int64_t p = 0; p < P; ++p) minp = std::min(minp, c->h_pstart[p + 1] - c->h_pstart[p]);
+    int64_t tip = c->opts.tip_tiles;
+    if (tip == 0) tip = 6 * L.kc;           // auto: 6 bandwidths of decay
+    tip = (tip + 7) / 8 * 8;
+    if (tip <= 0 || tip > minp) tip = minp;
+    if (tip < L.kc) tip = std::min<int64_t>(minp, L.kc);
+    c->tipT = (int)tip;
+    if (P > 1 && minp < 8 * minlen) { SPK_SET_ERR(c, "partition too short (%lld tile rows < %lld)", (long long)minp, (long long)(8 * minlen)); return SPK_ERR_ARG; }
+    if (nsb < kb) { SPK_SET_ERR(c, "matrix smaller than one band window (n=%lld, k=%d)", (long long)n, k); return SPK_ERR_UNSUPPORTED; }
+  }
 
   const size_t kk = (size_t)c->kp * c->kp;
   SPK_CUDA(c, cudaMalloc(&c->band, sizeof(double) * (size_t)L.elems()));
   SPK_CUDA(c, cudaMalloc(&c->d_pstart, sizeof(int64_t) * (P + 1)));
   SPK_CUDA(c, cudaMemcpyAsync(c->d_pstart, c->h_pstart, sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, c->stream));
-  SPK_CUDA(c, cudaMalloc(&c->Sb, sizeof(double) * kk * P));
-  SPK_CUDA(c, cudaMalloc(&c->St, sizeof(double) * kk * P));
+  if (!wide) {
+    SPK_CUDA(c, cudaMalloc(&c->Sb, sizeof(double) * kk * P));
+    SPK_CUDA(c, cudaMalloc(&c->St, sizeof(double) * kk * P));
+  }
   SPK_CUDA(c, cudaMalloc(&c->Vb, sizeof(double) * kk * P));
   SPK_CUDA(c, cudaMalloc(&c->Wt, sizeof(double) * kk * P));
   SPK_CUDA(c, cudaMalloc(&c->Red, sizeof(double) * kk * P));
@@ -147,6 +185,7 @@ static int plan(spk_ctx* c, int64_t n, int k) {
   SPK_CUDA(c, cudaMemsetAsync(c->haloL, 0, sizeof(double) * c->kp, c->stream));
   SPK_CUDA(c, cudaMemsetAsync(c->haloR, 0, sizeof(double) * c->kp, c->stream));
   c->work_elems = L.nt * 8;
+  if (wide) return spk_wide_alloc(c);
   return SPK_OK;
 }
 
@@ -671,6 +710,7 @@ extern "C" int spk_view(spk_ctx* c, spk_info* info) {
   if (!c->have_band) return SPK_OK;
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+  { const int wrc = spk_wide_check(c); if (wrc) return wrc; }
   SPK_CUDA(c, cudaMemcpy(&c->boosted, c->d_boost, sizeof(int64_t), cudaMemcpyDeviceToHost));
   info->n = c->L.n; info->n_padded = c->L.nt * 8; info->k = c->L.k; info->k_padded = c->kp; info->kt = c->L.kt;
   info->partitions = c->P; info->tip_tiles = c->tipT; info->boosted_pivots = c->boosted; info->factored = c->factored;

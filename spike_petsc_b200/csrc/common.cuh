@@ -15,7 +15,8 @@
 
 #define SPK_TILE 8
 #define SPK_TILE_ELEMS 64
-#define SPK_MAX_KT 16
+#define SPK_MAX_KT 16      // widest band (in tiles) of the register-resident kernels (lu.cu, solve.cu, msweep.cu, tips.cu)
+#define SPK_MAX_K 512      // widest band overall: above 8*SPK_MAX_KT the super-block kernels of wide*.cu take over
 
 struct BandLayout {
   int64_t n;    // rows of the matrix
@@ -23,6 +24,7 @@ struct BandLayout {
   int k;        // half bandwidth
   int kt;       // ceil(k/8)
   int tpr;      // tiles per tile row = 2*kt+1
+  int kc;       // tiles of a coupling block / spike tip (kp/8): = kt for narrow bands, 8*KB for wide ones (kt = 8*KB+7 there)
   __host__ __device__ int64_t tile_off(int64_t I, int64_t J) const { return (I * tpr + (J - I + kt)) * SPK_TILE_ELEMS; }
   __host__ __device__ int64_t elems() const { return nt * (int64_t)tpr * SPK_TILE_ELEMS; }
   // element (i,j), |i-j| <= 8*kt+7 assumed in band storage range
@@ -77,6 +79,17 @@ struct spk_ctx {
   int peer_ipc[2];
   unsigned long long peer_seq_out[3], peer_seq_in[3];
   double *tips_mr, *work_mr; int nrhs_mr;   // multi-right-hand-side scratch (grow-only): coupling right-hand sides, sweep results
+  // wide-band path (wide.cuh): half-bandwidth > 128, super-blocks of 8x8 tiles
+  int wide;                  // 1: the band uses the wide factor format and kernels
+  int kb;                    // band width in super-blocks per side (even, 4..8)
+  int wide_G;                // column CTAs per partition group of the wide LU (0 = kb)
+  unsigned long long* wide_flags; int wide_flag_parts;   // dataflow flags of the wide LU (WIDE_FLAGS_PER_PART words per partition)
+  unsigned int* wide_abort;  // set by a wide kernel whose bounded wait expired
+  double* wband;             // row/column-reversed copies of the top tip windows (P partitions of tipT tile rows), factored for W^(t)
+  double* rband;             // reduced matrices I - W V in band format (P partitions of 8*kb tile rows), factored for R
+  double* VbT;               // V^(b) transposed (right operand of the reduced-matrix product)
+  int64_t *d_wpstart, *d_rpstart;   // partition boundaries (tile rows) inside wband / rband
+  void* d_wjobs; int wjobs_cap;     // device array of sweep jobs
   double *rscale, *cscale;   // optional equilibration (spk_set_scaling): the factored band is diag(r) A diag(c)
   double *cscale_base;       // allocation behind cscale: [kp left-halo scales | n local | kp right-halo scales]
   // operator for Krylov
@@ -179,3 +192,10 @@ int spk_launch_reduced_solve_multi(spk_ctx* c, double* x, int nrhs, int64_t ld, 
 int spk_launch_mcorrections(spk_ctx* c, double* x, int nrhs, int64_t ld, const double* tips, double* work, int64_t ld_work);
 int spk_launch_gather(spk_ctx* c, const int* idx_dev, int inverse, const double* in, double* out, int64_t n);
 int spk_launch_csr_mult(spk_ctx* c, const CsrDev& A, const double* x, double* y);
+// wide-band path (wide.cu): the spk_launch_* entry points above forward to these when c->wide
+int spk_wide_ul_windows(spk_ctx* c);
+int spk_wide_band_lu(spk_ctx* c);
+int spk_wide_tips(spk_ctx* c, int what);
+int spk_wide_main_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld);
+int spk_wide_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld, const double* rtop, const double* rbot, size_t tip_stride,
+                         double* work, int64_t ldw);

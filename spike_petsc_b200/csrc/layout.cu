@@ -84,7 +84,7 @@ int spk_launch_pack_rows_chunk(spk_ctx* c, const double* src_dev, int64_t row0, 
 }
 int spk_launch_pack_finish(spk_ctx* c) {   // identity on the padded rows of the last tile row
   const BandLayout& L = c->L;
-  if (L.nt * SPK_TILE > L.n) { k_pad_identity<<<1, 8, 0, c->stream>>>(c->band, L); SPK_KERNEL_CHECK(c); }
+  if (L.nt * SPK_TILE > L.n) { k_pad_identity<<<1, 64, 0, c->stream>>>(c->band, L); SPK_KERNEL_CHECK(c); }
   return SPK_OK;
 }
 int spk_launch_pack_dense(spk_ctx* c, const double* src_dev, int layout) {
@@ -93,7 +93,7 @@ int spk_launch_pack_dense(spk_ctx* c, const double* src_dev, int layout) {
   const int64_t ng = c->opts.n_global > 0 ? c->opts.n_global : L.n;
   k_pack_dense<<<c->sm_count * 8, 256, 0, c->stream>>>(src_dev, c->band, L, layout, -c->opts.row_offset, ng - c->opts.row_offset);
   SPK_KERNEL_CHECK(c);
-  if (L.nt * SPK_TILE > L.n) { k_pad_identity<<<1, 8, 0, c->stream>>>(c->band, L); SPK_KERNEL_CHECK(c); }
+  if (L.nt * SPK_TILE > L.n) { k_pad_identity<<<1, 64, 0, c->stream>>>(c->band, L); SPK_KERNEL_CHECK(c); }
   return SPK_OK;
 }
 
@@ -183,7 +183,7 @@ int spk_launch_pack_csr(spk_ctx* c, const CsrDev& A, const int* rowperm_dev, con
   SPK_CUDA(c, cudaMemsetAsync(c->band, 0, sizeof(double) * (size_t)L.elems(), c->stream));
   k_pack_csr<<<c->sm_count * 8, 256, 0, c->stream>>>(A.n, A.ia, A.ja, A.a, rowperm_dev, icolperm_dev, c->band, L);
   SPK_KERNEL_CHECK(c);
-  if (L.nt * SPK_TILE > L.n) { k_pad_identity<<<1, 8, 0, c->stream>>>(c->band, L); SPK_KERNEL_CHECK(c); }
+  if (L.nt * SPK_TILE > L.n) { k_pad_identity<<<1, 64, 0, c->stream>>>(c->band, L); SPK_KERNEL_CHECK(c); }
   return SPK_OK;
 }
 
@@ -241,10 +241,10 @@ __global__ void __launch_bounds__(256) k_band_matmult(const double* __restrict__
       const int64_t col = J * SPK_TILE + 2 * tq;
       double2 xv;
       if (J < 0) {          // rows owned by the left-neighbour rank: haloL holds its last 8*kt entries
-        if (!haloL) continue;
-        xv = *reinterpret_cast<const double2*>(haloL + (col + (int64_t)L.kt * SPK_TILE));
+        if (!haloL || col + (int64_t)L.kc * SPK_TILE < 0) continue;   // (beyond the coupling block: structurally zero)
+        xv = *reinterpret_cast<const double2*>(haloL + (col + (int64_t)L.kc * SPK_TILE));
       } else if (J >= L.nt) {  // right neighbour: haloR holds its first 8*kt entries
-        if (!haloR) continue;
+        if (!haloR || col - L.nt * SPK_TILE >= (int64_t)L.kc * SPK_TILE) continue;
         xv = *reinterpret_cast<const double2*>(haloR + (col - L.nt * SPK_TILE));
       } else {
         xv = (col + 1 < L.n) ? *reinterpret_cast<const double2*>(x + col)

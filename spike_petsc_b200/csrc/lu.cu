@@ -394,10 +394,11 @@ static int launch_lu(spk_ctx* c, int grid, int first_part) {
   }
 }
 
-int spk_launch_lu(spk_ctx* c) { return launch_lu<false>(c, c->P, 0); }
+int spk_launch_lu(spk_ctx* c) { return c->wide ? spk_wide_band_lu(c) : launch_lu<false>(c, c->P, 0); }
 
 // bottom-up windows for W^(t): partitions 1..P-1 (and partition 0 when a left-neighbour rank exists)
 int spk_launch_ul_tips(spk_ctx* c) {
+  if (c->wide) return spk_wide_ul_windows(c);
   const int first = (c->opts.rank > 0) ? 0 : 1;
   const int grid = c->P - first;
   if (grid <= 0) return SPK_OK;

@@ -220,6 +220,7 @@ static int launch_msweep_cols(spk_ctx* c, MSweepArgs a, int nrhs) {
 
 // g = D^-1 b for nrhs columns (column r at b + r*ld / x + r*ld), 8*MS_GROUPS columns per pass over the band
 int spk_launch_msweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld) {
+  if (c->wide) return spk_wide_main_sweep(c, b, x, nrhs, ld);
   MSweepArgs a{};
   a.band = c->band; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.in = b; a.x = x; a.ld = ld; a.n = c->L.n;
   a.mode = MSWEEP_MAIN; a.P = c->P; a.tipT = c->tipT;
@@ -229,6 +230,7 @@ int spk_launch_msweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t 
 // window corrections of all columns: tips = coupling right-hand sides written by spk_launch_reduced_solve_multi,
 // work = nrhs columns of padded length ld_work (forward results of the window sweeps)
 int spk_launch_mcorrections(spk_ctx* c, double* x, int nrhs, int64_t ld, const double* tips, double* work, int64_t ld_work) {
+  if (c->wide) return spk_wide_corrections(c, x, nrhs, ld, tips, tips + (size_t)c->P * c->kp, 2 * (size_t)c->P * c->kp, work, ld_work);
   MSweepArgs a{};
   a.band = c->band; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.in = nullptr; a.x = x; a.ld = ld; a.n = c->L.n;
   a.mode = MSWEEP_CORR; a.P = c->P; a.tipT = c->tipT;

@@ -263,6 +263,7 @@ static int launch_sweep_any(spk_ctx* c, const SweepArgs& a, int grid) {
 }
 
 int spk_launch_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld) {
+  if (c->wide) return spk_wide_main_sweep(c, b, x, nrhs, ld);
   for (int r = 0; r < nrhs; ++r) {
     SweepArgs a{};
     a.band = c->band; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.P = c->P;
@@ -274,6 +275,14 @@ int spk_launch_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t l
 }
 
 int spk_launch_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld) {
+  if (c->wide) {
+    for (int r = 0; r < nrhs; ++r) {
+      const double* rt = c->gtip + (size_t)r * 2 * c->P * c->kp;
+      const int rc = spk_wide_corrections(c, x + (size_t)r * ld, 1, ld, rt, rt + (size_t)c->P * c->kp, 0, c->work, c->L.nt * 8);
+      if (rc) return rc;
+    }
+    return SPK_OK;
+  }
   for (int r = 0; r < nrhs; ++r) {
     SweepArgs a{};
     a.band = c->band; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.P = c->P;
@@ -337,7 +346,7 @@ __device__ __forceinline__ void block_matvec(const double* __restrict__ M, const
 }
 __global__ void __launch_bounds__(1024) k_reduced_solve(const RedSolveArgs a) {
   extern __shared__ __align__(16) double sm[];
-  const int kp = a.L.kt * 8, KT = a.L.kt;
+  const int kp = a.L.kc * 8, KT = a.L.kc;
   double* gb = sm; double* gt = gb + kp; double* tv = gt + kp; double* xt = tv + kp; double* xb = xt + kp;
   const int i = blockIdx.x + a.first_iface;
   const bool bnd = (i == a.boundary_iface);
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(1024) k_reduced_solve(const RedSolveArgs a) {
 
 // r_top of partition 0 from the left neighbour's x_b:  r = C_0 x_b,  C_0(r,c) = A(r, c - kp)
 __global__ void __launch_bounds__(1024) k_rtop_left(const double* __restrict__ band, BandLayout L, const double* __restrict__ xb, double* rtop) {
-  const int kp = L.kt * 8;
+  const int kp = L.kc * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < kp; r += (int)(blockDim.x >> 5)) {
     double s1 = 0.0;

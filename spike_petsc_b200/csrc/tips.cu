@@ -498,6 +498,7 @@ static cudaError_t red_launch(spk_ctx* c, int grid, const RedArgs& r, size_t sme
 //   what = 4: every W^(t) of this rank (they need the tip windows only; what = 0 / 3 then skip them)
 int spk_launch_tips(spk_ctx* c, int what, int unused) {
   (void)unused;
+  if (c->wide) return spk_wide_tips(c, what);
   const int kp = c->kp, P = c->P;
   const size_t smem = tips_smem(c->L.kt);
   SPK_CUDA(c, cudaFuncSetAttribute(k_spike_tip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -273,7 +273,7 @@ def test_error_paths(spk, oracle):
         S.mult(np.ones(400))                         # band overwritten, keep_original not requested
     S2 = spk.Spike()
     with pytest.raises(spk.SpikeError):
-        S2.set_band_synthetic(100_000, 1000)         # wide band: not covered by the window kernel
+        S2.set_band_synthetic(100_000, 1000)         # wider than 512: not supported
     S.close(); S2.close()
 
 
