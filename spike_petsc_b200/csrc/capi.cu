@@ -185,6 +185,7 @@ static int plan(spk_ctx* c, int64_t n, int k) {
   SPK_CUDA(c, cudaMemsetAsync(c->haloL, 0, sizeof(double) * c->kp, c->stream));
   SPK_CUDA(c, cudaMemsetAsync(c->haloR, 0, sizeof(double) * c->kp, c->stream));
   c->work_elems = L.nt * 8;
+  c->bnd_cols = 1;
   if (wide) return spk_wide_alloc(c);
   return SPK_OK;
 }

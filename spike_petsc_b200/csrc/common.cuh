@@ -90,6 +90,8 @@ struct spk_ctx {
   double* VbT;               // V^(b) transposed (right operand of the reduced-matrix product)
   int64_t *d_wpstart, *d_rpstart;   // partition boundaries (tile rows) inside wband / rband
   void* d_wjobs; int wjobs_cap;     // device array of sweep jobs
+  double* redw; int redw_cols;      // scratch of the wide reduced solve: g_b, g_t, t, x_t, x_b (kp x columns per interface)
+  int bnd_cols;                     // right-hand-side columns the boundary exchange buffers (remoteGtop, remoteXbot, xbBoundary) hold
   double *rscale, *cscale;   // optional equilibration (spk_set_scaling): the factored band is diag(r) A diag(c)
   double *cscale_base;       // allocation behind cscale: [kp left-halo scales | n local | kp right-halo scales]
   // operator for Krylov
@@ -197,5 +199,6 @@ int spk_wide_ul_windows(spk_ctx* c);
 int spk_wide_band_lu(spk_ctx* c);
 int spk_wide_tips(spk_ctx* c, int what);
 int spk_wide_main_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld);
+int spk_wide_reduced_solve(spk_ctx* c, const double* x, int nrhs, int64_t ld, double* rtop, double* rbot, size_t tip_stride);
 int spk_wide_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld, const double* rtop, const double* rbot, size_t tip_stride,
                          double* work, int64_t ldw);

@@ -403,6 +403,7 @@ int spk_launch_rtop_left(spk_ctx* c) {
 }
 
 int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int iface_lo, int iface_hi) {
+  if (c->wide) return spk_wide_reduced_solve(c, x, nrhs, ld, c->gtip, c->gtip + (size_t)c->P * c->kp, 2 * (size_t)c->P * c->kp);
   const bool has_right = c->opts.rank + 1 < c->opts.nranks;
   if (has_right && iface_hi == c->P - 1) iface_hi = c->P;   // include the boundary interface
   const int n = iface_hi - iface_lo;
@@ -430,6 +431,7 @@ int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int if
 // All right-hand sides in one launch (grid.y = column): tips[r] = rtop | rbot of column r, 2*P*kp doubles each.
 // Single-rank contexts (no boundary interface).
 int spk_launch_reduced_solve_multi(spk_ctx* c, double* x, int nrhs, int64_t ld, double* tips) {
+  if (c->wide) return spk_wide_reduced_solve(c, x, nrhs, ld, tips, tips + (size_t)c->P * c->kp, 2 * (size_t)c->P * c->kp);
   const int n = c->P - 1;
   if (n <= 0) return SPK_OK;
   RedSolveArgs a;

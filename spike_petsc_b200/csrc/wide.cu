@@ -47,6 +47,7 @@ void spk_wide_free(spk_ctx* c) {
   auto F = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
   F(c->wide_flags); F(c->wide_abort); F(c->wband); F(c->rband); F(c->VbT); F(c->d_wpstart); F(c->d_rpstart);
   if (c->d_wjobs) { cudaFree(c->d_wjobs); c->d_wjobs = nullptr; }
+  F(c->redw); c->redw_cols = 0;
   c->wide = 0; c->kb = 0;
 }
 
@@ -351,5 +352,133 @@ int spk_wide_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld, const doub
   if (rc) return rc;
   k_wide_corr_apply<<<dim3(2 * c->P, nrhs), 256, 0, c->stream>>>(a);
   SPK_KERNEL_CHECK(c);
+  return SPK_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// reduced solve for wide bands, all right-hand sides at once.  Per interface i (partition i below, i+1 above):
+//     t = g_t - W g_b,   x_t = R t,   x_b = g_b - V x_t,   r_bot(i) = B_i x_t,   r_top(i+1) = C_{i+1} x_b
+// Each product is (kp x kp) times (kp x nrhs): k_wide_mv runs it on the FP64 tensor cores, one CTA per 64 rows of
+// one interface, the matrix tiles straight from L2 as left fragments (dense row-major W, R, V or the coupling
+// blocks where they lie in the band), the vectors as right fragments from a column-major scratch (ld = kp).
+// The narrow path's k_reduced_solve (solve.cu) does the same with mat-vecs; at kp = 512 and 32 columns that would
+// re-read the three 2 MB matrices per column.
+struct WideMvArgs {
+  int mode;                           // 0: dense row-major (ld = kp)   1: B_i in the band   2: C_{i+1} in the band
+  const double* M; size_t m_stride; int m_off;      // dense: matrix of interface i = M + (i + m_off) * m_stride
+  const double* M_remote; int remote_iface;         // dense: interface remote_iface uses M_remote instead
+  const double* band; BandLayout L; const int64_t* pstart;
+  const double* X; const double* base; double* out;  // per interface blocks of kp x ncap (column-major, ld = kp) ...
+  size_t v_stride;                                   // ... v_stride apart
+  double* out_ext; size_t oe_iface; long long oe_ld;  // or (out == nullptr) an external output: out_ext + i*oe_iface, column c at + c*oe_ld
+  int kp, nrhs, first; double alpha;                 // out = base + alpha * M X
+};
+__global__ void __launch_bounds__(256) k_wide_mv(const WideMvArgs a) {
+  const int i = blockIdx.y + a.first;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  const int kp = a.kp, nk = kp >> 3;
+  const int rt = blockIdx.x * 8 + warp;
+  const int c0 = blockIdx.z * 32;
+  const double* X = a.X + (size_t)i * a.v_stride;
+  double2 acc[4];
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct) acc[ct] = make_double2(0.0, 0.0);
+  int klo = 0, khi = nk;
+  const double* mrow = nullptr; long long mstep = 0;
+  if (a.mode == 0) {
+    const double* M = (i == a.remote_iface) ? a.M_remote : a.M + (size_t)(i + a.m_off) * a.m_stride;
+    mrow = M + (size_t)(8 * rt + g) * kp + 2 * tq; mstep = 8;
+  } else {
+    const int64_t tb = a.pstart[i + 1];
+    if (a.mode == 1) { khi = rt + 1; mrow = a.band + a.L.tile_off(tb - a.L.kc + rt, tb) + 2 * lane; }   // B_i: tiles k <= rt
+    else { klo = rt; mrow = a.band + a.L.tile_off(tb + rt, tb - a.L.kc) + 2 * lane; }                   // C_{i+1}: tiles k >= rt
+    mstep = SPK_TILE_ELEMS;
+  }
+  for (int k = klo; k < khi; ++k) {
+    const double2 av = *reinterpret_cast<const double2*>(mrow + (long long)k * mstep);
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) {
+      const int col = c0 + 8 * ct + g;
+      const double2 bv = (col < a.nrhs) ? *reinterpret_cast<const double2*>(X + (size_t)col * kp + 8 * k + 2 * tq) : make_double2(0.0, 0.0);
+      dmma_cc(acc[ct], av, bv);
+    }
+  }
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct) {
+    const int col = c0 + 8 * ct + 2 * tq, row = 8 * rt + g;
+    double vx = a.alpha * acc[ct].x, vy = a.alpha * acc[ct].y;
+    if (a.base) {
+      const double* b = a.base + (size_t)i * a.v_stride;
+      if (col < a.nrhs) vx += b[(size_t)col * kp + row];
+      if (col + 1 < a.nrhs) vy += b[(size_t)(col + 1) * kp + row];
+    }
+    if (a.out) {
+      double* o = a.out + (size_t)i * a.v_stride;
+      if (col < a.nrhs) o[(size_t)col * kp + row] = vx;
+      if (col + 1 < a.nrhs) o[(size_t)(col + 1) * kp + row] = vy;
+    } else {
+      double* o = a.out_ext + (size_t)i * a.oe_iface;
+      if (col < a.nrhs) o[(long long)col * a.oe_ld + row] = vx;
+      if (col + 1 < a.nrhs) o[(long long)(col + 1) * a.oe_ld + row] = vy;
+    }
+  }
+}
+// g_b(i) = last kp entries of partition i, g_t(i) = first kp entries of partition i+1 (or the right rank's, remote)
+__global__ void k_wide_red_gather(const double* __restrict__ x, int64_t ldx, int64_t n, const int64_t* __restrict__ pstart, int kp,
+                                  int first, int remote_iface, const double* __restrict__ remote_gt, double* gb, double* gt, size_t v_stride) {
+  const int i = blockIdx.x + first, col = blockIdx.y;
+  const int64_t tb = pstart[i + 1] * 8;
+  for (int e = threadIdx.x; e < kp; e += blockDim.x) {
+    gb[(size_t)i * v_stride + (size_t)col * kp + e] = x[(size_t)col * ldx + tb - kp + e];
+    double v;
+    if (i == remote_iface) v = remote_gt[(size_t)col * kp + e];
+    else v = (tb + e < n) ? x[(size_t)col * ldx + tb + e] : 0.0;
+    gt[(size_t)i * v_stride + (size_t)col * kp + e] = v;
+  }
+}
+
+int spk_wide_reduced_solve(spk_ctx* c, const double* x, int nrhs, int64_t ld, double* rtop, double* rbot, size_t tip_stride) {
+  const bool has_right = c->opts.rank + 1 < c->opts.nranks;
+  const int nif = (c->P - 1) + (has_right ? 1 : 0);
+  if (nif <= 0) return SPK_OK;
+  const int kp = c->kp, P = c->P;
+  const int bnd = has_right ? P - 1 : -1;
+  if (c->redw_cols < nrhs) {
+    if (c->redw) { cudaFree(c->redw); c->redw = nullptr; }
+    c->redw_cols = 0;
+    SPK_CUDA(c, cudaMalloc(&c->redw, sizeof(double) * 5 * (size_t)P * kp * nrhs));
+    c->redw_cols = nrhs;
+  }
+  const size_t vs = (size_t)kp * c->redw_cols, blk = (size_t)P * vs;
+  double *gb = c->redw, *gt = gb + blk, *tv = gt + blk, *xt = tv + blk, *xb = xt + blk;
+  k_wide_red_gather<<<dim3(nif, nrhs), 256, 0, c->stream>>>(x, ld, c->L.n, c->d_pstart, kp, 0, bnd, c->remoteGtop, gb, gt, vs);
+  SPK_KERNEL_CHECK(c);
+  WideMvArgs a{};
+  a.band = c->band; a.L = c->L; a.pstart = c->d_pstart; a.kp = kp; a.nrhs = nrhs; a.first = 0; a.v_stride = vs;
+  a.m_stride = (size_t)kp * kp; a.remote_iface = -1;
+  const dim3 grid(kp / 64, nif, (nrhs + 31) / 32);
+  // t = g_t - W g_b
+  a.mode = 0; a.M = c->Wt; a.m_off = 1; a.M_remote = c->remoteWt; a.remote_iface = bnd; a.X = gb; a.base = gt; a.out = tv; a.alpha = -1.0;
+  k_wide_mv<<<grid, 256, 0, c->stream>>>(a); SPK_KERNEL_CHECK(c);
+  // x_t = R t
+  a.M = c->Red; a.m_off = 0; a.remote_iface = -1; a.X = tv; a.base = nullptr; a.out = xt; a.alpha = 1.0;
+  k_wide_mv<<<grid, 256, 0, c->stream>>>(a); SPK_KERNEL_CHECK(c);
+  // x_b = g_b - V x_t
+  a.M = c->Vb; a.X = xt; a.base = gb; a.out = xb; a.alpha = -1.0;
+  k_wide_mv<<<grid, 256, 0, c->stream>>>(a); SPK_KERNEL_CHECK(c);
+  // r_bot(i) = B_i x_t
+  a.mode = 1; a.X = xt; a.base = nullptr; a.out = nullptr; a.alpha = 1.0;
+  a.out_ext = rbot; a.oe_iface = (size_t)kp; a.oe_ld = (long long)tip_stride;
+  k_wide_mv<<<grid, 256, 0, c->stream>>>(a); SPK_KERNEL_CHECK(c);
+  // r_top(i+1) = C_{i+1} x_b for the local interfaces; the boundary one hands x_b to the right rank instead
+  if (P - 1 > 0) {
+    a.mode = 2; a.X = xb; a.out_ext = rtop + kp;
+    k_wide_mv<<<dim3(kp / 64, P - 1, (nrhs + 31) / 32), 256, 0, c->stream>>>(a); SPK_KERNEL_CHECK(c);
+  }
+  if (has_right) {
+    if (nrhs > c->bnd_cols) { SPK_SET_ERR(c, "sharded wide solve: %d right-hand sides exceed the boundary buffers (%d)", nrhs, c->bnd_cols); return SPK_ERR_STATE; }
+    SPK_CUDA(c, cudaMemcpy2DAsync(c->xbBoundary, sizeof(double) * kp, xb + (size_t)bnd * vs, sizeof(double) * kp, sizeof(double) * kp, nrhs,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+  }
   return SPK_OK;
 }
