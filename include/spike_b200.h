@@ -90,7 +90,9 @@ int spk_get_band_rows(spk_ctx *ctx, double *band_rows_host);
 
 /* ---- the hot path ------------------------------------------------------------------------------ */
 /* PCSetUp(b->pc) at src/matbanded.c:178 (and MatLUFactor of a MATBANDED): per-partition banded LU
- * (no pivoting, diagonal boosting), spike tips V^(b)/W^(t), reduced-system factorisation. In place. */
+ * (no pivoting, diagonal boosting), spike tips V^(b)/W^(t), reduced-system factorisation. In place.
+ * Half-bandwidths up to 128 run the register-resident window kernel (csrc/lu.cu); 129..512 the super-block kernel
+ * whose trailing updates are 64^3 FP64 tensor-core products (csrc/wide_lu.cu); wider bands are refused. */
 int spk_factor(spk_ctx *ctx);
 /* PCApply(b->pc,x,y) at src/matbanded.c:190 (and MatSolve / MatMatSolve): x = B^{-1} b for nrhs vectors of
  * leading dimension n.  b and x may alias.  nrhs >= 2 takes the block path: sweeps and window corrections run for
@@ -150,10 +152,14 @@ enum {
  *      [WT_FIRST -> left's REMOTE_WT], phase 11 (band LU), finish the exchange, phase 1 (local tips and,
  *      REMOTE_WT being set, the boundary block in the same launch), phase 2 (no-op then)
  *   solve : phase 0 (sweeps), [G_TOP -> left's REMOTE_G_TOP], phase 1 (reduced systems),
- *           [X_BOT -> right's REMOTE_X_BOT], phase 2 (corrections).  Device vectors, nrhs = 1.
+ *           [X_BOT -> right's REMOTE_X_BOT], phase 2 (corrections).  Device vectors.
+ *           nrhs > 1 (column r at b + r*n): the vector items become kp x nrhs blocks (column r at + r*kp); reserve
+ *           the exchange buffers once with spk_reserve_rhs(ctx, max nrhs) after the band is set and before
+ *           spk_peer_mailbox_create.  Phases 1 and 2 use the nrhs of phase 0.
  * With nranks == 1 spk_factor / spk_solve run all phases back to back. */
 int spk_factor_phase(spk_ctx *ctx, int phase);
 int spk_solve_phase(spk_ctx *ctx, int phase, const double *b, double *x, int nrhs);
+int spk_reserve_rhs(spk_ctx *ctx, int nrhs);
 
 /* ---- the same exchanges through NVLink peer memory instead of host-driven NCCL send/recv (csrc/peer.cu).
  * Every rank owns a mailbox in device memory; neighbours map it with CUDA IPC (the 64-byte handle travels
@@ -168,7 +174,9 @@ int spk_solve_phase(spk_ctx *ctx, int phase, const double *b, double *x, int nrh
  *                             dev_ptr <- its device address (either may be NULL)
  *   spk_peer_mailbox_attach : side 0 = left neighbour, 1 = right; pass the neighbour's handle, or its device
  *                             address when it lives in the same process
- *   spk_peer_check          : synchronise the stream; SPK_ERR_STATE if a bounded spin (~2 s) expired */
+ *   spk_peer_check          : synchronise the stream; SPK_ERR_STATE if a bounded spin expired
+ * A spin that expires (SPIKE_B200_PEER_TIMEOUT_S seconds, default 20) poisons its destination with NaN, acknowledges
+ * nothing, and makes every later factor / solve / post / wait call on the context fail until the band is set anew. */
 int spk_peer_mailbox_create(spk_ctx *ctx, void *handle64, void **dev_ptr);
 int spk_peer_mailbox_attach(spk_ctx *ctx, int side, const void *handle64, void *direct_ptr);
 int spk_peer_post(spk_ctx *ctx, int which);   /* which: SPK_BND_WT_FIRST, SPK_BND_G_TOP, SPK_BND_X_BOT */

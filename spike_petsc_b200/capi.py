@@ -81,6 +81,7 @@ def lib():
         L.spk_set_boundary.argtypes = [vp, C.c_int, vp]
         L.spk_factor_phase.argtypes = [vp, C.c_int]
         L.spk_solve_phase.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+        L.spk_reserve_rhs.argtypes = [vp, C.c_int]
         L.spk_peer_mailbox_create.argtypes = [vp, vp, C.POINTER(vp)]
         L.spk_peer_mailbox_attach.argtypes = [vp, C.c_int, vp, vp]
         L.spk_peer_post.argtypes = [vp, C.c_int]
@@ -243,8 +244,12 @@ class Spike:
     def factor_phase(self, phase: int):
         self._ck(lib().spk_factor_phase(self._h, phase), f"spk_factor_phase({phase})")
 
-    def solve_phase(self, phase: int, b=None, x=None):
-        self._ck(lib().spk_solve_phase(self._h, phase, _addr(b), _addr(x), 1), f"spk_solve_phase({phase})")
+    def solve_phase(self, phase: int, b=None, x=None, nrhs: int = 1):
+        self._ck(lib().spk_solve_phase(self._h, phase, _addr(b), _addr(x), nrhs), f"spk_solve_phase({phase})")
+
+    def reserve_rhs(self, nrhs: int):
+        """Size the boundary exchange buffers for nrhs columns per sharded solve (before peer_create)."""
+        self._ck(lib().spk_reserve_rhs(self._h, nrhs), "spk_reserve_rhs")
 
     def get_boundary(self, which: int, buf):
         self._ck(lib().spk_get_boundary(self._h, which, _addr(buf)), f"spk_get_boundary({which})")

@@ -31,7 +31,7 @@ static void free_band(spk_ctx* c) {
   auto F = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
   F(c->band); F(c->orig); F(c->dinv); F(c->d_pstart); F(c->Sb); F(c->St); F(c->Vb); F(c->Wt); F(c->Red);
   F(c->RedPiv); F(c->work); F(c->gtip); F(c->xtip); F(c->xb); F(c->xt); F(c->corr);
-  F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->xtopRemote); F(c->xbBoundary); F(c->haloL); F(c->haloR);
+  F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->gtopOut); F(c->xtopRemote); F(c->xbBoundary); F(c->haloL); F(c->haloR);
   F(c->opA.ia); F(c->opA.ja); F(c->opA.a); F(c->rscale); F(c->cscale_base); c->cscale = nullptr; F(c->tips_mr); F(c->work_mr); c->nrhs_mr = 0;
   free(c->h_pstart); c->h_pstart = nullptr;
   spk_wide_free(c);
@@ -246,6 +246,22 @@ extern "C" int spk_keep_original(spk_ctx* c, int keep) {
   return SPK_OK;
 }
 
+// Boundary exchange buffers for `nrhs` right-hand-side columns per sharded solve (default 1).  After the band is set,
+// before the peer mailbox is created (its layout follows the buffer sizes).
+extern "C" int spk_reserve_rhs(spk_ctx* c, int nrhs) {
+  if (!c || nrhs < 1) return SPK_ERR_ARG;
+  if (!c->have_band) { SPK_SET_ERR(c, "spk_reserve_rhs: set the band first"); return SPK_ERR_STATE; }
+  if (c->mbox) { SPK_SET_ERR(c, "spk_reserve_rhs: call before spk_peer_mailbox_create"); return SPK_ERR_STATE; }
+  if (nrhs == c->bnd_cols) return SPK_OK;
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+  const size_t bytes = sizeof(double) * (size_t)c->kp * nrhs;
+  auto R = [&](double*& p) -> cudaError_t { if (p) cudaFree(p); p = nullptr; cudaError_t e = cudaMalloc(&p, bytes); if (e == cudaSuccess) e = cudaMemset(p, 0, bytes); return e; };
+  SPK_CUDA(c, R(c->remoteGtop)); SPK_CUDA(c, R(c->remoteXbot)); SPK_CUDA(c, R(c->xbBoundary)); SPK_CUDA(c, R(c->gtopOut));
+  c->bnd_cols = nrhs;
+  return SPK_OK;
+}
+
 // rows per upload chunk of spk_set_band_dense(host, ROWS); 0 = 256 MB worth.  Debug hook for the tests (not public).
 static int64_t g_pack_chunk_rows = 0;
 extern "C" int spk_debug_set_pack_chunk_rows(int64_t rows) { g_pack_chunk_rows = rows > 0 ? ((rows + 7) & ~7ll) : 0; return SPK_OK; }
@@ -440,6 +456,7 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
   if (!c->have_band) { SPK_SET_ERR(c, "spk_factor: no band set"); return SPK_ERR_STATE; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   int rc = SPK_OK;
+  if ((phase == 0 || phase == 10) && spk_peer_failed(c)) return SPK_ERR_STATE;
   if (phase == 0) {
     if (c->factored && spk_lu_source(c) == c->band) { SPK_SET_ERR(c, "band already factored (the factorisation is in place unless spk_keep_original(ctx,1) kept the unfactored band)"); return SPK_ERR_STATE; }
     c->factored = 0;
@@ -478,6 +495,7 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
     if (!has_right || with_boundary) {
       SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
       c->factored = 1; c->timed_factor = 1;
+      return spk_peer_note(c);
     }
     return SPK_OK;
   }
@@ -489,7 +507,7 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
     }
     SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     c->factored = 1; c->timed_factor = 1;
-    return SPK_OK;
+    return spk_peer_note(c);
   }
   SPK_SET_ERR(c, "bad factor phase %d", phase);
   return SPK_ERR_ARG;
@@ -532,6 +550,7 @@ int spk_solve_dev(spk_ctx* c, const double* b, double* x) {
 // Several right-hand sides (device pointers, column r at b + r*n): the partition sweeps run for all columns at
 // once on the tensor cores (msweep.cu: the band is read once per 32 columns), the O(P kp^2) reduced solves and the
 // window corrections are per column.
+static int ensure_multi_scratch(spk_ctx* c, int nrhs);
 static int solve_multi_dev(spk_ctx* c, const double* b, double* x, int nrhs) {
   const int64_t n = c->L.n;
   int rc = SPK_OK;
@@ -547,14 +566,8 @@ static int solve_multi_dev(spk_ctx* c, const double* b, double* x, int nrhs) {
   if (c->P > 1) {
     // scratch for all columns: coupling right-hand sides (2*P*kp each) and the forward results of the window sweeps
     const int64_t npad = c->L.nt * 8;
-    if (c->nrhs_mr < nrhs) {
-      if (c->tips_mr) { cudaFree(c->tips_mr); c->tips_mr = nullptr; }
-      if (c->work_mr) { cudaFree(c->work_mr); c->work_mr = nullptr; }
-      c->nrhs_mr = 0;
-      SPK_CUDA(c, cudaMalloc(&c->tips_mr, sizeof(double) * 2 * (size_t)c->P * c->kp * nrhs));
-      SPK_CUDA(c, cudaMalloc(&c->work_mr, sizeof(double) * (size_t)npad * nrhs));
-      c->nrhs_mr = nrhs;
-    }
+    rc = ensure_multi_scratch(c, nrhs);
+    if (rc) return rc;
     SPK_CUDA(c, cudaMemsetAsync(c->tips_mr, 0, sizeof(double) * 2 * (size_t)c->P * c->kp * nrhs, c->stream));
     STAGE_BEGIN(c, 4); rc = spk_launch_reduced_solve_multi(c, x, nrhs, n, c->tips_mr); STAGE_END(c, 4);
     if (rc) return rc;
@@ -569,37 +582,73 @@ static int solve_multi_dev(spk_ctx* c, const double* b, double* x, int nrhs) {
 //   phase 0: g = D^-1 b                      -> exchange SPK_BND_G_TOP (to the left rank)
 //   phase 1: reduced systems (incl. boundary) -> exchange SPK_BND_X_BOT (to the right rank)
 //   phase 2: coupling right-hand side of partition 0 + corrections
+static int ensure_multi_scratch(spk_ctx* c, int nrhs) {
+  const int64_t npad = c->L.nt * 8;
+  if (c->nrhs_mr < nrhs) {
+    if (c->tips_mr) { cudaFree(c->tips_mr); c->tips_mr = nullptr; }
+    if (c->work_mr) { cudaFree(c->work_mr); c->work_mr = nullptr; }
+    c->nrhs_mr = 0;
+    SPK_CUDA(c, cudaMalloc(&c->tips_mr, sizeof(double) * 2 * (size_t)c->P * c->kp * nrhs));
+    SPK_CUDA(c, cudaMalloc(&c->work_mr, sizeof(double) * (size_t)npad * nrhs));
+    c->nrhs_mr = nrhs;
+  }
+  return SPK_OK;
+}
+
 extern "C" int spk_solve_phase(spk_ctx* c, int phase, const double* b, double* x, int nrhs) {
-  if (!c || nrhs != 1) return SPK_ERR_ARG;
+  if (!c || nrhs < 1) return SPK_ERR_ARG;
   if (!c->factored) { SPK_SET_ERR(c, "spk_solve_phase before the factorisation is complete"); return SPK_ERR_STATE; }
   if (c->opts.mem != SPK_MEM_DEVICE) { SPK_SET_ERR(c, "split-phase solve needs device vectors (opts.mem = SPK_MEM_DEVICE)"); return SPK_ERR_ARG; }
+  if (nrhs > c->bnd_cols) { SPK_SET_ERR(c, "spk_solve_phase: %d right-hand sides, boundary buffers hold %d (spk_reserve_rhs)", nrhs, c->bnd_cols); return SPK_ERR_ARG; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   int rc = SPK_OK;
+  const int64_t n = c->L.n;
   if (phase == 0) {
     if (!b || !x) return SPK_ERR_ARG;
-    c->cur_x = x;
+    if (spk_peer_failed(c)) return SPK_ERR_STATE;
+    c->cur_x = x; c->cur_nrhs = nrhs;
     SPK_CUDA(c, cudaEventRecord(c->evs0, c->stream));
     if (c->rscale) {   // equilibrated band: the sweeps run in place on diag(r) b
-      rc = spk_launch_vec_scale(c, x, b, c->rscale, c->L.n);
+      for (int r = 0; r < nrhs && rc == SPK_OK; ++r) rc = spk_launch_vec_scale(c, x + (size_t)r * n, b + (size_t)r * n, c->rscale, n);
       if (rc) return rc;
       b = x;
     }
-    STAGE_BEGIN(c, 3); rc = spk_launch_sweep(c, b, x, 1, c->L.n); STAGE_END(c, 3);
+    STAGE_BEGIN(c, 3);
+    rc = nrhs >= 2 ? spk_launch_msweep(c, b, x, nrhs, n) : spk_launch_sweep(c, b, x, 1, n);
+    STAGE_END(c, 3);
+    if (rc == SPK_OK && c->bnd_cols > 1 && c->opts.rank > 0)   // g^(t) of every column, packed for the left neighbour
+      SPK_CUDA(c, cudaMemcpy2DAsync(c->gtopOut, sizeof(double) * c->kp, x, sizeof(double) * (size_t)n, sizeof(double) * c->kp, nrhs,
+                                    cudaMemcpyDeviceToDevice, c->stream));
     return rc;
   }
   if (!c->cur_x) { SPK_SET_ERR(c, "solve phase %d without phase 0", phase); return SPK_ERR_STATE; }
+  nrhs = c->cur_nrhs;
   if (phase == 1) {
-    STAGE_BEGIN(c, 4); rc = spk_launch_reduced_solve(c, c->cur_x, 1, c->L.n, 0, c->P - 1); STAGE_END(c, 4);
+    STAGE_BEGIN(c, 4);
+    if (nrhs >= 2) {
+      rc = ensure_multi_scratch(c, nrhs);
+      if (rc == SPK_OK) SPK_CUDA(c, cudaMemsetAsync(c->tips_mr, 0, sizeof(double) * 2 * (size_t)c->P * c->kp * nrhs, c->stream));
+      if (rc == SPK_OK) rc = spk_launch_reduced_solve_multi(c, c->cur_x, nrhs, n, c->tips_mr);
+    } else {
+      rc = spk_launch_reduced_solve(c, c->cur_x, 1, n, 0, c->P - 1);
+    }
+    STAGE_END(c, 4);
     return rc;
   }
   if (phase == 2) {
     STAGE_BEGIN(c, 5);
-    if (c->opts.rank > 0) rc = spk_launch_rtop_left(c);
-    if (rc == SPK_OK) rc = spk_launch_corrections(c, c->cur_x, 1, c->L.n);
+    if (nrhs >= 2) {
+      if (c->opts.rank > 0) rc = spk_launch_rtop_left(c, c->tips_mr, 2 * (size_t)c->P * c->kp, nrhs);
+      if (rc == SPK_OK) rc = spk_launch_mcorrections(c, c->cur_x, nrhs, n, c->tips_mr, c->work_mr, c->L.nt * 8);
+    } else {
+      if (c->opts.rank > 0) rc = spk_launch_rtop_left(c, c->gtip, 0, 1);
+      if (rc == SPK_OK) rc = spk_launch_corrections(c, c->cur_x, 1, n);
+    }
     STAGE_END(c, 5);
-    if (rc == SPK_OK && c->cscale) rc = spk_launch_vec_scale(c, c->cur_x, c->cur_x, c->cscale, c->L.n);
+    for (int r = 0; r < nrhs && rc == SPK_OK && c->cscale; ++r) rc = spk_launch_vec_scale(c, c->cur_x + (size_t)r * n, c->cur_x + (size_t)r * n, c->cscale, n);
     SPK_CUDA(c, cudaEventRecord(c->evs1, c->stream));
     c->timed_solve = 1;
+    if (rc == SPK_OK) rc = spk_peer_note(c);
     return rc;
   }
   SPK_SET_ERR(c, "bad solve phase %d", phase);
@@ -726,16 +775,16 @@ extern "C" int spk_view(spk_ctx* c, spk_info* info) {
 // ---- multi-GPU boundary hooks: buffers follow opts.mem (device pointers in sharded runs) --------
 extern "C" int spk_tip_size(spk_ctx* c, int* kp) { if (!c || !kp) return SPK_ERR_ARG; *kp = c->kp; return SPK_OK; }
 int spk_bnd_desc(spk_ctx* c, int which, double** ptr, size_t* count, int* is_out) {
-  const size_t kk = (size_t)c->kp * c->kp, k1 = (size_t)c->kp;
+  const size_t kk = (size_t)c->kp * c->kp, k1 = (size_t)c->kp * c->bnd_cols, kh = (size_t)c->kp;
   switch (which) {
     case SPK_BND_WT_FIRST:     *ptr = c->Wt;          *count = kk; *is_out = 1; return 0;  // W^(t) of my partition 0
     case SPK_BND_REMOTE_WT:    *ptr = c->remoteWt;    *count = kk; *is_out = 0; return 0;
-    case SPK_BND_G_TOP:        *ptr = c->cur_x;       *count = k1; *is_out = 1; return c->cur_x ? 0 : 1;
+    case SPK_BND_G_TOP:        *ptr = c->bnd_cols > 1 ? c->gtopOut : c->cur_x; *count = k1; *is_out = 1; return c->cur_x ? 0 : 1;
     case SPK_BND_REMOTE_G_TOP: *ptr = c->remoteGtop;  *count = k1; *is_out = 0; return 0;
     case SPK_BND_X_BOT:        *ptr = c->xbBoundary;  *count = k1; *is_out = 1; return 0;
     case SPK_BND_REMOTE_X_BOT: *ptr = c->remoteXbot;  *count = k1; *is_out = 0; return 0;
-    case SPK_BND_HALO_LEFT:    *ptr = c->haloL;       *count = k1; *is_out = 0; return 0;
-    case SPK_BND_HALO_RIGHT:   *ptr = c->haloR;       *count = k1; *is_out = 0; return 0;
+    case SPK_BND_HALO_LEFT:    *ptr = c->haloL;       *count = kh; *is_out = 0; return 0;
+    case SPK_BND_HALO_RIGHT:   *ptr = c->haloR;       *count = kh; *is_out = 0; return 0;
     default: return 1;
   }
 }

@@ -68,7 +68,9 @@ struct spk_ctx {
   double *corr;        // P * 2 * tipT*8
   int64_t work_elems;
   // remote (multi-GPU) boundary buffers
-  double *remoteWt, *remoteGtop, *remoteXbot, *xtopRemote, *xbBoundary;
+  double *remoteWt, *remoteGtop, *remoteXbot, *xtopRemote, *xbBoundary;   // (the vector items hold kp x bnd_cols doubles)
+  double *gtopOut;     // g^(t) of every column packed for the left neighbour (bnd_cols > 1)
+  int cur_nrhs;        // columns of the split-phase solve in progress
   double *haloL, *haloR; // MatMult halos (8*kt entries of the neighbours' x)
   double *cur_x;       // output vector of the solve in progress (split-phase)
   int have_remote_wt;  // the right neighbour's W^(t) has been set for the factorisation in progress
@@ -78,6 +80,7 @@ struct spk_ctx {
   double *mbox, *peer_mbox[2];
   int peer_ipc[2];
   unsigned long long peer_seq_out[3], peer_seq_in[3];
+  unsigned long long* h_peer_err;   // pinned host mirror of the mailbox error word (peer.cu)
   double *tips_mr, *work_mr; int nrhs_mr;   // multi-right-hand-side scratch (grow-only): coupling right-hand sides, sweep results
   // wide-band path (wide.cuh): half-bandwidth > 128, super-blocks of 8x8 tiles
   int wide;                  // 1: the band uses the wide factor format and kernels
@@ -113,6 +116,8 @@ struct spk_ctx {
 };
 
 void spk_peer_release(spk_ctx* c);   // peer.cu
+int spk_peer_failed(spk_ctx* c);     // an earlier exchange expired (pinned mirror, no sync)
+int spk_peer_note(spk_ctx* c);       // enqueue the mirror copy of the error word
 // band the LU and the tip windows read: the kept original if there is one that still equals the unfactored band
 static inline double* spk_lu_source(spk_ctx* c) { return (c->orig && !c->rscale) ? c->orig : c->band; }
 int spk_bnd_desc(spk_ctx* c, int which, double** ptr, size_t* count, int* is_out);   // capi.cu
@@ -185,7 +190,7 @@ int spk_launch_matmult(spk_ctx* c, const double* band, const double* x, double* 
 int spk_launch_lu(spk_ctx* c);            // per-partition LU (+ S_b capture, dinv)
 int spk_launch_ul_tips(spk_ctx* c);       // UL window -> S_t
 int spk_launch_tips(spk_ctx* c, int what, int unused);  // 0: local tips + reduced blocks, 1: boundary reduced block
-int spk_launch_rtop_left(spk_ctx* c);
+int spk_launch_rtop_left(spk_ctx* c, double* rtop, size_t tip_stride, int nrhs);   // column r: rtop + r*tip_stride <- C_0 (remoteXbot + r*kp)
 int spk_launch_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld);   // g = D^-1 b
 int spk_launch_msweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_t ld);   // g = D^-1 b, nrhs columns at once (msweep.cu)
 int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int iface_lo, int iface_hi);

@@ -36,6 +36,7 @@ struct MSweepArgs {
   size_t tip_stride;
   double* work;         // forward results of the window sweeps, column r at work + r*ld_work
   int64_t ld_work;
+  int has_left, has_right;   // neighbour ranks present: partition 0's top / partition P-1's bottom correction is active
 };
 
 template <int KT>
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__((MS_GROUPS + 1) * 32) k_msweep(const MSweepArg
   if (corr) {   // same jobs as k_sweep's correction mode (single rank: no remote neighbours)
     const int side = blockIdx.x & 1;
     const int64_t plen = t1 - t0;
-    const bool top_on = p > 0, bot_on = p < a.P - 1;
+    const bool top_on = (p > 0) || a.has_left, bot_on = (p < a.P - 1) || a.has_right;   // neighbour ranks: sharded contexts
     const bool full = 2 * (int64_t)a.tipT > plen;
     const int64_t W = full ? plen : a.tipT;
     if (full) {
@@ -235,5 +236,6 @@ int spk_launch_mcorrections(spk_ctx* c, double* x, int nrhs, int64_t ld, const d
   a.band = c->band; a.tpr = c->L.tpr; a.pstart = c->d_pstart; a.in = nullptr; a.x = x; a.ld = ld; a.n = c->L.n;
   a.mode = MSWEEP_CORR; a.P = c->P; a.tipT = c->tipT;
   a.tips = tips; a.tip_stride = 2 * (size_t)c->P * c->kp; a.work = work; a.ld_work = ld_work;
+  a.has_left = c->opts.rank > 0; a.has_right = c->opts.rank + 1 < c->opts.nranks;
   return launch_msweep_cols(c, a, nrhs);
 }

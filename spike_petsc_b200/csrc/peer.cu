@@ -12,13 +12,15 @@
 // exchange still overlaps the band LU (posted before it, awaited after it).
 //
 // Mailbox layout (identical on all ranks; doubles, then 64-bit words):
-//   channel 0 (W^(t),  right -> left): data[2][kp*kp]     channel 1 (g^(t), right -> left): data[2][kp]
-//   channel 2 (x^(b),  left -> right): data[2][kp]        words: per channel flag[2], ack
+//   channel 0 (W^(t),  right -> left): data[2][kp*kp]     channel 1 (g^(t), right -> left): data[2][kp*cols]
+//   channel 2 (x^(b),  left -> right): data[2][kp*cols]   words: per channel flag[2], ack      (cols: spk_reserve_rhs, default 1)
 // data/flag slots alternate with the sequence number; a producer may be at most two items ahead of its
 // consumer (it spins on the ack word, which lives in ITS mailbox), so a rank that calls spk_factor repeatedly
 // cannot overrun a slow neighbour.  Every spin is bounded (~2 s of SM clocks): a protocol error surfaces as
 // SPK_ERR_STATE from spk_peer_check instead of a hung GPU.
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 
 struct PeerLayout {
   size_t data_off[3];   // in doubles
@@ -26,10 +28,11 @@ struct PeerLayout {
   size_t words_off;     // in doubles (= 8-byte words)
   size_t total;         // in doubles
 };
-static PeerLayout peer_layout(int kp) {
+static PeerLayout peer_layout(const spk_ctx* c) {
   PeerLayout L;
+  const int kp = c->kp;
   const size_t kk = (size_t)kp * kp;
-  L.count[0] = kk; L.count[1] = (size_t)kp; L.count[2] = (size_t)kp;
+  L.count[0] = kk; L.count[1] = (size_t)kp * c->bnd_cols; L.count[2] = (size_t)kp * c->bnd_cols;
   size_t off = 0;
   for (int ch = 0; ch < 3; ++ch) { L.data_off[ch] = off; off += 2 * L.count[ch]; }
   L.words_off = off;
@@ -45,20 +48,32 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-#define PEER_SPIN_CYCLES (4LL << 30)
+// Spin bound in SM clock ticks: SPIKE_B200_PEER_TIMEOUT_S seconds (default 20) at 2 GHz.  An expired spin is LOUD on
+// the data path: the consumer fills its destination with NaN and does not acknowledge, the producer neither stores
+// nor releases (its consumer then expires in turn); the sticky error word is mirrored into pinned host memory after
+// every factor / solve (spk_peer_note) and fails the next call.
+static long long peer_spin_cycles() {
+  const char* e = getenv("SPIKE_B200_PEER_TIMEOUT_S");
+  double sec = e ? atof(e) : 20.0;
+  if (!(sec > 0.0)) sec = 20.0;
+  return (long long)(sec * 2.0e9);
+}
 
 // producer: wait until the slot is free (ack >= seq-2), store the item into the consumer's mailbox, release the flag
 __global__ void __launch_bounds__(256) k_peer_post(const double* __restrict__ src, int n, double* dst, unsigned long long* flag,
-                                                   const unsigned long long* ack, unsigned long long seq, unsigned long long* err) {
+                                                   const unsigned long long* ack, unsigned long long seq, unsigned long long* err, long long limit) {
+  __shared__ int ok;
   if (threadIdx.x == 0) {
+    ok = 1;
     const long long t0 = clock64();
     while (ld_acquire_sys(ack) + 2 < seq) {
-      if (clock64() - t0 > PEER_SPIN_CYCLES) { atomicExch(err, 1ull); break; }
+      if (clock64() - t0 > limit) { atomicExch(err, 1ull); ok = 0; break; }
       __nanosleep(200);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  if (!ok) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) st_release_sys(flag, seq);
@@ -66,15 +81,21 @@ __global__ void __launch_bounds__(256) k_peer_post(const double* __restrict__ sr
 
 // consumer: acquire the flag, copy the item out of my mailbox, acknowledge into the producer's mailbox
 __global__ void __launch_bounds__(256) k_peer_wait(double* __restrict__ dst, int n, const double* src, const unsigned long long* flag,
-                                                   unsigned long long* ack, unsigned long long seq, unsigned long long* err) {
+                                                   unsigned long long* ack, unsigned long long seq, unsigned long long* err, long long limit) {
+  __shared__ int ok;
   if (threadIdx.x == 0) {
+    ok = 1;
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < seq) {
-      if (clock64() - t0 > PEER_SPIN_CYCLES) { atomicExch(err, 2ull); break; }
+      if (clock64() - t0 > limit) { atomicExch(err, 2ull); ok = 0; break; }
       __nanosleep(200);
     }
   }
   __syncthreads();
+  if (!ok) {   // poison: whatever consumes this item must not look plausible
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __longlong_as_double(0x7ff8000000000000ll);
+    return;
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcv(src + i);
   __syncthreads();
   if (threadIdx.x == 0) st_release_sys(ack, seq);
@@ -83,12 +104,14 @@ __global__ void __launch_bounds__(256) k_peer_wait(double* __restrict__ dst, int
 extern "C" int spk_peer_mailbox_create(spk_ctx* c, void* handle64, void** dev_ptr) {
   if (!c || !c->have_band) return SPK_ERR_ARG;
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
-  const PeerLayout L = peer_layout(c->kp);
+  const PeerLayout L = peer_layout(c);
   if (!c->mbox) {
     SPK_CUDA(c, cudaMalloc(&c->mbox, sizeof(double) * L.total));
     SPK_CUDA(c, cudaMemsetAsync(c->mbox, 0, sizeof(double) * L.total, c->stream));
     SPK_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int ch = 0; ch < 3; ++ch) c->peer_seq_out[ch] = c->peer_seq_in[ch] = 0;
+    if (!c->h_peer_err) SPK_CUDA(c, cudaHostAlloc((void**)&c->h_peer_err, sizeof(unsigned long long), cudaHostAllocDefault));
+    *c->h_peer_err = 0ull;   // a new mailbox starts clean
   }
   if (handle64) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
@@ -121,6 +144,21 @@ void spk_peer_release(spk_ctx* c) {
     c->peer_mbox[s] = nullptr; c->peer_ipc[s] = 0;
   }
   if (c->mbox) { cudaFree(c->mbox); c->mbox = nullptr; }
+  if (c->h_peer_err) { cudaFreeHost(c->h_peer_err); c->h_peer_err = nullptr; }
+}
+
+// the error word as last mirrored into pinned host memory (no synchronisation): non-zero = an earlier exchange expired
+int spk_peer_failed(spk_ctx* c) {
+  if (!c->h_peer_err || !*(volatile unsigned long long*)c->h_peer_err) return 0;
+  SPK_SET_ERR(c, "an earlier peer mailbox exchange timed out (code %llu): results since then are poisoned", *c->h_peer_err);
+  return 1;
+}
+// enqueue the mirror copy (end of every factor / solve on a context with a mailbox)
+int spk_peer_note(spk_ctx* c) {
+  if (!c->mbox || !c->h_peer_err) return SPK_OK;
+  const PeerLayout L = peer_layout(c);
+  SPK_CUDA(c, cudaMemcpyAsync(c->h_peer_err, reinterpret_cast<unsigned long long*>(c->mbox + L.words_off) + 9, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  return SPK_OK;
 }
 
 static int peer_channel(int which, int* ch, int* side, int* is_post) {
@@ -140,17 +178,18 @@ extern "C" int spk_peer_post(spk_ctx* c, int which) {
   int ch, side, post;
   if (!c || peer_channel(which, &ch, &side, &post) || !post) return SPK_ERR_ARG;
   if (!c->mbox || !c->peer_mbox[side]) { SPK_SET_ERR(c, "spk_peer_post: no mailbox attached on side %d", side); return SPK_ERR_STATE; }
+  if (spk_peer_failed(c)) return SPK_ERR_STATE;
   double* p; size_t n; int out;
   if (spk_bnd_desc(c, which, &p, &n, &out) || !out) { SPK_SET_ERR(c, "spk_peer_post: item %d unavailable", which); return SPK_ERR_ARG; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
-  const PeerLayout L = peer_layout(c->kp);
+  const PeerLayout L = peer_layout(c);
   const unsigned long long seq = ++c->peer_seq_out[ch];
   const int slot = (int)(seq & 1ull);
   double* peer = c->peer_mbox[side];
   unsigned long long* peer_words = reinterpret_cast<unsigned long long*>(peer + L.words_off);
   unsigned long long* my_words = reinterpret_cast<unsigned long long*>(c->mbox + L.words_off);
   k_peer_post<<<1, 256, 0, c->stream>>>(p, (int)n, peer + L.data_off[ch] + (size_t)slot * L.count[ch], peer_words + 3 * ch + slot,
-                                        my_words + 3 * ch + 2, seq, my_words + 9);
+                                        my_words + 3 * ch + 2, seq, my_words + 9, peer_spin_cycles());
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }
@@ -160,16 +199,17 @@ extern "C" int spk_peer_wait(spk_ctx* c, int which) {
   int ch, side, post;
   if (!c || peer_channel(which, &ch, &side, &post) || post) return SPK_ERR_ARG;
   if (!c->mbox || !c->peer_mbox[side]) { SPK_SET_ERR(c, "spk_peer_wait: no mailbox attached on side %d", side); return SPK_ERR_STATE; }
+  if (spk_peer_failed(c)) return SPK_ERR_STATE;
   double* p; size_t n; int out;
   if (spk_bnd_desc(c, which, &p, &n, &out) || out) { SPK_SET_ERR(c, "spk_peer_wait: bad item %d", which); return SPK_ERR_ARG; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
-  const PeerLayout L = peer_layout(c->kp);
+  const PeerLayout L = peer_layout(c);
   const unsigned long long seq = ++c->peer_seq_in[ch];
   const int slot = (int)(seq & 1ull);
   unsigned long long* peer_words = reinterpret_cast<unsigned long long*>(c->peer_mbox[side] + L.words_off);
   unsigned long long* my_words = reinterpret_cast<unsigned long long*>(c->mbox + L.words_off);
   k_peer_wait<<<1, 256, 0, c->stream>>>(p, (int)n, c->mbox + L.data_off[ch] + (size_t)slot * L.count[ch], my_words + 3 * ch + slot,
-                                        peer_words + 3 * ch + 2, seq, my_words + 9);
+                                        peer_words + 3 * ch + 2, seq, my_words + 9, peer_spin_cycles());
   SPK_KERNEL_CHECK(c);
   if (which == SPK_BND_REMOTE_WT) c->have_remote_wt = 1;
   return SPK_OK;
@@ -179,7 +219,7 @@ extern "C" int spk_peer_wait(spk_ctx* c, int which) {
 extern "C" int spk_peer_check(spk_ctx* c) {
   if (!c || !c->mbox) return SPK_ERR_ARG;
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
-  const PeerLayout L = peer_layout(c->kp);
+  const PeerLayout L = peer_layout(c);
   unsigned long long e = 0;
   SPK_CUDA(c, cudaMemcpyAsync(&e, reinterpret_cast<unsigned long long*>(c->mbox + L.words_off) + 9, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
   SPK_CUDA(c, cudaStreamSynchronize(c->stream));

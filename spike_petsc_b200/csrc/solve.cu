@@ -309,6 +309,7 @@ struct RedSolveArgs {
   const double* remoteWt; const double* remoteGtop; double* xbBoundary;
   int64_t n;
   int64_t x_stride; size_t tip_stride;   // several right-hand sides: blockIdx.y selects x + y*x_stride, rtop/rbot + y*tip_stride
+  size_t bnd_stride;                     // ... and remoteGtop / xbBoundary + y*bnd_stride
 };
 // out[r] = base[r] - sum_c M[r*kp+c] v[c] (or just the product when base == nullptr).  8 warps; each warp
 // takes 4 rows per pass and issues all their loads before the shuffle reductions (memory-level
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(1024) k_reduced_solve(const RedSolveArgs a) {
   double* const rbot_o = a.rbot + (size_t)blockIdx.y * a.tip_stride;
   for (int e = threadIdx.x; e < kp; e += blockDim.x) {
     gb[e] = xg[(tb - KT) * 8 + e];
-    gt[e] = bnd ? a.remoteGtop[e] : ((tb * 8 + e < a.n) ? xg[tb * 8 + e] : 0.0);
+    gt[e] = bnd ? a.remoteGtop[(size_t)blockIdx.y * a.bnd_stride + e] : ((tb * 8 + e < a.n) ? xg[tb * 8 + e] : 0.0);
   }
   __syncthreads();
   const double* W = bnd ? a.remoteWt : a.Wt + (size_t)(i + 1) * kp * kp;
@@ -378,16 +379,19 @@ __global__ void __launch_bounds__(1024) k_reduced_solve(const RedSolveArgs a) {
     }
     for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
     if (lane == 0) {
-      if (!bnd) rtop_o[(size_t)(i + 1) * kp + r] = s1; else a.xbBoundary[r] = xb[r];
+      if (!bnd) rtop_o[(size_t)(i + 1) * kp + r] = s1; else a.xbBoundary[(size_t)blockIdx.y * a.bnd_stride + r] = xb[r];
       rbot_o[(size_t)i * kp + r] = s2;
     }
   }
 }
 
-// r_top of partition 0 from the left neighbour's x_b:  r = C_0 x_b,  C_0(r,c) = A(r, c - kp)
-__global__ void __launch_bounds__(1024) k_rtop_left(const double* __restrict__ band, BandLayout L, const double* __restrict__ xb, double* rtop) {
+// r_top of partition 0 from the left neighbour's x_b:  r = C_0 x_b,  C_0(r,c) = A(r, c - kp); one CTA per column
+__global__ void __launch_bounds__(1024) k_rtop_left(const double* __restrict__ band, BandLayout L, const double* __restrict__ xb_all, double* rtop_all,
+                                                    size_t tip_stride) {
   const int kp = L.kc * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double* xb = xb_all + (size_t)blockIdx.x * kp;
+  double* rtop = rtop_all + (size_t)blockIdx.x * tip_stride;
   for (int r = warp; r < kp; r += (int)(blockDim.x >> 5)) {
     double s1 = 0.0;
     for (int c = lane; c < kp; c += 32)
@@ -396,8 +400,8 @@ __global__ void __launch_bounds__(1024) k_rtop_left(const double* __restrict__ b
     if (lane == 0) rtop[r] = s1;
   }
 }
-int spk_launch_rtop_left(spk_ctx* c) {
-  k_rtop_left<<<1, 1024, 0, c->stream>>>(c->band, c->L, c->remoteXbot, c->gtip);
+int spk_launch_rtop_left(spk_ctx* c, double* rtop, size_t tip_stride, int nrhs) {
+  k_rtop_left<<<nrhs, 1024, 0, c->stream>>>(c->band, c->L, c->remoteXbot, rtop, tip_stride);
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }
@@ -417,7 +421,7 @@ int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int if
     a.first_iface = iface_lo;
     a.boundary_iface = has_right ? c->P - 1 : -1;
     a.remoteWt = c->remoteWt; a.remoteGtop = c->remoteGtop; a.xbBoundary = c->xbBoundary; a.n = c->L.n;
-    a.x_stride = 0; a.tip_stride = 0;
+    a.x_stride = 0; a.tip_stride = 0; a.bnd_stride = 0;
     // as many warps per CTA as keep every interface resident at once (2048 threads per SM): 32 warps = one pass per
     // block mat-vec when there are at most two interfaces per SM
     const int per_sm = (n + c->sm_count - 1) / c->sm_count;
@@ -429,23 +433,25 @@ int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int if
 }
 
 // All right-hand sides in one launch (grid.y = column): tips[r] = rtop | rbot of column r, 2*P*kp doubles each.
-// Single-rank contexts (no boundary interface).
+// On a sharded context the boundary interface (remote W^(t), g^(t) in; x^(b) out, kp doubles per column) rides along.
 int spk_launch_reduced_solve_multi(spk_ctx* c, double* x, int nrhs, int64_t ld, double* tips) {
   if (c->wide) return spk_wide_reduced_solve(c, x, nrhs, ld, tips, tips + (size_t)c->P * c->kp, 2 * (size_t)c->P * c->kp);
-  const int n = c->P - 1;
+  const bool has_right = c->opts.rank + 1 < c->opts.nranks;
+  const int n = c->P - 1 + (has_right ? 1 : 0);
   if (n <= 0) return SPK_OK;
   RedSolveArgs a;
   a.band = c->band; a.L = c->L; a.pstart = c->d_pstart; a.Vb = c->Vb; a.Wt = c->Wt; a.Rinv = c->Red;
   a.x = x; a.rtop = tips; a.rbot = tips + (size_t)c->P * c->kp;
-  a.first_iface = 0; a.boundary_iface = -1;
+  a.first_iface = 0; a.boundary_iface = has_right ? c->P - 1 : -1;
   a.remoteWt = c->remoteWt; a.remoteGtop = c->remoteGtop; a.xbBoundary = c->xbBoundary; a.n = c->L.n;
-  a.x_stride = ld; a.tip_stride = 2 * (size_t)c->P * c->kp;
+  a.x_stride = ld; a.tip_stride = 2 * (size_t)c->P * c->kp; a.bnd_stride = (size_t)c->kp;
   for (int r0 = 0; r0 < nrhs; r0 += 65535) {
     const int nr = std::min(nrhs - r0, 65535);
     const int per_sm = (int)(((int64_t)n * nr + c->sm_count - 1) / c->sm_count);
     const int threads = std::max(256, std::min(1024, (2048 / std::max(per_sm, 1)) / 32 * 32));
     RedSolveArgs b = a;
     b.x = x + (size_t)r0 * ld; b.rtop = a.rtop + (size_t)r0 * a.tip_stride; b.rbot = a.rbot + (size_t)r0 * a.tip_stride;
+    b.remoteGtop = a.remoteGtop + (size_t)r0 * a.bnd_stride; b.xbBoundary = a.xbBoundary + (size_t)r0 * a.bnd_stride;
     k_reduced_solve<<<dim3(n, nr), threads, sizeof(double) * 5 * c->kp, c->stream>>>(b);
     SPK_KERNEL_CHECK(c);
   }

@@ -19,19 +19,25 @@ import sys
 from . import capi
 
 
-def shard_rows(n_global: int, world: int):
-    """Contiguous row blocks, every boundary a multiple of 8 rows (tile size)."""
-    tiles = (n_global + 7) // 8
-    bounds = [min(n_global, (tiles * r // world) * 8) for r in range(world + 1)]
+def shard_rows(n_global: int, world: int, k: int = 0):
+    """Contiguous row blocks, every boundary a multiple of 8 rows (tile size) -- of 64 rows (super-block size) for
+    the wide-band path, half-bandwidth k > 128."""
+    al = 64 if k > 128 else 8
+    tiles = (n_global + al - 1) // al
+    bounds = [min(n_global, (tiles * r // world) * al) for r in range(world + 1)]
     bounds[-1] = n_global
     return bounds
 
 
 class ShardedSpike:
-    def __init__(self, engine, rank: int, world: int, dist=None):
+    def __init__(self, engine, rank: int, world: int, dist=None, nrhs: int = 1):
         """engine: an object with the split-phase API of capi.Spike (factor_phase, solve_phase,
-        get_boundary, set_boundary, tip_size) created for this rank's row block."""
+        get_boundary, set_boundary, tip_size) created for this rank's row block.
+        nrhs: the most right-hand-side columns one solve() will carry (sizes the exchange buffers / mailboxes)."""
         self.e, self.rank, self.world, self.dist = engine, rank, world, dist
+        self.nrhs = nrhs
+        if nrhs > 1:
+            engine.reserve_rhs(nrhs)
         self._bufs = None
         self._peer = None        # None: not decided yet; True: NVLink mailboxes; False: NCCL send/recv
         self._peer_verified = False
@@ -117,7 +123,7 @@ class ShardedSpike:
         import torch
         kp = self.e.tip_size()
         mk = lambda m: torch.zeros(m, dtype=torch.float64, device=like.device)  # noqa: E731
-        self._bufs = {"wt_out": mk(kp * kp), "wt_in": mk(kp * kp), "v_out": mk(kp), "v_in": mk(kp)}
+        self._bufs = {"wt_out": mk(kp * kp), "wt_in": mk(kp * kp), "v_out": mk(kp * self.nrhs), "v_in": mk(kp * self.nrhs)}
         self.kp = kp
 
     def _ptr(self, t):
@@ -169,14 +175,18 @@ class ShardedSpike:
         if has_right:
             self.e.factor_phase(2)
 
-    def solve(self, bvec, xvec):
-        """bvec, xvec: this rank's rows of b and x (tensors on the rank's device; may alias)."""
+    def solve(self, bvec, xvec, nrhs: int = 1):
+        """bvec, xvec: this rank's rows of b and x (tensors on the rank's device; may alias); nrhs > 1: nrhs columns,
+        column r at offset r * (local rows)."""
+        if nrhs > self.nrhs:
+            raise ValueError(f"solve with {nrhs} columns on a ShardedSpike created for {self.nrhs}")
+        kw = {"nrhs": nrhs} if nrhs > 1 else {}
         if self._bufs is None:
             self._alloc(bvec)
         b = self._bufs
         has_left, has_right = self.rank > 0, self.rank + 1 < self.world
         if self.world > 1 and self._peer_setup():
-            self.e.solve_phase(0, self._ptr(bvec), self._ptr(xvec))
+            self.e.solve_phase(0, self._ptr(bvec), self._ptr(xvec), **kw)
             if has_left:
                 self.e.peer_post(capi.BND_G_TOP)
             if has_right:
@@ -191,7 +201,7 @@ class ShardedSpike:
                 self.e.peer_check()
                 self._peer_verified = True
             return xvec
-        self.e.solve_phase(0, self._ptr(bvec), self._ptr(xvec))
+        self.e.solve_phase(0, self._ptr(bvec), self._ptr(xvec), **kw)
         if self.world > 1:
             if has_left:
                 self.e.get_boundary(capi.BND_G_TOP, self._ptr(b["v_out"]))

@@ -141,9 +141,13 @@ def test_sharded_peer_mailbox_protocol(spk, oracle, n, k, R, parts, tip):
     assert _run(spk, oracle, n, k, R, parts, tip, mailbox=True) < 1e-10
 
 
-def test_peer_mailbox_spin_is_bounded(spk):
-    """A wait whose item never arrives gives up after ~2 s and spk_peer_check reports it (no hung GPU)."""
+def test_peer_mailbox_spin_is_bounded(spk, monkeypatch):
+    """A wait whose item never arrives gives up after SPIKE_B200_PEER_TIMEOUT_S seconds (no hung GPU) and the failure
+    is loud: the destination is filled with NaN, nothing is acknowledged, spk_peer_check reports it, and the next
+    factor / solve call on the context fails."""
+    import torch
     from spike_petsc_b200 import capi
+    monkeypatch.setenv("SPIKE_B200_PEER_TIMEOUT_S", "1")
     E = [spk.Spike(partitions=2, mem=spk.MEM_DEVICE, rank=r, nranks=2, row_offset=r * 8000, n_global=16000) for r in range(2)]
     for e in E:
         e.set_band_synthetic(8000, 10)
@@ -152,9 +156,18 @@ def test_peer_mailbox_spin_is_bounded(spk):
     E[1].peer_attach(0, ptr=ptrs[0])
     with pytest.raises(RuntimeError):
         E[0].peer_post(capi.BND_REMOTE_WT)          # not an "out" item
+    E[0].factor_phase(10)
+    E[0].factor_phase(11)
     E[0].peer_wait(capi.BND_REMOTE_WT)              # nobody posted
+    E[0].factor_phase(1)                            # enqueues the mirror copy of the error word
+    E[0].factor_phase(2)
     with pytest.raises(RuntimeError, match="timed out"):
         E[0].peer_check()
+    kp = E[0].tip_size()
+    buf = torch.zeros(kp * kp, dtype=torch.float64, device="cuda")
+    with pytest.raises(RuntimeError, match="timed out"):
+        E[0].factor_phase(10)                       # the context stays failed until the mailbox is recreated
+    del buf
     for e in E:
         e.close()
 

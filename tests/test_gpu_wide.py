@@ -116,3 +116,80 @@ def test_wide_refactor_with_kept_original(spk, oracle):
     assert relerr(x1, np.ones(n)) < 1e-10
     assert relerr(S.mult(np.ones(n)), b) < 1e-14
     S.close()
+
+
+# ------------------------------------------------------------------ sharded (multi-GPU protocol on one GPU)
+def _run_sharded(spk, oracle, n, k, R, parts, tip, nrhs, mailbox):
+    """R row-block shards as R contexts on one device; boundary items moved by tensor copies (the order ShardedSpike
+    uses with NCCL) or through the peer mailboxes; nrhs columns per solve."""
+    import torch
+    from spike_petsc_b200 import capi
+    bounds = spk.shard_rows(n, R, k)
+    E = []
+    for r in range(R):
+        e = spk.Spike(partitions=parts, tip_tiles=tip, mem=spk.MEM_DEVICE, rank=r, nranks=R, row_offset=bounds[r], n_global=n)
+        e.set_band_synthetic(bounds[r + 1] - bounds[r], k)
+        if nrhs > 1:
+            e.reserve_rhs(nrhs)
+        E.append(e)
+    kp = E[0].tip_size()
+    dev = "cuda"
+    a = oracle.gen_band(n, k)
+    lu, _ = oracle.band_lu(a)
+    U = np.stack([oracle.gen_vec(n, 50 + c) for c in range(nrhs)])
+    Bm = np.stack([oracle.band_mult(a, u) for u in U])
+    wt = [torch.zeros(kp * kp, dtype=torch.float64, device=dev) for _ in range(R)]
+    if mailbox:
+        ptrs = [e.peer_create()[1] for e in E]
+        for r in range(R):
+            if r > 0:
+                E[r].peer_attach(0, ptr=ptrs[r - 1])
+            if r + 1 < R:
+                E[r].peer_attach(1, ptr=ptrs[r + 1])
+    for e in E:
+        e.factor_phase(10)
+    for r in range(1, R):
+        E[r].peer_post(capi.BND_WT_FIRST) if mailbox else E[r].get_boundary(capi.BND_WT_FIRST, wt[r].data_ptr())
+    for e in E:
+        e.factor_phase(11)
+    for r in range(R):
+        if r + 1 < R:
+            E[r].peer_wait(capi.BND_REMOTE_WT) if mailbox else E[r].set_boundary(capi.BND_REMOTE_WT, wt[r + 1].data_ptr())
+        E[r].factor_phase(1)
+        if r + 1 < R:
+            E[r].factor_phase(2)
+    bs = [torch.from_numpy(np.ascontiguousarray(Bm[:, bounds[r]:bounds[r + 1]])).to(dev) for r in range(R)]
+    xo = [torch.zeros_like(b) for b in bs]
+    v = [torch.zeros(kp * nrhs, dtype=torch.float64, device=dev) for _ in range(R)]
+    for rep in range(2):
+        for r in range(R):
+            E[r].solve_phase(0, bs[r].data_ptr(), xo[r].data_ptr(), nrhs)
+        for r in range(1, R):
+            E[r].peer_post(capi.BND_G_TOP) if mailbox else E[r].get_boundary(capi.BND_G_TOP, v[r].data_ptr())
+        for r in range(R - 1):
+            E[r].peer_wait(capi.BND_REMOTE_G_TOP) if mailbox else E[r].set_boundary(capi.BND_REMOTE_G_TOP, v[r + 1].data_ptr())
+        for r in range(R):
+            E[r].solve_phase(1)
+        for r in range(R - 1):
+            E[r].peer_post(capi.BND_X_BOT) if mailbox else E[r].get_boundary(capi.BND_X_BOT, v[r].data_ptr())
+        for r in range(1, R):
+            E[r].peer_wait(capi.BND_REMOTE_X_BOT) if mailbox else E[r].set_boundary(capi.BND_REMOTE_X_BOT, v[r - 1].data_ptr())
+        for r in range(R):
+            E[r].solve_phase(2)
+        if mailbox:
+            for e in E:
+                e.peer_check()
+    torch.cuda.synchronize()
+    X = np.concatenate([t.cpu().numpy() for t in xo], axis=1)
+    for e in E:
+        e.close()
+    return max(relerr(X[c], oracle.band_solve(lu, Bm[c])) for c in range(nrhs))
+
+
+@pytest.mark.parametrize("n,k,R,parts,tip,nrhs,mailbox", [
+    (16_384, 256, 2, 2, -1, 1, False), (24_576, 512, 3, 1, -1, 1, True), (32_768, 512, 2, 2, -1, 32, True),
+    (20_000, 136, 4, 1, -1, 9, False), (30_000, 50, 3, 2, -1, 12, True), (40_000, 100, 4, 2, 0, 32, False)])
+def test_sharded_wide_and_multi_rhs(spk, oracle, n, k, R, parts, tip, nrhs, mailbox):
+    """BASELINE config 5's protocol in small: wide band, 32 right-hand sides, row blocks on several ranks; also the
+    narrow kernels with several columns per sharded solve."""
+    assert _run_sharded(spk, oracle, n, k, R, parts, tip, nrhs, mailbox) < RTOL
