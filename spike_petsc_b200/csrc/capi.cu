@@ -15,6 +15,24 @@ int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, 
 
 static char g_err[512] = "";
 
+// Grow-only device staging buffers owned by the context: host-vector calls (spk_solve / spk_mult / spk_permute /
+// spk_krylov through the PC/KSP glue, i.e. once per Krylov iteration) reuse them instead of cudaMalloc + cudaFree
+// + implicit synchronisation per call.
+static double* stage_buf(spk_ctx* c, int slot, size_t bytes) {
+  if (c->stage_bytes[slot] < bytes) {
+    if (c->stage[slot]) { cudaStreamSynchronize(c->stream); cudaFree(c->stage[slot]); c->stage[slot] = nullptr; c->stage_bytes[slot] = 0; }
+    if (cudaMalloc(&c->stage[slot], bytes) != cudaSuccess) { SPK_SET_ERR(c, "staging buffer of %zu bytes: %s", bytes, cudaGetErrorString(cudaGetLastError())); return nullptr; }
+    c->stage_bytes[slot] = bytes;
+  }
+  return (double*)c->stage[slot];
+}
+// device temporaries of the setup calls: freed on every exit path
+struct DevTmp {
+  void* p = nullptr;
+  ~DevTmp() { if (p) cudaFree(p); }
+  template <class T> cudaError_t alloc(T** out, size_t bytes) { cudaError_t e = cudaMalloc(&p, bytes); *out = (T*)p; return e; }
+};
+
 #define STAGE_BEGIN(c, i) cudaEventRecord((c)->evst[i][0], (c)->stream)
 #define STAGE_END(c, i) do { cudaEventRecord((c)->evst[i][1], (c)->stream); (c)->stage_timed[i] = 1; } while (0)
 
@@ -32,6 +50,7 @@ static void free_band(spk_ctx* c) {
   F(c->band); F(c->orig); F(c->dinv); F(c->d_pstart); F(c->Sb); F(c->St); F(c->Vb); F(c->Wt); F(c->Red);
   F(c->RedPiv); F(c->work); F(c->gtip); F(c->xtip); F(c->xb); F(c->xt); F(c->corr);
   F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->gtopOut); F(c->xtopRemote); F(c->xbBoundary); F(c->haloL); F(c->haloR);
+  for (int i = 0; i < 4; ++i) { if (c->stage[i]) { cudaFree(c->stage[i]); c->stage[i] = nullptr; } c->stage_bytes[i] = 0; }
   F(c->opA.ia); F(c->opA.ja); F(c->opA.a); F(c->rscale); F(c->cscale_base); c->cscale = nullptr; F(c->tips_mr); F(c->work_mr); c->nrhs_mr = 0;
   free(c->h_pstart); c->h_pstart = nullptr;
   spk_wide_free(c);
@@ -237,6 +256,10 @@ extern "C" int spk_set_scaling(spk_ctx* c, const double* rscale, const double* c
 
 extern "C" int spk_keep_original(spk_ctx* c, int keep) {
   if (!c) return SPK_ERR_ARG;
+  if (keep && c->have_band && c->rscale && !c->orig) {
+    SPK_SET_ERR(c, "spk_keep_original: the band is already equilibrated (spk_set_scaling); request the copy before scaling");
+    return SPK_ERR_STATE;
+  }
   c->keep_orig = keep ? 1 : 0;
   if (keep && c->have_band && !c->factored && !c->orig) {
     SPK_CUDA(c, cudaSetDevice(c->opts.device));
@@ -308,15 +331,16 @@ extern "C" int spk_set_band_dense(spk_ctx* c, int64_t n, int k, const double* ba
     return rc;
   }
   const double* src = band;
-  double* tmp = nullptr;
+  DevTmp tmp;
   if (mem == SPK_MEM_HOST) {
-    SPK_CUDA(c, cudaMalloc(&tmp, bytes));
-    SPK_CUDA(c, cudaMemcpyAsync(tmp, band, bytes, cudaMemcpyHostToDevice, c->stream));
-    src = tmp;
+    double* t;
+    SPK_CUDA(c, tmp.alloc(&t, bytes));
+    SPK_CUDA(c, cudaMemcpyAsync(t, band, bytes, cudaMemcpyHostToDevice, c->stream));
+    src = t;
   }
   rc = spk_launch_pack_dense(c, src, layout);
   if (rc == SPK_OK) rc = finish_band(c);
-  if (tmp) { cudaStreamSynchronize(c->stream); cudaFree(tmp); }
+  if (tmp.p) cudaStreamSynchronize(c->stream);
   return rc;
 }
 
@@ -390,20 +414,21 @@ extern "C" int spk_set_band_csr(spk_ctx* c, int n, const int* ia, const int* ja,
   int rc = plan(c, n, k);
   if (rc) return rc;
   CsrDev A;
+  struct CsrGuard { CsrDev& A; ~CsrGuard() { cudaFree(A.ia); cudaFree(A.ja); cudaFree(A.a); } } guard{A};
+  DevTmp t_rp, t_ic;
   rc = upload_csr(c, A, n, ia, ja, a);
   int *d_rp = nullptr, *d_ic = nullptr;
   if (rc == SPK_OK && rowperm) {
-    SPK_CUDA(c, cudaMalloc(&d_rp, sizeof(int) * (size_t)n));
+    SPK_CUDA(c, t_rp.alloc(&d_rp, sizeof(int) * (size_t)n));
     SPK_CUDA(c, cudaMemcpyAsync(d_rp, rowperm, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   }
   if (rc == SPK_OK && colperm) {
-    SPK_CUDA(c, cudaMalloc(&d_ic, sizeof(int) * (size_t)n));
+    SPK_CUDA(c, t_ic.alloc(&d_ic, sizeof(int) * (size_t)n));
     SPK_CUDA(c, cudaMemcpyAsync(d_ic, icol.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   }
   if (rc == SPK_OK) rc = spk_launch_pack_csr(c, A, d_rp, d_ic);
   if (rc == SPK_OK) rc = finish_band(c);
   cudaStreamSynchronize(c->stream);
-  cudaFree(A.ia); cudaFree(A.ja); cudaFree(A.a); cudaFree(d_rp); cudaFree(d_ic);
   if (rc == SPK_OK) { *kmax = k; *frac = f; c->frac = f; }
   return rc;
 }
@@ -436,15 +461,15 @@ extern "C" int spk_get_band_rows(spk_ctx* c, double* rows_host) {
   if (!c->have_band) { SPK_SET_ERR(c, "no band set"); return SPK_ERR_STATE; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   const size_t bytes = sizeof(double) * (size_t)c->L.n * (2 * (size_t)c->L.k + 1);
+  DevTmp guard;
   double* tmp;
-  SPK_CUDA(c, cudaMalloc(&tmp, bytes));
+  SPK_CUDA(c, guard.alloc(&tmp, bytes));
   int rc = spk_launch_unpack_rows(c, c->band, tmp);
   if (rc == SPK_OK) {
     cudaError_t e = cudaMemcpyAsync(rows_host, tmp, bytes, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { SPK_SET_ERR(c, "copy back failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
   }
-  cudaFree(tmp);
   return rc;
 }
 
@@ -664,11 +689,11 @@ extern "C" int spk_solve(spk_ctx* c, const double* b, double* x, int nrhs) {
   const double* bd = b; double* xd = x;
   double* tmp = nullptr;
   if (c->opts.mem == SPK_MEM_HOST) {
-    SPK_CUDA(c, cudaMalloc(&tmp, sizeof(double) * (size_t)n * nrhs));
+    tmp = stage_buf(c, 0, sizeof(double) * (size_t)n * nrhs);
+    if (!tmp) return SPK_ERR_NOMEM;
     SPK_CUDA(c, cudaMemcpyAsync(tmp, b, sizeof(double) * (size_t)n * nrhs, cudaMemcpyHostToDevice, c->stream));
     bd = tmp; xd = tmp;
   }
-  const int launches0 = c->launches;
   SPK_CUDA(c, cudaEventRecord(c->evs0, c->stream));
   int rc = SPK_OK;
   if (nrhs >= 2) rc = solve_multi_dev(c, bd, xd, nrhs);
@@ -680,27 +705,26 @@ extern "C" int spk_solve(spk_ctx* c, const double* b, double* x, int nrhs) {
     if (e == cudaSuccess && tmp) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { SPK_SET_ERR(c, "solve copy-back failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
   }
-  (void)launches0;
-  if (tmp) { cudaStreamSynchronize(c->stream); cudaFree(tmp); }
   return rc;
 }
 
 extern "C" int spk_mult(spk_ctx* c, const double* x, double* y) {
   if (!c || !x || !y) return SPK_ERR_ARG;
   if (!c->have_band) { SPK_SET_ERR(c, "spk_mult: no band set"); return SPK_ERR_STATE; }
-  const double* A = c->factored ? c->orig : c->band;
-  if (!A) { SPK_SET_ERR(c, "spk_mult after spk_factor needs spk_keep_original(ctx,1) before the band is set"); return SPK_ERR_STATE; }
+  // always the UNSCALED, unfactored operator: the kept original when there is one, else the working band while it
+  // is still neither factored nor equilibrated
+  const double* A = c->orig ? c->orig : ((c->factored || c->rscale) ? nullptr : c->band);
+  if (!A) { SPK_SET_ERR(c, "spk_mult after spk_factor / spk_set_scaling needs spk_keep_original(ctx,1) before them"); return SPK_ERR_STATE; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   const int64_t n = c->L.n;
   if (c->opts.mem == SPK_MEM_HOST) {
-    double* tx; double* ty;
-    SPK_CUDA(c, cudaMalloc(&tx, sizeof(double) * (size_t)n));
-    SPK_CUDA(c, cudaMalloc(&ty, sizeof(double) * (size_t)n));
+    double* tx = stage_buf(c, 0, sizeof(double) * (size_t)n);
+    double* ty = stage_buf(c, 1, sizeof(double) * (size_t)n);
+    if (!tx || !ty) return SPK_ERR_NOMEM;
     SPK_CUDA(c, cudaMemcpyAsync(tx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     int rc = spk_launch_matmult(c, A, tx, ty);
     cudaError_t e = cudaMemcpyAsync(y, ty, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(tx); cudaFree(ty);
     if (rc == SPK_OK && e != cudaSuccess) { SPK_SET_ERR(c, "mult copy failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
     return rc;
   }
@@ -710,19 +734,20 @@ extern "C" int spk_mult(spk_ctx* c, const double* x, double* y) {
 extern "C" int spk_permute(spk_ctx* c, const int* idx, int inverse, double* v, int64_t n) {
   if (!c || !idx || !v || n <= 0) return SPK_ERR_ARG;
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
-  int* d_idx; double *d_in, *d_out;
-  SPK_CUDA(c, cudaMalloc(&d_idx, sizeof(int) * (size_t)n));
-  SPK_CUDA(c, cudaMalloc(&d_out, sizeof(double) * (size_t)n));
+  int* d_idx = (int*)stage_buf(c, 2, sizeof(int) * (size_t)n);
+  double* d_out = stage_buf(c, 1, sizeof(double) * (size_t)n);
+  if (!d_idx || !d_out) return SPK_ERR_NOMEM;
   SPK_CUDA(c, cudaMemcpyAsync(d_idx, idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   const bool host = (c->opts.mem == SPK_MEM_HOST);
+  double* d_in = v;
   if (host) {
-    SPK_CUDA(c, cudaMalloc(&d_in, sizeof(double) * (size_t)n));
+    d_in = stage_buf(c, 0, sizeof(double) * (size_t)n);
+    if (!d_in) return SPK_ERR_NOMEM;
     SPK_CUDA(c, cudaMemcpyAsync(d_in, v, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  } else d_in = v;
+  }
   int rc = spk_launch_gather(c, d_idx, inverse, d_in, d_out, n);
   cudaError_t e = cudaMemcpyAsync(v, d_out, sizeof(double) * (size_t)n, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(d_idx); cudaFree(d_out); if (host) cudaFree(d_in);
   if (rc == SPK_OK && e != cudaSuccess) { SPK_SET_ERR(c, "permute copy failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
   return rc;
 }
@@ -731,14 +756,19 @@ extern "C" int spk_krylov(spk_ctx* c, int method, int restart, double rtol, int 
                           double* rnorm, int* converged) {
   if (!c || !b || !x || !its || !rnorm) return SPK_ERR_ARG;
   if (!c->factored) { SPK_SET_ERR(c, "spk_krylov before spk_factor"); return SPK_ERR_STATE; }
+  if (c->opts.nranks > 1) {
+    SPK_SET_ERR(c, "spk_krylov on a sharded context: the dots need an all-reduce and the apply the boundary exchanges -- use ShardedSpike.krylov (spike_petsc_b200/sharded.py), which drives the split-phase calls");
+    return SPK_ERR_STATE;
+  }
   if (!c->opA.ia && !c->orig) { SPK_SET_ERR(c, "spk_krylov needs an operator: spk_set_operator_csr or spk_keep_original"); return SPK_ERR_STATE; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   const int64_t n = c->L.n;
   const double* bd = b; double* xd = x;
   double *tb = nullptr, *tx = nullptr;
   if (c->opts.mem == SPK_MEM_HOST) {
-    SPK_CUDA(c, cudaMalloc(&tb, sizeof(double) * (size_t)n));
-    SPK_CUDA(c, cudaMalloc(&tx, sizeof(double) * (size_t)n));
+    tb = stage_buf(c, 0, sizeof(double) * (size_t)n);
+    tx = stage_buf(c, 1, sizeof(double) * (size_t)n);
+    if (!tb || !tx) return SPK_ERR_NOMEM;
     SPK_CUDA(c, cudaMemcpyAsync(tb, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     bd = tb; xd = tx;
   }
@@ -750,7 +780,6 @@ extern "C" int spk_krylov(spk_ctx* c, int method, int restart, double rtol, int 
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { SPK_SET_ERR(c, "krylov copy-back failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
   }
-  if (tb) { cudaFree(tb); cudaFree(tx); }
   return rc;
 }
 
@@ -818,6 +847,7 @@ extern "C" int spk_debug_reset_factored(spk_ctx* c) { if (!c) return SPK_ERR_ARG
 // restore the unfactored band from the copy kept by spk_keep_original(ctx,1) (device-to-device, async)
 extern "C" int spk_debug_restore_band(spk_ctx* c) {
   if (!c || !c->orig) return SPK_ERR_STATE;
+  if (c->rscale) { SPK_SET_ERR(c, "restore_band on an equilibrated context would drop the scaling"); return SPK_ERR_STATE; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   SPK_CUDA(c, cudaMemcpyAsync(c->band, c->orig, sizeof(double) * (size_t)c->L.elems(), cudaMemcpyDeviceToDevice, c->stream));
   c->factored = 0; c->launches = 0;

@@ -97,6 +97,7 @@ struct spk_ctx {
   int bnd_cols;                     // right-hand-side columns the boundary exchange buffers (remoteGtop, remoteXbot, xbBoundary) hold
   double *rscale, *cscale;   // optional equilibration (spk_set_scaling): the factored band is diag(r) A diag(c)
   double *cscale_base;       // allocation behind cscale: [kp left-halo scales | n local | kp right-halo scales]
+  void* stage[4]; size_t stage_bytes[4];   // grow-only staging for host-vector calls (capi.cu)
   // operator for Krylov
   CsrDev opA;
   // bookkeeping

@@ -70,6 +70,19 @@ struct Kry {
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) fail = 1;
   }
   double dot(const double* x, const double* y) { double h; dots(x, n, 1, y, &h); return h; }
+  // the same reductions left in device memory at hdev + off (no copy, no synchronisation)
+  void dots_dev(const double* V, int64_t ld, int nv, const double* w, int off) {
+    for (int v0 = 0; v0 < nv; v0 += 8) {
+      const int m = nv - v0 < 8 ? nv - v0 : 8;
+      cudaMemsetAsync(hdev + off + v0, 0, sizeof(double) * m, c->stream);
+      k_multi_dot<<<grid, 256, 0, c->stream>>>(V + (int64_t)v0 * ld, ld, m, w, n, hdev + off + v0);
+      check();
+    }
+  }
+  void fetch(double* host, int cnt) {   // ONE device-to-host copy + synchronisation
+    cudaMemcpyAsync(host, hdev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) fail = 1;
+  }
   void axpby(double a, const double* x, double b, double* y) { k_axpby<<<grid, 256, 0, c->stream>>>(a, x, b, y, n); check(); }
   void lin3(const double* x, double a, const double* y, double b, const double* w, double* z) { k_lin3<<<grid, 256, 0, c->stream>>>(x, a, y, b, w, z, n); check(); }
 };
@@ -86,9 +99,9 @@ int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, 
   int rc = SPK_OK;
   SPK_CUDA(c, cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, c->stream));
   if (method == SPK_KSP_GMRES) {
-    double *V, *t;
-    SPK_CUDA(c, cudaMalloc(&V, sizeof(double) * (size_t)n * (m + 1)));
-    SPK_CUDA(c, cudaMalloc(&t, sizeof(double) * (size_t)n));
+    double *V = nullptr, *t = nullptr;
+    if (cudaMalloc(&V, sizeof(double) * (size_t)n * (m + 2)) != cudaSuccess) { SPK_SET_ERR(c, "GMRES basis of %d vectors does not fit", m + 1); return SPK_ERR_NOMEM; }
+    t = V + (size_t)n * (m + 1);
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
     if ((rc = K.pc(b, V))) goto gdone;
     {
@@ -113,11 +126,14 @@ int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, 
           double* vj1 = V + (size_t)(j + 1) * n;
           if ((rc = K.amul(V + (size_t)j * n, t))) goto gdone;
           if ((rc = K.pc(t, vj1))) goto gdone;
-          K.dots(V, n, j + 1, vj1, hcol.data());  // classical Gram-Schmidt: all dots against the unmodified w
-          SPK_CUDA(c, cudaMemcpyAsync(K.hdev, hcol.data(), sizeof(double) * (j + 1), cudaMemcpyHostToDevice, c->stream));
+          // classical Gram-Schmidt, one host round per iteration: h = V^T w stays on the device and feeds the
+          // update w -= V h directly; ||w||^2 lands behind it; (h, ||w||^2) come back in a single copy
+          K.dots_dev(V, n, j + 1, vj1, 0);
           k_multi_axpy<<<K.grid, 256, 0, c->stream>>>(V, n, j + 1, K.hdev, vj1, n);
           K.check();
-          const double hn = std::sqrt(K.dot(vj1, vj1));
+          K.dots_dev(vj1, n, 1, vj1, j + 1);
+          K.fetch(hcol.data(), j + 2);
+          const double hn = std::sqrt(hcol[j + 1]);
           for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
           H[(size_t)(j + 1) * m + j] = hn;
           if (hn != 0.0) K.axpby(1.0 / hn, vj1, 0.0, vj1);
@@ -150,7 +166,7 @@ int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, 
     }
   gdone:
     cudaStreamSynchronize(c->stream);
-    cudaFree(V); cudaFree(t);
+    cudaFree(V);
   } else {
     double *r, *rh, *p, *v, *s, *t, *tmp;
     SPK_CUDA(c, cudaMalloc(&r, sizeof(double) * (size_t)n * 7));
@@ -163,8 +179,9 @@ int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, 
       res = bnorm;
       SPK_CUDA(c, cudaMemcpyAsync(rh, r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
       if (bnorm == 0.0) conv = 1;
+      double rho_next = K.dot(rh, r);
       while (!conv && it < maxit) {
-        const double rho1 = K.dot(rh, r);
+        const double rho1 = rho_next;
         if (rho1 == 0.0) break;
         const double beta = (rho1 / rho) * (alpha / omega);
         // p = r + beta (p - omega v)
@@ -175,13 +192,17 @@ int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, 
         K.lin3(r, -alpha, v, 0.0, nullptr, s);
         if ((rc = K.amul(s, tmp))) goto bdone;
         if ((rc = K.pc(tmp, t))) goto bdone;
-        const double tt = K.dot(t, t);
-        omega = (tt == 0.0) ? 0.0 : K.dot(t, s) / tt;
+        double ts2[2];   // (t,t) and (t,s) in one host round
+        K.dots_dev(t, n, 1, t, 0); K.dots_dev(t, n, 1, s, 1); K.fetch(ts2, 2);
+        const double tt = ts2[0];
+        omega = (tt == 0.0) ? 0.0 : ts2[1] / tt;
         K.lin3(x, alpha, p, omega, s, x);
         K.lin3(s, -omega, t, 0.0, nullptr, r);
         rho = rho1;
         ++it;
-        res = std::sqrt(K.dot(r, r));
+        double rr2[2];   // (r,r) for the convergence test and (rh,r) for the next iteration in one host round
+        K.dots_dev(r, n, 1, r, 0); K.dots_dev(rh, n, 1, r, 1); K.fetch(rr2, 2);
+        res = std::sqrt(rr2[0]); rho_next = rr2[1];
         if (res <= rtol * bnorm) conv = 1;
         if (omega == 0.0) break;
       }

@@ -258,6 +258,130 @@ class ShardedSpike:
         self.e.mult(self._ptr(xvec), self._ptr(yvec))
         return yvec
 
+    # ---- sharded Krylov: inner KSPSolve of KSPSolve_Reorder (/root/reference/src/kspreorder.c:124) on a row-block
+    #      sharded band.  Same recurrences as csrc/krylov.cu (PETSc defaults restated: x0 = 0, left preconditioning,
+    #      preconditioned residual norm, ||r_k|| <= rtol ||M^-1 b||, GMRES(restart) with classical Gram-Schmidt).
+    #      Operator = sharded band MatMult (kp-entry halos), preconditioner = sharded SPIKE solve (two vector
+    #      exchanges), every group of inner products = ONE all-reduce of a few doubles.
+    def _dots(self, pairs):
+        import torch
+        t = torch.stack([torch.dot(a, b) for a, b in pairs])
+        if self.world > 1:
+            td = self.dist
+            if td is None:
+                import torch.distributed as td
+            td.all_reduce(t)
+        return t.tolist()
+
+    def krylov(self, bvec, xvec, method=capi.GMRES, restart=30, rtol=1e-5, maxit=10000):
+        """-> (iterations, residual norm, converged); xvec receives this rank's rows of the solution."""
+        import math
+        import torch
+        n = bvec.numel()
+        new = lambda: torch.empty(n, dtype=bvec.dtype, device=bvec.device)  # noqa: E731
+        x = xvec
+        x.zero_()
+        it, conv, res = 0, False, 0.0
+        if method == capi.GMRES:
+            m = restart if restart > 0 else 30
+            V = [new() for _ in range(m + 1)]
+            t = new()
+            self.solve(bvec, V[0])
+            bnorm = math.sqrt(self._dots([(V[0], V[0])])[0])
+            res = bnorm
+            if bnorm == 0.0:
+                return 0, 0.0, True
+            first = True
+            while it < maxit and not conv:
+                if not first:
+                    self.mult(x, t)
+                    torch.sub(bvec, t, out=t)
+                    self.solve(t, V[0])
+                    res = math.sqrt(self._dots([(V[0], V[0])])[0])
+                    if res <= rtol * bnorm:
+                        conv = True
+                        break
+                first = False
+                V[0].mul_(1.0 / res)
+                H = [[0.0] * m for _ in range(m + 1)]
+                cs, sn, g = [0.0] * m, [0.0] * m, [0.0] * (m + 1)
+                g[0] = res
+                j = 0
+                while j < m and it < maxit:
+                    w = V[j + 1]
+                    self.mult(V[j], t)
+                    self.solve(t, w)
+                    h = self._dots([(V[i], w) for i in range(j + 1)])      # classical Gram-Schmidt: one all-reduce
+                    for i in range(j + 1):
+                        w.add_(V[i], alpha=-h[i])
+                    hn = math.sqrt(self._dots([(w, w)])[0])
+                    for i in range(j + 1):
+                        H[i][j] = h[i]
+                    H[j + 1][j] = hn
+                    if hn != 0.0:
+                        w.mul_(1.0 / hn)
+                    for i in range(j):
+                        a0, a1 = H[i][j], H[i + 1][j]
+                        H[i][j] = cs[i] * a0 + sn[i] * a1
+                        H[i + 1][j] = -sn[i] * a0 + cs[i] * a1
+                    a0, a1 = H[j][j], H[j + 1][j]
+                    d = math.hypot(a0, a1)
+                    cs[j], sn[j] = a0 / d, a1 / d
+                    H[j][j], H[j + 1][j] = d, 0.0
+                    g[j + 1] = -sn[j] * g[j]
+                    g[j] = cs[j] * g[j]
+                    it += 1
+                    res = abs(g[j + 1])
+                    j += 1
+                    if res <= rtol * bnorm:
+                        conv = True
+                        break
+                y = [0.0] * j
+                for i in range(j - 1, -1, -1):
+                    sacc = g[i]
+                    for q in range(i + 1, j):
+                        sacc -= H[i][q] * y[q]
+                    y[i] = sacc / H[i][i]
+                for i in range(j):
+                    x.add_(V[i], alpha=y[i])
+            return it, res, conv
+        # BiCGStab
+        r, rh, p, v, s_, t, tmp = (new() for _ in range(7))
+        p.zero_(); v.zero_()
+        rho = alpha = omega = 1.0
+        self.solve(bvec, r)
+        bnorm = math.sqrt(self._dots([(r, r)])[0])
+        res = bnorm
+        rh.copy_(r)
+        if bnorm == 0.0:
+            return 0, 0.0, True
+        rho_next = self._dots([(rh, r)])[0]
+        while not conv and it < maxit:
+            rho1 = rho_next
+            if rho1 == 0.0:
+                break
+            beta = (rho1 / rho) * (alpha / omega)
+            p.add_(v, alpha=-omega).mul_(beta).add_(r)          # p = r + beta (p - omega v)
+            self.mult(p, tmp)
+            self.solve(tmp, v)
+            alpha = rho1 / self._dots([(rh, v)])[0]
+            torch.add(r, v, alpha=-alpha, out=s_)
+            self.mult(s_, tmp)
+            self.solve(tmp, t)
+            tt, ts = self._dots([(t, t), (t, s_)])
+            omega = 0.0 if tt == 0.0 else ts / tt
+            x.add_(p, alpha=alpha).add_(s_, alpha=omega)
+            torch.add(s_, t, alpha=-omega, out=r)
+            rho = rho1
+            it += 1
+            rr, rho_next = self._dots([(r, r), (rh, r)])
+            res = math.sqrt(rr)
+            if res <= rtol * bnorm:
+                conv = True
+            if omega == 0.0:
+                break
+        return it, res, conv
+
     def _sync(self, t):
         # No host synchronisation: the engine enqueues on the legacy default stream, which is also
         # torch's current stream, and torch.distributed orders its NCCL stream against the current

@@ -41,6 +41,16 @@ class NumpyEngine:
     def tip_size(self):
         return self.k
 
+    def mult(self, x, y):
+        """y = A x on this rank's rows; the neighbours' k-entry halos arrive through set_boundary."""
+        k = self.k
+        v = self.Aloc @ x.numpy()
+        if self.C is not None:
+            v[:k] += self.C @ self.remote["halo_l"]
+        if self.B is not None:
+            v[-k:] += self.B @ self.remote["halo_r"]
+        y.copy_(torch.from_numpy(v))
+
     def factor_phase(self, ph):
         k, m = self.k, self.m
         if ph == 1:
@@ -68,6 +78,10 @@ class NumpyEngine:
             self.remote["gt"] = v
         elif which == capi.BND_REMOTE_X_BOT:
             self.remote["xb"] = v
+        elif which == capi.BND_HALO_LEFT:
+            self.remote["halo_l"] = v
+        elif which == capi.BND_HALO_RIGHT:
+            self.remote["halo_r"] = v
 
     def solve_phase(self, ph, b=None, x=None):
         k = self.k
@@ -214,3 +228,76 @@ def test_shard_rows_are_tile_aligned():
         b = shard_rows(n, w)
         assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
         assert all(v % 8 == 0 for v in b[:-1])
+
+
+# ---------------------------------------------------------------------------------------------- sharded Krylov
+def _krylov_worker(rank, world, port, n, k, method, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle import oracle as O
+        from spike_petsc_b200.sharded import ShardedSpike, shard_rows
+        kb = 3                                     # preconditioner: the band of half-width kb < k of the operator
+        a = O.gen_band(n, k, delta=0.6)            # not diagonally dominant: the Krylov loop has work to do
+        A = np.zeros((n, n))
+        for i in range(n):
+            for d in range(-k, k + 1):
+                if 0 <= i + d < n:
+                    A[i, i + d] = a[i, d + k]
+        Bm = np.triu(np.tril(A, kb), -kb)
+        u = O.gen_vec(n, 7)
+        bfull = A @ u
+        bounds = shard_rows(n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+
+        class Eng(NumpyEngine):                    # SPIKE on the band Bm, MatMult with the full operator A
+            def __init__(self):
+                super().__init__(Bm, lo, hi, k, rank, world)
+                self.Aop = A[lo:hi, max(lo - k, 0):min(hi + k, n)].copy()
+
+            def mult(self, x, y):
+                xl = self.remote["halo_l"] if lo > 0 else np.zeros(0)
+                xr = self.remote["halo_r"] if hi < n else np.zeros(0)
+                y.copy_(torch.from_numpy(self.Aop @ np.concatenate([xl, x.numpy(), xr])))
+
+        S = ShardedSpike(Eng(), rank, world)
+        b = torch.from_numpy(bfull[lo:hi].copy())
+        x = torch.zeros_like(b)
+        S.factor(b)
+        its, res, conv = S.krylov(b, x, method=method, restart=30, rtol=1e-9, maxit=500)
+        err = torch.tensor([float(np.abs(x.numpy() - u[lo:hi]).max())], dtype=torch.float64)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            # the same solve on one process: exact band LU of Bm as preconditioner (oracle Krylov)
+            band = np.zeros((n, 2 * k + 1))
+            for i in range(n):
+                for d in range(-kb, kb + 1):
+                    if 0 <= i + d < n:
+                        band[i, d + k] = A[i, i + d]
+            lu, _ = O.band_lu(band)
+            _, its_ref, _, rc_ref = O.krylov_band(a, lu, bfull, method=O.GMRES if method == 0 else O.BICGSTAB, restart=30, rtol=1e-9, maxit=500)
+            out.put((its, conv, err.item(), its_ref, rc_ref == 0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,method", [(2, 0), (3, 0), (2, 1), (3, 1)])
+def test_sharded_krylov_gloo(world, method):
+    """ShardedSpike.krylov (GMRES / BiCGStab with one all-reduce per group of dots, halo MatMult, sharded SPIKE
+    apply) needs the same number of iterations (+-1) as the single-process oracle Krylov with the exact band solve."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_krylov_worker, args=(r, world, port, 480, 5, method, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    its, conv, err, its_ref, conv_ref = q.get(timeout=5)
+    assert conv and conv_ref
+    assert abs(its - its_ref) <= 1, (its, its_ref)
+    assert err < 1e-6
