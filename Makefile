@@ -19,8 +19,9 @@ $(LIBDIR)/libspike_b200.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 # PETSc-shaped host glue (C): PCBANDED / KSPREORDER / MatCreateSubMatrixBanded on the C ABI
-$(LIBDIR)/libspike_petsc.so: $(HOST)/pcbanded.c $(HOST)/kspreorder.c $(HOST)/petscshim.c $(HOST)/matio.c $(HOST)/petscshim.h $(HOST)/spike_petsc.h $(LIBDIR)/libspike_b200.so
-	/usr/bin/gcc -O2 -fPIC -Wall -shared -o $@ $(HOST)/pcbanded.c $(HOST)/kspreorder.c $(HOST)/petscshim.c $(HOST)/matio.c -L$(LIBDIR) -lspike_b200 -Wl,-rpath,'$$ORIGIN' -lm
+HOSTSRC := $(HOST)/pcbanded.c $(HOST)/kspreorder.c $(HOST)/matbanded_type.c $(HOST)/ordering.c $(HOST)/petscshim.c $(HOST)/matio.c
+$(LIBDIR)/libspike_petsc.so: $(HOSTSRC) $(HOST)/petscshim.h $(HOST)/petsc_access.h $(HOST)/spike_petsc.h $(LIBDIR)/libspike_b200.so
+	/usr/bin/gcc -O2 -fPIC -Wall -shared -o $@ $(HOSTSRC) -L$(LIBDIR) -lspike_b200 -Wl,-rpath,'$$ORIGIN' -lm
 
 oracle:
 	$(MAKE) -C oracle

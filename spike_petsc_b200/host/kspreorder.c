@@ -13,7 +13,7 @@
  * Inner options use the "reorder_" prefix (:218-221): -reorder_ksp_type gmres|bcgs, -reorder_ksp_rtol,
  * -reorder_ksp_max_it, -reorder_ksp_gmres_restart, -reorder_pc_type banded, -reorder_pc_banded_kmax/frac.
  */
-#include "spike_petsc.h"
+#include "petsc_access.h"
 #include "../../include/spike_b200.h"
 #include <stdio.h>
 #include <stdlib.h>
@@ -34,40 +34,45 @@ static PetscErrorCode KSPSetFromOptions_Reorder(KSP ksp) {   /* :134-151 */
   char inner[144], tname[64] = "";
   PetscBool flg;
   snprintf(r->ordertype, sizeof r->ordertype, "natural");   /* MATORDERINGNATURAL, :144 */
-  PetscOptionsGetString(ksp->prefix, "-mat_ordering_type", r->ordertype, sizeof r->ordertype, NULL);
-  snprintf(inner, sizeof inner, "%sreorder_", ksp->prefix);
+  PetscOptionsGetString(SPK_PREFIX(ksp), "-mat_ordering_type", r->ordertype, sizeof r->ordertype, NULL);
+  snprintf(inner, sizeof inner, "%sreorder_", SPK_PREFIX(ksp));
   PetscOptionsGetString(inner, "-ksp_type", tname, sizeof tname, &flg);
   if (flg) {
     if (!strcmp(tname, "gmres")) r->method = SPK_KSP_GMRES;
     else if (!strcmp(tname, "bcgs")) r->method = SPK_KSP_BCGS;
-    else SETERRQ(PETSC_ERR_SUP, "inner KSP type %s not available on the device (gmres, bcgs)", tname);
+    else SPK_ERR(PETSC_ERR_SUP, "inner KSP type %s not available on the device (gmres, bcgs)", tname);
   }
   PetscOptionsGetReal(inner, "-ksp_rtol", &ksp->rtol, NULL);
   PetscOptionsGetInt(inner, "-ksp_max_it", &ksp->max_it, NULL);
   PetscOptionsGetInt(inner, "-ksp_gmres_restart", &r->restart, NULL);
   PetscOptionsGetString(inner, "-pc_type", tname, sizeof tname, &flg);
-  if (flg && strcmp(tname, "banded")) SETERRQ(PETSC_ERR_SUP, "inner PC type %s not available (banded)", tname);
-  snprintf(r->pc->prefix, sizeof r->pc->prefix, "%s", inner);
-  return r->pc->ops->setfromoptions(r->pc);
+  if (flg && strcmp(tname, "banded")) SPK_ERR(PETSC_ERR_SUP, "inner PC type %s not available (banded)", tname);
+  PCSetOptionsPrefix(r->pc, inner);
+  return PCSetFromOptions(r->pc);
 }
 
 static PetscErrorCode KSPSetUp_Reorder(KSP ksp) {            /* :11-28 */
   KSP_Reorder *r = (KSP_Reorder *)ksp->data;
   PetscErrorCode ierr;
   Mat A = ksp->A, M = ksp->M ? ksp->M : ksp->A;
-  if (!A) SETERRQ(PETSC_ERR_ARG_WRONGSTATE, "KSPREORDER: no operators");
+  PetscInt n, nr, nc; const PetscInt *ai, *aj, *ridx, *cidx; const PetscScalar *aa;
+  if (!A) SPK_ERR(PETSC_ERR_ARG_WRONGSTATE, "KSPREORDER: no operators");
   if (r->rorder) { ISDestroy(&r->rorder); ISDestroy(&r->corder); }   /* the reference leaks these on re-setup */
   ierr = MatGetOrdering(M, r->ordertype, &r->rorder, &r->corder);CHKERRQ(ierr);     /* :19 */
-  if (r->rorder->n != A->n || r->corder->n != A->n) SETERRQ(PETSC_ERR_ARG_OUTOFRANGE, "ordering has wrong length");
+  ierr = SpkMatGetCSR(A, &n, &ai, &aj, &aa);CHKERRQ(ierr);
+  ierr = SpkISGetIndices(r->rorder, &nr, &ridx);CHKERRQ(ierr);
+  ierr = SpkISGetIndices(r->corder, &nc, &cidx);CHKERRQ(ierr);
+  if (nr != n || nc != n) SPK_ERR(PETSC_ERR_ARG_OUTOFRANGE, "ordering has wrong length");
   /* PM = MatPermute(M, rorder, corder) (:20) is fused into the band extraction of the inner PC ...  */
   ierr = PCSetOperators(r->pc, A, M);CHKERRQ(ierr);
-  ierr = PCBandedSetPermutation_Private(r->pc, r->rorder->idx, r->corder->idx);CHKERRQ(ierr);
+  ierr = PCBandedSetPermutation_Private(r->pc, ridx, cidx);CHKERRQ(ierr);
   ierr = PCSetUp(r->pc);CHKERRQ(ierr);                                              /* KSPSetUp(inner), :24 */
   /* ... and PA = MatPermute(A, rorder, corder) (:21) into the device copy of the Krylov operator */
   spk_ctx *ctx = PCBandedGetContext_Private(r->pc);
-  if (spk_set_operator_csr(ctx, A->n, A->i, A->j, A->a, r->rorder->idx, r->corder->idx))
-    SETERRQ(PETSC_ERR_LIB, "KSPREORDER: %s", spk_last_error(ctx));
-  return 0;
+  if (spk_set_operator_csr(ctx, n, ai, aj, aa, ridx, cidx))
+    SPK_ERR(PETSC_ERR_LIB, "KSPREORDER: %s", spk_last_error(ctx));
+  ierr = SpkMatRestoreCSR(A, &n, &ai, &aj, &aa);CHKERRQ(ierr);
+  return 0;   /* (the index arrays stay borrowed by the inner PC until the ISs are destroyed) */
 }
 
 static PetscErrorCode KSPSolve_Reorder(KSP ksp) {            /* :113-128 */
@@ -75,15 +80,22 @@ static PetscErrorCode KSPSolve_Reorder(KSP ksp) {            /* :113-128 */
   Vec x = ksp->vec_sol, b = ksp->vec_rhs;
   spk_ctx *ctx = PCBandedGetContext_Private(r->pc);
   int its = 0, conv = 0; double rn = 0.0;
-  if (!ctx) SETERRQ(PETSC_ERR_ARG_WRONGSTATE, "KSPREORDER: solve before setup");
-  if (spk_permute(ctx, r->corder->idx, 0, x->a, x->n)) SETERRQ(PETSC_ERR_LIB, "%s", spk_last_error(ctx));   /* :122 */
-  if (spk_permute(ctx, r->rorder->idx, 0, b->a, b->n)) SETERRQ(PETSC_ERR_LIB, "%s", spk_last_error(ctx));   /* :123 */
-  if (spk_krylov(ctx, r->method, r->restart, ksp->rtol, ksp->max_it, b->a, x->a, &its, &rn, &conv))           /* :124 */
-    SETERRQ(PETSC_ERR_LIB, "KSPREORDER: %s", spk_last_error(ctx));
+  PetscInt n, nr; PetscScalar *xa, *ba; const PetscInt *ridx, *cidx; PetscErrorCode ierr;
+  if (!ctx) SPK_ERR(PETSC_ERR_ARG_WRONGSTATE, "KSPREORDER: solve before setup");
+  ierr = SpkVecGetArray(x, &n, &xa);CHKERRQ(ierr);
+  ierr = SpkVecGetArray(b, &n, &ba);CHKERRQ(ierr);
+  ierr = SpkISGetIndices(r->rorder, &nr, &ridx);CHKERRQ(ierr);
+  ierr = SpkISGetIndices(r->corder, &nr, &cidx);CHKERRQ(ierr);
+  if (spk_permute(ctx, cidx, 0, xa, n)) SPK_ERR(PETSC_ERR_LIB, "%s", spk_last_error(ctx));   /* :122 */
+  if (spk_permute(ctx, ridx, 0, ba, n)) SPK_ERR(PETSC_ERR_LIB, "%s", spk_last_error(ctx));   /* :123 */
+  if (spk_krylov(ctx, r->method, r->restart, ksp->rtol, ksp->max_it, ba, xa, &its, &rn, &conv))           /* :124 */
+    SPK_ERR(PETSC_ERR_LIB, "KSPREORDER: %s", spk_last_error(ctx));
   ksp->its = its; ksp->rnorm = rn;
   ksp->reason = conv ? 2 /* KSP_CONVERGED_RTOL */ : -3 /* KSP_DIVERGED_ITS */;                                /* :125 */
-  if (spk_permute(ctx, r->corder->idx, 1, x->a, x->n)) SETERRQ(PETSC_ERR_LIB, "%s", spk_last_error(ctx));   /* :126 */
-  if (spk_permute(ctx, r->rorder->idx, 1, b->a, b->n)) SETERRQ(PETSC_ERR_LIB, "%s", spk_last_error(ctx));   /* :127 */
+  if (spk_permute(ctx, cidx, 1, xa, n)) SPK_ERR(PETSC_ERR_LIB, "%s", spk_last_error(ctx));   /* :126 */
+  if (spk_permute(ctx, ridx, 1, ba, n)) SPK_ERR(PETSC_ERR_LIB, "%s", spk_last_error(ctx));   /* :127 */
+  ierr = SpkVecRestoreArray(x, &xa);CHKERRQ(ierr);
+  ierr = SpkVecRestoreArray(b, &ba);CHKERRQ(ierr);
   return 0;
 }
 
@@ -101,6 +113,9 @@ static PetscErrorCode KSPDestroy_Reorder(KSP ksp) {          /* :174-185 */
   return 0;
 }
 
+/* the embedded preconditioner (the reference reaches it through the "reorder_" options prefix only) */
+PetscErrorCode KSPReorderGetPC(KSP ksp, PC *pc) { *pc = ((KSP_Reorder *)ksp->data)->pc; return 0; }
+
 PetscErrorCode KSPCreate_Reorder(KSP ksp) {                  /* :197-223 */
   KSP_Reorder *r = (KSP_Reorder *)calloc(1, sizeof(*r));
   PetscErrorCode ierr;
@@ -114,6 +129,6 @@ PetscErrorCode KSPCreate_Reorder(KSP ksp) {                  /* :197-223 */
   ksp->ops->setfromoptions = KSPSetFromOptions_Reorder;
   ierr = PCCreate(&r->pc);CHKERRQ(ierr);
   ierr = PCCreate_Banded(r->pc);CHKERRQ(ierr);
-  snprintf(r->pc->prefix, sizeof r->pc->prefix, "%sreorder_", ksp->prefix);          /* :218-221 */
+  { char inner[144]; snprintf(inner, sizeof inner, "%sreorder_", SPK_PREFIX(ksp)); PCSetOptionsPrefix(r->pc, inner); }   /* :218-221 */
   return 0;
 }

@@ -9,7 +9,7 @@
  * Nothing here computes on the CPU except MatCreateSubMatrixBanded, which the reference exports as
  * a stand-alone host utility (src/matbanded.h:5) and which is restated for API completeness.
  */
-#include "spike_petsc.h"
+#include "petsc_access.h"
 #include "../../include/spike_b200.h"
 #include <math.h>
 #include <stdio.h>
@@ -18,31 +18,33 @@
 
 /* ---- MatCreateSubMatrixBanded, /root/reference/src/matbanded.c:22-107 (host utility) ---------- */
 PetscErrorCode MatCreateSubMatrixBanded(Mat A, PetscInt *kmax, PetscReal *frac, Mat *B) {
-  const PetscInt n = A->n;
+  PetscInt n; const PetscInt *ai, *aj; const PetscScalar *aa;
+  PetscErrorCode ierr = SpkMatGetCSR(A, &n, &ai, &aj, &aa);CHKERRQ(ierr);
   PetscReal *w = (PetscReal *)calloc((size_t)(n > 0 ? n : 1), sizeof(PetscReal));
   PetscReal normA = 0.0, normB = 0.0;
   PetscInt r, c, k;
   for (r = 0; r < n; ++r)                       /* :38-49 */
-    for (c = A->i[r]; c < A->i[r + 1]; ++c) { w[abs(r - A->j[c])] += fabs(A->a[c]); normA += fabs(A->a[c]); }
+    for (c = ai[r]; c < ai[r + 1]; ++c) { w[abs(r - aj[c])] += fabs(aa[c]); normA += fabs(aa[c]); }
   for (k = 0; k < *kmax; ++k) {                 /* :53-56; the reference has no k<n guard (reads past w) */
-    if (k >= n) { free(w); SETERRQ(PETSC_ERR_ARG_OUTOFRANGE, "kmax %d exceeds matrix order %d before the norm fraction is reached", *kmax, n); }
+    if (k >= n) { free(w); SPK_ERR(PETSC_ERR_ARG_OUTOFRANGE, "kmax %d exceeds matrix order %d before the norm fraction is reached", *kmax, n); }
     normB += w[k];
     if (normB >= (*frac) * normA) break;
   }
   free(w);
   PetscInt nnz = 0;                             /* :65-79 count, :84-99 copy (column order preserved) */
-  for (r = 0; r < n; ++r) for (c = A->i[r]; c < A->i[r + 1]; ++c) if (abs(A->j[c] - r) <= k) ++nnz;
+  for (r = 0; r < n; ++r) for (c = ai[r]; c < ai[r + 1]; ++c) if (abs(aj[c] - r) <= k) ++nnz;
   PetscInt *bi = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(n + 1));
   PetscInt *bj = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz > 0 ? nnz : 1));
   PetscScalar *ba = (PetscScalar *)malloc(sizeof(PetscScalar) * (size_t)(nnz > 0 ? nnz : 1));
   nnz = 0; bi[0] = 0;
   for (r = 0; r < n; ++r) {
-    for (c = A->i[r]; c < A->i[r + 1]; ++c) { if (abs(A->j[c] - r) > k) continue; bj[nnz] = A->j[c]; ba[nnz] = A->a[c]; ++nnz; }
+    for (c = ai[r]; c < ai[r + 1]; ++c) { if (abs(aj[c] - r) > k) continue; bj[nnz] = aj[c]; ba[nnz] = aa[c]; ++nnz; }
     bi[r + 1] = nnz;
   }
-  PetscErrorCode ierr = MatCreateSeqAIJWithArrays(n, bi, bj, ba, B);
+  ierr = MatCreateSeqAIJWithArrays(n, bi, bj, ba, B);
   free(bi); free(bj); free(ba);
   CHKERRQ(ierr);
+  ierr = SpkMatRestoreCSR(A, &n, &ai, &aj, &aa);CHKERRQ(ierr);
   *kmax = k;                                    /* :104-105 */
   *frac = normB / normA;
   return 0;
@@ -55,6 +57,7 @@ typedef struct {
   spk_ctx  *ctx;         /* replaces {Mat B; PC pc;}: the band lives on the GPU, factored in place */
   PetscInt  partitions, tip_tiles;
   const PetscInt *rowperm, *colperm;   /* borrowed from KSPREORDER: B = band(pmat(rowperm, colperm)) */
+  PetscInt  nsetup;                    /* factorisations performed (diagnostics / tests) */
 } PC_Banded;
 
 static PetscErrorCode PCReset_Banded(PC pc) {          /* :120-129 */
@@ -69,37 +72,48 @@ static PetscErrorCode PCDestroy_Banded(PC pc) {        /* :133-145 */
 }
 static PetscErrorCode PCSetFromOptions_Banded(PC pc) { /* :149-161 */
   PC_Banded *b = (PC_Banded *)pc->data;
-  PetscOptionsGetInt(pc->prefix, "-pc_banded_kmax", &b->kmax, NULL);
-  PetscOptionsGetReal(pc->prefix, "-pc_banded_frac", &b->frac, NULL);
+  PetscOptionsGetInt(SPK_PREFIX(pc), "-pc_banded_kmax", &b->kmax, NULL);
+  PetscOptionsGetReal(SPK_PREFIX(pc), "-pc_banded_frac", &b->frac, NULL);
   /* engine knobs (new): inner-object prefix "banded_" like the reference's embedded PC (:278-281) */
-  char inner[192]; snprintf(inner, sizeof inner, "%sbanded_", pc->prefix);
+  char inner[192]; snprintf(inner, sizeof inner, "%sbanded_", SPK_PREFIX(pc));
   PetscOptionsGetInt(inner, "-spike_partitions", &b->partitions, NULL);
   PetscOptionsGetInt(inner, "-spike_tip_tiles", &b->tip_tiles, NULL);
   return 0;
 }
+/* First call (setupcalled == 0, :171): choose k, extract the band, factor.  A later call means PETSc saw the operator
+ * change (PCSetUp returns early otherwise); the reference then re-runs PCSetUp(inner) on its stale B (:178) -- here
+ * the band is extracted from the current pmat again and refactored, which is what a changed operator needs. */
 static PetscErrorCode PCSetUp_Banded(PC pc) {          /* :165-180 */
   PC_Banded *b = (PC_Banded *)pc->data;
-  if (pc->setupcalled == 0) {
-    if (!pc->pmat) SETERRQ(PETSC_ERR_ARG_WRONGSTATE, "PCBANDED: no preconditioner matrix set");
-    if (b->ctx) spk_destroy(&b->ctx);
-    spk_opts o; spk_default_opts(&o);
-    o.partitions = b->partitions; o.tip_tiles = b->tip_tiles; o.mem = SPK_MEM_HOST;
-    if (spk_create(&b->ctx, &o)) SETERRQ(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(NULL));
-    b->k = b->kmax; b->f = b->frac;                    /* :172-173 */
-    int k = b->k; double f = b->f;
-    /* MatCreateSubMatrixBanded(pc->pmat, &b->k, &b->f, &b->B) (:174), on the (permuted) operator */
-    if (spk_set_band_csr(b->ctx, pc->pmat->n, pc->pmat->i, pc->pmat->j, pc->pmat->a, b->rowperm, b->colperm, &k, &f))
-      SETERRQ(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
-    b->k = k; b->f = f;
-    /* PCSetUp(b->pc) (:178): the SPIKE factorisation */
-    if (spk_factor(b->ctx)) SETERRQ(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
-  }
+  PetscInt n; const PetscInt *ai, *aj; const PetscScalar *aa;
+  PetscErrorCode ierr;
+  if (!pc->pmat) SPK_ERR(PETSC_ERR_ARG_WRONGSTATE, "PCBANDED: no preconditioner matrix set");
+  if (b->ctx) spk_destroy(&b->ctx);
+  spk_opts o; spk_default_opts(&o);
+  o.partitions = b->partitions; o.tip_tiles = b->tip_tiles; o.mem = SPK_MEM_HOST;
+  if (spk_create(&b->ctx, &o)) SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(NULL));
+  b->k = b->kmax; b->f = b->frac;                      /* :172-173 */
+  int k = b->k; double f = b->f;
+  /* MatCreateSubMatrixBanded(pc->pmat, &b->k, &b->f, &b->B) (:174), on the (permuted) operator */
+  ierr = SpkMatGetCSR(pc->pmat, &n, &ai, &aj, &aa);CHKERRQ(ierr);
+  if (spk_set_band_csr(b->ctx, n, ai, aj, aa, b->rowperm, b->colperm, &k, &f))
+    SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
+  ierr = SpkMatRestoreCSR(pc->pmat, &n, &ai, &aj, &aa);CHKERRQ(ierr);
+  b->k = k; b->f = f;
+  /* PCSetUp(b->pc) (:178): the SPIKE factorisation */
+  if (spk_factor(b->ctx)) SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
+  b->nsetup++;
   return 0;
 }
 static PetscErrorCode PCApply_Banded(PC pc, Vec x, Vec y) {  /* :184-192 */
   PC_Banded *b = (PC_Banded *)pc->data;
-  if (!b->ctx) SETERRQ(PETSC_ERR_ARG_WRONGSTATE, "PCBANDED: apply before setup");
-  if (spk_solve(b->ctx, x->a, y->a, 1)) SETERRQ(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
+  PetscInt n; PetscScalar *xa, *ya; PetscErrorCode ierr;
+  if (!b->ctx) SPK_ERR(PETSC_ERR_ARG_WRONGSTATE, "PCBANDED: apply before setup");
+  ierr = SpkVecGetArray(x, &n, &xa);CHKERRQ(ierr);
+  ierr = SpkVecGetArray(y, &n, &ya);CHKERRQ(ierr);
+  if (spk_solve(b->ctx, xa, ya, 1)) SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
+  ierr = SpkVecRestoreArray(x, &xa);CHKERRQ(ierr);
+  ierr = SpkVecRestoreArray(y, &ya);CHKERRQ(ierr);
   return 0;
 }
 static PetscErrorCode PCView_Banded(PC pc, char *buf, size_t len) {  /* :196-211 */
@@ -143,3 +157,4 @@ PetscErrorCode PCBandedGetInfo(PC pc, PetscInt *k, PetscReal *f, PetscInt *parti
 PetscErrorCode PCBandedSetPermutation_Private(PC pc, const PetscInt *rowperm, const PetscInt *colperm) {
   PC_Banded *b = (PC_Banded *)pc->data; b->rowperm = rowperm; b->colperm = colperm; return 0; }
 spk_ctx *PCBandedGetContext_Private(PC pc) { return ((PC_Banded *)pc->data)->ctx; }
+PetscErrorCode PCBandedGetSetupCount(PC pc, PetscInt *nsetup) { *nsetup = ((PC_Banded *)pc->data)->nsetup; return 0; }

@@ -55,7 +55,7 @@ PetscErrorCode MatGetOrdering(Mat A, const char *type, IS *row, IS *col) {
 PetscErrorCode MatCreateSeqAIJWithArrays(PetscInt n, const PetscInt *i, const PetscInt *j, const PetscScalar *a, Mat *A) {
   Mat m = (Mat)calloc(1, sizeof(*m));
   const PetscInt nnz = i[n];
-  m->n = n; m->refct = 1;
+  m->n = n; m->ncols = n; m->refct = 1; snprintf(m->type, sizeof m->type, "seqaij");
   m->i = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(n + 1));
   m->j = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz > 0 ? nnz : 1));
   m->a = (PetscScalar *)malloc(sizeof(PetscScalar) * (size_t)(nnz > 0 ? nnz : 1));
@@ -66,9 +66,37 @@ PetscErrorCode MatCreateSeqAIJWithArrays(PetscInt n, const PetscInt *i, const Pe
 }
 PetscErrorCode MatDestroy(Mat *A) {
   if (!A || !*A) return 0;
-  if (--(*A)->refct <= 0) { free((*A)->i); free((*A)->j); free((*A)->a); free(*A); }
+  if (--(*A)->refct <= 0) {
+    if ((*A)->ops->destroy) (*A)->ops->destroy(*A);
+    if ((*A)->i || (*A)->j) { free((*A)->i); free((*A)->j); free((*A)->a); }   /* (SeqDense borrows its array) */
+    free(*A);
+  }
   *A = NULL; return 0;
 }
+PetscErrorCode MatCreateSeqDense(PetscInt n, PetscInt ncols, PetscScalar *data, Mat *A) {
+  Mat m = (Mat)calloc(1, sizeof(*m));
+  m->n = n; m->ncols = ncols; m->a = data; m->refct = 1; snprintf(m->type, sizeof m->type, "seqdense");
+  *A = m; return 0;
+}
+static struct { char name[16]; MatCreateFn fn; } g_mat[8];
+static int g_nmat;
+PetscErrorCode MatRegister(const char *type, MatCreateFn fn) {
+  for (int i = 0; i < g_nmat; ++i) if (!strcmp(g_mat[i].name, type)) { g_mat[i].fn = fn; return 0; }
+  if (g_nmat >= 8) SETERRQ(PETSC_ERR_ARG_OUTOFRANGE, "too many Mat types");
+  snprintf(g_mat[g_nmat].name, 16, "%s", type); g_mat[g_nmat].fn = fn; ++g_nmat; return 0;
+}
+PetscErrorCode MatCreate(Mat *A) { Mat m = (Mat)calloc(1, sizeof(*m)); m->refct = 1; *A = m; return 0; }
+PetscErrorCode MatSetType(Mat A, const char *type) {
+  for (int i = 0; i < g_nmat; ++i) if (!strcmp(g_mat[i].name, type)) { snprintf(A->type, sizeof A->type, "%s", type); return g_mat[i].fn(A); }
+  SETERRQ(PETSC_ERR_ARG_OUTOFRANGE, "Unknown Mat type %s", type);
+}
+#define MAT_OP(A, op, ...) do { if (!(A)->ops->op) SETERRQ(PETSC_ERR_SUP, "Mat type %s has no " #op, (A)->type); return (A)->ops->op(__VA_ARGS__); } while (0)
+PetscErrorCode MatMult(Mat A, Vec x, Vec y) { MAT_OP(A, mult, A, x, y); }
+PetscErrorCode MatLUFactor(Mat A, IS row, IS col, const void *info) { MAT_OP(A, lufactor, A, row, col, info); }
+PetscErrorCode MatSolve(Mat A, Vec b, Vec x) { MAT_OP(A, solve, A, b, x); }
+PetscErrorCode MatMatSolve(Mat A, Mat B, Mat X) { MAT_OP(A, matsolve, A, B, X); }
+PetscErrorCode MatGetDiagonal(Mat A, Vec d) { MAT_OP(A, getdiagonal, A, d); }
+PetscErrorCode MatView(Mat A, char *buf, size_t len) { if (len) buf[0] = 0; MAT_OP(A, view, A, buf, len); }
 PetscErrorCode VecCreateSeqWithArray(PetscInt n, PetscScalar *a, Vec *v) { Vec x = (Vec)calloc(1, sizeof(*x)); x->n = n; x->a = a; *v = x; return 0; }
 PetscErrorCode VecDestroy(Vec *v) { if (v && *v) { free(*v); *v = NULL; } return 0; }
 PetscErrorCode ISCreateGeneral(PetscInt n, const PetscInt *idx, IS *is) {
@@ -93,12 +121,15 @@ PetscErrorCode PCDestroy(PC *pc) {
   free(*pc); *pc = NULL; return 0;
 }
 PetscErrorCode KSPCreate(KSP *ksp) { *ksp = (KSP)calloc(1, sizeof(**ksp)); (*ksp)->rtol = 1e-5; (*ksp)->max_it = 10000; return 0; }
-PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat M) { ksp->A = A; ksp->M = M; return 0; }
+PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat M) { ksp->A = A; ksp->M = M; ksp->setupstage = 0; return 0; }
+/* KSPSolve sets up once per operator (PETSc's setupstage): KSPSetOperators / KSPSetFromOptions ask for a new setup,
+ * repeated solves with the same operator reuse orderings, band and factors -- the reference's guard at
+ * src/matbanded.c:171 relies on exactly that. */
 PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
   PetscErrorCode ierr;
   ksp->vec_rhs = b; ksp->vec_sol = x;
   if (!ksp->ops->solve) SETERRQ(PETSC_ERR_ARG_WRONGSTATE, "KSP has no type");
-  ierr = ksp->ops->setup(ksp); CHKERRQ(ierr);
+  if (!ksp->setupstage) { ierr = ksp->ops->setup(ksp); CHKERRQ(ierr); ksp->setupstage = 1; }
   return ksp->ops->solve(ksp);
 }
 PetscErrorCode KSPDestroy(KSP *ksp) {
@@ -108,7 +139,7 @@ PetscErrorCode KSPDestroy(KSP *ksp) {
 }
 
 PetscErrorCode KSPSetOptionsPrefix(KSP ksp, const char *prefix) { snprintf(ksp->prefix, sizeof ksp->prefix, "%s", prefix ? prefix : ""); return 0; }
-PetscErrorCode KSPSetFromOptions(KSP ksp) { return ksp->ops->setfromoptions ? ksp->ops->setfromoptions(ksp) : 0; }
+PetscErrorCode KSPSetFromOptions(KSP ksp) { ksp->setupstage = 0; return ksp->ops->setfromoptions ? ksp->ops->setfromoptions(ksp) : 0; }
 PetscErrorCode KSPView(KSP ksp, char *buf, size_t len) { if (len) buf[0] = 0; return ksp->ops->view ? ksp->ops->view(ksp, buf, len) : 0; }
 PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt *its) { *its = ksp->its; return 0; }
 PetscErrorCode KSPGetConvergedReason(KSP ksp, int *reason) { *reason = ksp->reason; return 0; }

@@ -25,10 +25,22 @@ typedef enum { PETSC_FALSE, PETSC_TRUE } PetscBool;
 #define PETSC_ERR_SUP 56
 #define PETSC_ERR_LIB 76
 
-/* SeqAIJ-like matrix: 0-based CSR, rows sorted by column (what MatGetRow returns) */
-typedef struct _p_Mat { PetscInt n; PetscInt *i, *j; PetscScalar *a; int refct; } *Mat;
+/* SeqAIJ-like matrix: 0-based CSR, rows sorted by column (what MatGetRow returns).  Other Mat types (SeqDense:
+ * a = column-major n x ncols, i = j = NULL; MATBANDED: everything behind ->data) fill the ops table, as PETSc's
+ * MatCreate_XXX constructors do. */
+typedef struct _p_Mat *Mat;
 typedef struct _p_Vec { PetscInt n; PetscScalar *a; } *Vec;
 typedef struct _p_IS  { PetscInt n; PetscInt *idx; } *IS;
+struct _MatOps {
+  PetscErrorCode (*mult)(Mat, Vec, Vec);
+  PetscErrorCode (*lufactor)(Mat, IS, IS, const void *info);
+  PetscErrorCode (*solve)(Mat, Vec, Vec);
+  PetscErrorCode (*matsolve)(Mat, Mat, Mat);
+  PetscErrorCode (*getdiagonal)(Mat, Vec);
+  PetscErrorCode (*view)(Mat, char *buf, size_t len);
+  PetscErrorCode (*destroy)(Mat);
+};
+struct _p_Mat { PetscInt n; PetscInt *i, *j; PetscScalar *a; int refct; PetscInt ncols; struct _MatOps ops[1]; void *data; char type[16]; };
 
 typedef struct _p_PC *PC;
 struct _PCOps {
@@ -52,6 +64,7 @@ struct _KSPOps {
 };
 typedef PetscErrorCode (*MatOrderingFn)(Mat, const char *type, IS *row, IS *col);
 struct _p_KSP {
+  int setupstage;      /* 0: KSPSetUp needed (new operators / options), 1: set up */
   struct _KSPOps ops[1];
   Mat A, M;            /* operators (KSPSetOperators) */
   Vec vec_rhs, vec_sol;
@@ -74,6 +87,17 @@ PetscErrorCode MatGetOrdering(Mat, const char *type, IS *row, IS *col);
 /* object helpers */
 PetscErrorCode MatCreateSeqAIJWithArrays(PetscInt n, const PetscInt *i, const PetscInt *j, const PetscScalar *a, Mat *A);
 PetscErrorCode MatDestroy(Mat *A);
+PetscErrorCode MatCreateSeqDense(PetscInt n, PetscInt ncols, PetscScalar *data, Mat *A);   /* column-major, data borrowed */
+typedef PetscErrorCode (*MatCreateFn)(Mat);
+PetscErrorCode MatRegister(const char *type, MatCreateFn fn);     /* MatRegister("banded", MatCreate_Banded) */
+PetscErrorCode MatCreate(Mat *A);
+PetscErrorCode MatSetType(Mat A, const char *type);
+PetscErrorCode MatMult(Mat A, Vec x, Vec y);
+PetscErrorCode MatLUFactor(Mat A, IS row, IS col, const void *info);
+PetscErrorCode MatSolve(Mat A, Vec b, Vec x);
+PetscErrorCode MatMatSolve(Mat A, Mat B, Mat X);
+PetscErrorCode MatGetDiagonal(Mat A, Vec d);
+PetscErrorCode MatView(Mat A, char *buf, size_t len);
 PetscErrorCode VecCreateSeqWithArray(PetscInt n, PetscScalar *a, Vec *v);
 PetscErrorCode VecDestroy(Vec *v);
 PetscErrorCode ISCreateGeneral(PetscInt n, const PetscInt *idx, IS *is);

@@ -21,7 +21,20 @@ PetscErrorCode PCCreate_Banded(PC pc);
 PetscErrorCode PCBandedSetMaxHalfBandwith(PC pc, PetscInt kmax);   /* (sic) reference spelling, src/matbanded.c:305 */
 PetscErrorCode PCBandedSetNormFraction(PC pc, PetscReal frac);
 PetscErrorCode PCBandedGetInfo(PC pc, PetscInt *k, PetscReal *f, PetscInt *partitions, long long *boosted);
+PetscErrorCode PCBandedGetSetupCount(PC pc, PetscInt *nsetup);
 PetscErrorCode KSPCreate_Reorder(KSP ksp);
+PetscErrorCode KSPReorderGetPC(KSP ksp, PC *pc);
+/* MATBANDED Mat type (matbanded_type.c): MatRegister("banded", MatCreate_Banded); ops mult / lufactor / solve / matsolve /
+ * getdiagonal / view / destroy on the GPU band.  MatCreateBanded = MatCreate + MatSetType + MatBandedSetFromAIJ. */
+PetscErrorCode MatCreate_Banded(Mat B);
+PetscErrorCode MatBandedSetFromAIJ(Mat B, Mat A, PetscInt *kmax, PetscReal *frac);
+PetscErrorCode MatCreateBanded(Mat A, PetscInt *kmax, PetscReal *frac, Mat *B);
+PetscErrorCode MatBandedGetInfo(Mat B, PetscInt *k, PetscReal *f, PetscInt *nfactor);
+/* host orderings (ordering.c): reverse Cuthill-McKee and the deterministic stand-in for the reference's MC73-based
+ * "fiedler" ordering (src/petsc_mat_fiedler.c:11-58; MC73 is proprietary and absent).  perm[new] = old. */
+int SpkOrderingRCM(PetscInt n, const PetscInt *ai, const PetscInt *aj, PetscInt *perm);
+PetscErrorCode MatGetOrdering_RCM(Mat A, const char *type, IS *row, IS *col);
+PetscErrorCode MatGetOrdering_Fiedler(Mat A, const char *type, IS *row, IS *col);
 /* on-disk formats of the reference's drivers (matio.c): PETSc binary Mat/Vec (MatLoad, src/testbed2.c:93-96),
  * MatrixMarket export (src/wbm.c:520-523).  0-based CSR, arrays malloc'd for the caller (SpkFree). */
 int SpkMatLoadBinary(const char *path, int *rows, int *cols, int **ia, int **ja, double **a);

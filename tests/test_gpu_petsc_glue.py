@@ -132,6 +132,8 @@ def test_kspreorder_testbed2_flow(glue, oracle, ordering, ksp_type):
     if ordering != "natural":
         # move the dominant entries off the diagonal with a row permutation the matching must undo
         R = rng.permutation(n)
+        if ordering == "wbm":      # an involution (disjoint transpositions), see below
+            R = np.arange(n); pp = rng.permutation(n); R[pp[0::2]], R[pp[1::2]] = pp[1::2].copy(), pp[0::2].copy()
         A = sp.csr_matrix(A0[R, :])
         if ordering == "wbm":      # MatGetRowIJ(symmetric=TRUE) hazard: keep the pattern structurally symmetric
             if not oracle.have_mc64():
@@ -172,17 +174,13 @@ def test_kspreorder_testbed2_flow(glue, oracle, ordering, ksp_type):
     u = np.ones(n); b = np.ascontiguousarray(A @ u); b0 = b.copy(); x = np.zeros(n)
     vb, vx = _vec(L, b), _vec(L, x)
     rc = L.KSPSolve(ksp, vb, vx)
-    if ordering == "wbm":
-        # the reference exposes MC64's row matching as the COLUMN IS: the permuted matrix
-        # need not have a strong diagonal; parity here = same permutation applied, solve still succeeds or
-        # is reported as not converged -- never a crash.
-        assert rc == 0, L.PetscLastErrorMessage()
-    else:
-        assert rc == 0, L.PetscLastErrorMessage()
-        reason, its = C.c_int(), C.c_int()
-        L.KSPGetConvergedReason(ksp, C.byref(reason)); L.KSPGetIterationNumber(ksp, C.byref(its))
-        assert reason.value > 0 and its.value < 50
-        assert np.linalg.norm(x - u) < 1e-6            # "Error in solution" of src/testbed2.c:130-132
+    # "wbm": the reference exposes MC64's row matching as the COLUMN IS; the scrambling row permutation of
+    # this test is an involution, for which the two coincide, so the permuted matrix has its dominant diagonal back
+    assert rc == 0, L.PetscLastErrorMessage()
+    reason, its = C.c_int(), C.c_int()
+    L.KSPGetConvergedReason(ksp, C.byref(reason)); L.KSPGetIterationNumber(ksp, C.byref(its))
+    assert reason.value > 0 and its.value < 50
+    assert np.linalg.norm(x - u) < 1e-6            # "Error in solution" of src/testbed2.c:130-132
     np.testing.assert_array_equal(b, b0)                # b is permuted in place and restored (src/kspreorder.c:123,127)
     buf = C.create_string_buffer(1024); L.KSPView(ksp, buf, 1024)
     assert buf.value.decode().startswith(f"  reordering type = {ordering}\n")
@@ -218,4 +216,90 @@ def test_testbed2_from_petsc_binary_file(glue, tmp_path):
     vb, vx = _vec(L, b), _vec(L, x)
     assert L.KSPSolve(ksp, vb, vx) == 0, L.PetscLastErrorMessage()
     assert np.linalg.norm(x - u) / np.linalg.norm(u) < 1e-8
+    L.KSPDestroy(C.byref(ksp))
+
+
+def test_matbanded_mat_type(glue, oracle):
+    """MATBANDED: MatRegister("banded") / MatCreate / MatSetType / MatBandedSetFromAIJ, then MatMult, MatLUFactor,
+    MatSolve, MatMatSolve, MatGetDiagonal, MatView -- the Mat surface north_star names; k / frac as the reference's
+    extractor reports them (src/matbanded.c:104-105)."""
+    L = glue
+    vp = C.c_void_p
+    L.MatCreateBanded.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(vp)]
+    L.MatBandedGetInfo.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    for f in ("MatMult", "MatSolve", "MatMatSolve"):
+        getattr(L, f).argtypes = [vp, vp, vp]
+    L.MatLUFactor.argtypes = [vp, vp, vp, vp]
+    L.MatGetDiagonal.argtypes = [vp, vp]
+    L.MatView.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.MatCreateSeqDense.argtypes = [C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.MatDestroy.argtypes = [C.POINTER(vp)]
+    n, k = 5000, 9
+    A = _problem(n, k, 21); A.sort_indices()
+    m = _mat(L, A)
+    kk, ff, B = C.c_int(30), C.c_double(0.999), vp()
+    assert L.MatCreateBanded(m, C.byref(kk), C.byref(ff), C.byref(B)) == 0, L.PetscLastErrorMessage()
+    kref, fref = oracle.band_select(A.indptr, A.indices, A.data, 30, 0.999)
+    assert (kk.value, ff.value) == (kref, fref)
+    band = oracle.csr_to_band(A.indptr, A.indices, A.data, kref)
+    lu, _ = oracle.band_lu(band)
+    u = oracle.gen_vec(n, 4); y = np.zeros(n)
+    vu, vy = _vec(L, u), _vec(L, y)
+    assert L.MatMult(B, vu, vy) == 0, L.PetscLastErrorMessage()
+    yref = oracle.band_mult(band, u)
+    assert np.linalg.norm(y - yref) / np.linalg.norm(yref) < 1e-14
+    x = np.zeros(n); vx = _vec(L, x)
+    assert L.MatSolve(B, vy, vx) != 0                     # not factored yet
+    assert L.MatLUFactor(B, None, None, None) == 0, L.PetscLastErrorMessage()
+    assert L.MatSolve(B, vy, vx) == 0, L.PetscLastErrorMessage()
+    assert np.linalg.norm(x - oracle.band_solve(lu, y)) / np.linalg.norm(x) < 1e-10
+    assert L.MatMult(B, vu, vy) == 0                      # MatMult still multiplies by the unfactored band
+    assert np.linalg.norm(y - yref) / np.linalg.norm(yref) < 1e-14
+    nrhs = 5
+    Bm = np.asfortranarray(np.stack([oracle.band_mult(band, oracle.gen_vec(n, 30 + c)) for c in range(nrhs)], axis=1))
+    Xm = np.asfortranarray(np.zeros((n, nrhs)))
+    dB, dX = vp(), vp()
+    L.MatCreateSeqDense(n, nrhs, Bm.ctypes.data, C.byref(dB)); L.MatCreateSeqDense(n, nrhs, Xm.ctypes.data, C.byref(dX))
+    assert L.MatMatSolve(B, dB, dX) == 0, L.PetscLastErrorMessage()
+    for c in range(nrhs):
+        assert np.linalg.norm(Xm[:, c] - oracle.gen_vec(n, 30 + c)) / np.sqrt(n) < 1e-9
+    d = np.zeros(n); vd = _vec(L, d)
+    assert L.MatGetDiagonal(B, vd) == 0
+    np.testing.assert_array_equal(d, A.diagonal())
+    assert L.MatLUFactor(B, None, None, None) == 0        # refactor from the kept original
+    nf = C.c_int(); L.MatBandedGetInfo(B, None, None, C.byref(nf)); assert nf.value == 2
+    buf = C.create_string_buffer(512); L.MatView(B, buf, 512)
+    assert buf.value.decode().startswith(f"Mat Object: type=banded, rows={n}, cols={n}\n  half-bandwidth k = {kref}")
+    L.MatDestroy(C.byref(B))
+
+
+def test_kspsolve_sets_up_once_per_operator(glue):
+    """Two KSPSolve calls on one KSP factor once (PETSc's setup stage; the reference's guard at src/matbanded.c:171
+    relies on it); KSPSetOperators asks for a new setup."""
+    L = glue
+    L.PCBandedGetSetupCount.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    n, k = 3000, 6
+    A = _problem(n, k, 13); A.sort_indices()
+    L.PetscOptionsClear()
+    for name, val in [("-mat_ordering_type", "natural"), ("-reorder_ksp_type", "gmres"), ("-reorder_pc_type", "banded"),
+                      ("-reorder_ksp_rtol", "1e-10"), ("-reorder_pc_banded_kmax", "20"), ("-reorder_pc_banded_frac", "1.0")]:
+        L.PetscOptionsSetValue(name.encode(), val.encode())
+    m = _mat(L, A)
+    ksp = C.c_void_p(); L.KSPCreate(C.byref(ksp)); L.KSPCreate_Reorder(ksp)
+    L.KSPSetOperators(ksp, m, m)
+    assert L.KSPSetFromOptions(ksp) == 0
+    L.KSPReorderGetPC.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    inner_pc = C.c_void_p(); L.KSPReorderGetPC(ksp, C.byref(inner_pc))
+    for rep in range(2):
+        u = np.full(n, 1.0 + rep); b = np.ascontiguousarray(A @ u); x = np.zeros(n)
+        vb, vx = _vec(L, b), _vec(L, x)
+        assert L.KSPSolve(ksp, vb, vx) == 0, L.PetscLastErrorMessage()
+        assert np.linalg.norm(x - u) / np.linalg.norm(u) < 1e-8
+    cnt = C.c_int(); L.PCBandedGetSetupCount(inner_pc, C.byref(cnt))
+    assert cnt.value == 1
+    L.KSPSetOperators(ksp, m, m)                         # "new" operator: set up again
+    u = np.ones(n); b = np.ascontiguousarray(A @ u); x = np.zeros(n)
+    assert L.KSPSolve(ksp, _vec(L, b), _vec(L, x)) == 0
+    L.PCBandedGetSetupCount(inner_pc, C.byref(cnt))
+    assert cnt.value == 2
     L.KSPDestroy(C.byref(ksp))
