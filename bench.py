@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- SPIKE factor+solve of the synthetic diagonally dominant band N=10M, K=100, fp64
-(BASELINE.json metric / configs[2]) on N B200s of one node.
+"""bench.py -- SPIKE factor+solve of BASELINE.json's synthetic banded systems on N B200s of one node.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c3|c5|c2|c1]
   (N > 1: torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
-One "step" = one in-place factorisation (bottom-up tip windows, band LU, spike tips, reduced
-system) plus one solve of b = A*1 of the whole system, all ranks together (strong scaling: the same
-10M-row system is row-block sharded over the ranks; only spike tips cross NVLink).  The band is
-restored from a pristine device copy between steps, outside the timed brackets, because the
-factorisation is in place.  Prints ONE JSON line (rank 0).
+Default workload = the configuration BASELINE.json's metric is quoted on: C3, synthetic diagonally dominant band
+N = 10M, K = 100, fp64.  One "step" = one complete factorisation (tip windows, band LU, spike tips, reduced system)
+plus one solve of b = A*1 of the whole system by all ranks together (strong scaling: the same system is row-block
+sharded over the ranks; only spike tips cross NVLink).  Every step factors the kept unfactored band again (out of
+place: read the original, write the factors -- the same 2B of traffic as the in-place mode, nothing copied between
+steps).  Prints ONE JSON line (rank 0); the run exits non-zero when the solution error exceeds 1e-10.
+
+--config c5: BASELINE config 5 (N = 1M, K = 512, 32 right-hand sides; wide-band kernels, FP64 tensor roofline).
+At N = 1 the default run also reports the other single-GPU configurations (`other_configs`: C1, C2 at delta 1.2 / 1.0,
+C5 on one GPU, C4 end to end) so that they are driver-visible.
 """
 import argparse
 import json
@@ -22,10 +26,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_ROWS = 10_000_000
-K_HALF = 100
 SEED, DELTA = 20140601, 1.2
-METRIC = "spike_factor_plus_solve_ms_N10M_K100_fp64"
+CONFIGS = {
+    # name: rows, half-bandwidth, right-hand sides, partitions per GPU, truncation window (tiles), metric
+    "c3": dict(n=10_000_000, k=100, nrhs=1, parts=296, tip=78, metric="spike_factor_plus_solve_ms_N10M_K100_fp64"),
+    "c2": dict(n=1_000_000, k=50, nrhs=1, parts=592, tip=48, metric="spike_factor_plus_solve_ms_N1M_K50_fp64"),
+    "c1": dict(n=100_000, k=10, nrhs=1, parts=296, tip=24, metric="spike_factor_plus_solve_ms_N100k_K10_fp64"),
+    "c5": dict(n=1_000_000, k=512, nrhs=32, parts=64, tip=320, metric="spike_factor_plus_solve_ms_N1M_K512_32rhs_fp64"),
+}
+ERR_BAR = 1e-10
 
 
 def measured_peak():
@@ -33,6 +42,13 @@ def measured_peak():
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def fp64_tensor_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "MEASURED_FP64_PEAKS.json")))["fp64_dmma_tflops"]), "builder-measured (tools/microbench.cu)"
+    except Exception:
+        return 37.0, "builder-measured (round 1)"
 
 
 class ClockSampler:
@@ -76,24 +92,21 @@ class ClockSampler:
 
 def traffic_from_profiles():
     """dram bytes (read+write) per launch of the dominant kernel from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        return json.load(open(p)).get("k_band_lu_dram_bytes_per_launch")
-    except Exception:
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name))).get("k_band_lu_dram_bytes_per_launch")
+        except Exception:
+            continue
+    return None
 
 
 # ---------------------------------------------------------------------------------------------
-def run_reference(args):
-    """--impl reference: the reference CPU path restated (oracle): exact banded factor + solve as the
-    reference's PCBANDED + `-banded_pc_type lu` computes it, run partition-parallel (OpenMP SPIKE port)
-    on all host cores, on a bounded sample of the workload, scaled linearly in N."""
-    import numpy as np
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm uses every host core
-    if "TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ:
+# the reference CPU path, restated (oracle port): exact banded factor + solve as the reference's PCBANDED with
+# `-banded_pc_type lu` computes it, partition-parallel (OpenMP SPIKE port with exact windows) on all host cores.
+# ONE function for both the --impl reference arm and the cpu_baseline of our line, so the two agree by construction.
+# ---------------------------------------------------------------------------------------------
+def _host_threads():
+    if "TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ:   # torchrun exports OMP_NUM_THREADS=1
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import oracle as O
     try:
@@ -101,69 +114,300 @@ def run_reference(args):
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)))
     except OSError:
         pass
-    cores = O.num_threads()
-    n_s = 1_000_000          # 1/10 of the rows; banded factor/solve cost is linear in N at fixed K
-    scale = N_ROWS / n_s
-    a = O.gen_band(n_s, K_HALF, SEED, DELTA)
+    return O, O.num_threads()
+
+
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def cpu_port_run(cfg, sample_rows, steps, warmup):
+    """-> dict(ms per step at the FULL workload size, cores, sample_rows, extrapolated, err, serial_1core_ms)."""
+    import numpy as np
+    O, cores = _host_threads()
+    n_full, k = cfg["n"], cfg["k"]
+    n_s = min(sample_rows, n_full)
+    scale = n_full / n_s
+    a = O.gen_band(n_s, k, SEED, DELTA)
     b = O.band_mult(a, np.ones(n_s))
-    times = []
-    for it in range(args.warmup + args.steps):
-        S = O.Spike(n_s, K_HALF, max(cores * 4, 8), align=8, tip_rows=0)
+    times, err = [], 0.0
+    for it in range(warmup + steps):
+        S = O.Spike(n_s, k, max(cores * 4, 8), align=8, tip_rows=0)
         work = a.copy()
         t0 = time.perf_counter()
         S.factor(work, inplace=True)
         x = S.solve(b)
         dt = (time.perf_counter() - t0) * 1e3
-        if it >= args.warmup:
+        if it >= warmup:
             times.append(dt)
         err = float(np.abs(x - 1.0).max())
-    ms = sum(times) / len(times) * scale
-    line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic diagonally dominant band N=10M K=100 fp64, factor+solve (u=1, b=A*u)",
-                       "seed": SEED, "delta": DELTA},
-            "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port",
-                             "sample": f"N={n_s} rows (1/{int(scale)} of the workload) of the K=100 band, CPU truncated-SPIKE port "
-                                       f"with exact windows on {cores} threads, time scaled x{int(scale)} (cost linear in N); max|x-1|={err:.1e}"},
-            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
-
-
-def cpu_baseline_sample():
-    import numpy as np
-    from oracle import oracle as O
-    cores = O.num_threads()
-    n_s = 500_000
-    scale = N_ROWS / n_s
-    a = O.gen_band(n_s, K_HALF, SEED, DELTA)
-    b = O.band_mult(a, np.ones(n_s))
-    S = O.Spike(n_s, K_HALF, max(cores * 4, 8), align=8, tip_rows=0)
-    t0 = time.perf_counter()
-    S.factor(a, inplace=True)
-    x = S.solve(b)
-    ms = (time.perf_counter() - t0) * 1e3 * scale
-    # serial exact band LU (the reference runs `-n 1`, src/makefile:18) on a smaller slice
-    n1 = 100_000
-    a1 = O.gen_band(n1, K_HALF, SEED, DELTA)
+        del work, S
+    # the reference runs `-n 1` (src/makefile:18): serial no-pivot band LU + solve on ONE core, on a slice
+    n1 = min(100_000, n_s)
+    a1 = O.gen_band(n1, k, SEED, DELTA)
     b1 = O.band_mult(a1, np.ones(n1))
     t0 = time.perf_counter()
     lu, _ = O.band_lu(a1)
     O.band_solve(lu, b1)
-    serial_ms = (time.perf_counter() - t0) * 1e3 * (N_ROWS / n1)
-    return {"value": ms, "unit": "ms", "cores": cores, "kind": "port",
-            "sample": f"N={n_s} rows (1/{int(scale)}) of the K=100 workload, OpenMP SPIKE port, scaled x{int(scale)}; "
-                      f"max|x-1|={float(np.abs(x - 1).max()):.1e}; serial no-pivot band LU+solve on 1 core (N={n1}, scaled): {serial_ms:.0f} ms"}
+    serial_ms = (time.perf_counter() - t0) * 1e3 * (n_full / n1)
+    return {"ms": sum(times) / len(times) * scale, "cores": cores, "sample_rows": n_s, "extrapolated": n_s < n_full,
+            "scale": scale, "err": err, "serial_1core_ms": serial_ms, "serial_sample_rows": n1}
+
+
+def cpu_baseline_block(cfg, r):
+    what = f"N={r['sample_rows']} rows of the K={cfg['k']} band" + (f" (1/{int(round(r['scale']))} of the workload, time scaled linearly in N)"
+                                                                     if r["extrapolated"] else " (the full workload)")
+    return {"value": r["ms"], "unit": "ms", "cores": r["cores"], "kind": "port",
+            "sample": f"{what}; OpenMP truncated-SPIKE port with exact windows on {r['cores']} threads; max|x-1|={r['err']:.1e}",
+            "sample_rows": r["sample_rows"], "extrapolated": r["extrapolated"],
+            "serial_1core_ms": r["serial_1core_ms"], "serial_sample_rows": r["serial_sample_rows"],
+            "serial_note": "serial no-pivot band LU + solve on 1 core (the reference's `-n 1`, src/makefile:18), scaled linearly in N"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    # the full workload when host memory allows (band + working copy), else a 1/10 sample, flagged
+    need_gb = 8.0 * cfg["n"] * (2 * cfg["k"] + 1) * 2.3 / 1e9
+    full = _mem_available_gb() > need_gb + 8 and not args.reference_sample
+    sample = cfg["n"] if full else max(cfg["n"] // 10, 100_000)
+    r = cpu_port_run(cfg, sample, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": cfg["metric"], "value": r["ms"], "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic diagonally dominant band N={cfg['n']} K={cfg['k']} fp64, factor+solve (u=1, b=A*u)",
+                       "seed": SEED, "delta": DELTA},
+            "extrapolated": r["extrapolated"], "sample_rows": r["sample_rows"],
+            "cpu_baseline": cpu_baseline_block(cfg, r),
+            "e2e": {"value": r["ms"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
-def run_ours(args):
+# one banded configuration on this rank set: returns the measurements as a dict
+# ---------------------------------------------------------------------------------------------
+def run_band(cfgname, args, steps, warmup, delta=DELTA, parts=None, tip=None, sampler=None, want_e2e=False, krylov=False):
     import torch
     import torch.distributed as dist
     import spike_petsc_b200 as sp
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from spike_petsc_b200 import synthetic
+    import ctypes as C
+    cfg = CONFIGS[cfgname]
+    n, k, nrhs = cfg["n"], cfg["k"], cfg["nrhs"]
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    wide = k > 128
+    parts = parts if parts else cfg["parts"]
+    if wide and world > 1:
+        parts = max(parts // world, 2)
+    tip = cfg["tip"] if tip is None else tip
+    bounds = sp.shard_rows(n, world, k)
+    n_loc = bounds[rank + 1] - bounds[rank]
+    eng = sp.Spike(device=local, partitions=parts, tip_tiles=tip, mem=sp.MEM_DEVICE, rank=rank, nranks=world,
+                   row_offset=bounds[rank], n_global=n)
+    if not wide:
+        eng.keep_original(True)                    # out-of-place factorisation from the kept unfactored band
+    eng.set_band_synthetic(n_loc, k, SEED, delta)
+    S = sp.ShardedSpike(eng, rank, world, nrhs=nrhs)
+    L = sp.lib()
+    L.spk_debug_regen_synthetic.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
+    L.spk_debug_restore_band.argtypes = [C.c_void_p]
+    if nrhs == 1:
+        U = torch.ones(1, n_loc, dtype=torch.float64, device=dev)
+    else:       # SURVEY 8d: columns u_r = uniform(0,1) of the shared generator, seeds seed + r
+        import numpy as np
+        idx = np.arange(bounds[rank], bounds[rank + 1], dtype=np.uint64)
+        U = torch.from_numpy(np.stack([synthetic.u01(SEED + r, idx) for r in range(nrhs)])).to(dev)
+    B = torch.empty_like(U)
+    X = torch.empty_like(U)
+    for r in range(nrhs):
+        S.mult(U[r], B[r])                         # b = A u (src/testbed2.c:120-122), halos over NVLink
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_ms, stages, fms, sms = [], [], [], []
+    local_ms = 0.0
+    for it in range(warmup + steps):
+        if wide:                                   # in-place factorisation: regenerate the band outside the timed brackets
+            if L.spk_debug_regen_synthetic(eng._h, SEED, delta):
+                raise SystemExit("regen failed")
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        S.factor(U[0])
+        S.solve(B, X, nrhs=nrhs) if nrhs > 1 else S.solve(B[0], X[0])
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        local_ms = ms.item()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if it >= warmup:
+            iv = eng.view()
+            step_ms.append(ms.item()); stages.append(iv["stage_ms"]); fms.append(iv["factor_ms"]); sms.append(iv["solve_ms"])
+    clocks = sampler.stop() if sampler is not None else None
+    per_rank = None
+    if world > 1:
+        iv = eng.view()
+        mine = torch.tensor([local_ms, iv["factor_ms"], iv["solve_ms"]] + list(iv["stage_ms"][:6]), dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(v, 4) for v in t.tolist()] for t in allr]
+    S.check()
+    err2 = ((X - U).norm() ** 2); ref2 = (U.norm() ** 2)
+    if world > 1:
+        dist.all_reduce(err2); dist.all_reduce(ref2)
+    relerr = (err2.sqrt() / ref2.sqrt()).item()
+    info = eng.view()
+    kry = None
+    if krylov and world == 1:                      # the config's Krylov workload: SPIKE-preconditioned GMRES on the band operator
+        xk = torch.zeros(n_loc, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        _, its, rn, conv = eng.krylov(B[0].data_ptr(), method=sp.GMRES, restart=30, rtol=1e-5, maxit=200, x=xk.data_ptr())
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) * 1e3
+        kry = {"method": "gmres(30)", "rtol": 1e-5, "iterations": its, "converged": bool(conv), "ms_total": dt, "ms_per_iteration": dt / max(its, 1),
+               "rel_err_vs_exact_u": ((xk - U[0]).norm() / U[0].norm()).item()}
+    # ---- end to end through the C ABI with HOST buffers: pinned host band -> device (pack), factor, solve with host
+    #      b / x.  Every rank uploads its own slab over its own PCIe link.
+    e2e = None
+    if want_e2e:
+        if L.spk_debug_restore_band(eng._h):
+            raise SystemExit("restore failed")
+        torch.cuda.synchronize()
+        rows = torch.empty((n_loc, 2 * k + 1), dtype=torch.float64).pin_memory()
+        L.spk_get_band_rows(eng._h, rows.data_ptr())
+        bh = B[0].cpu().pin_memory(); xh = torch.empty_like(bh).pin_memory()
+        S = None
+        eng.close(); torch.cuda.empty_cache()
+        times = []
+        for it in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            h = sp.Spike(device=local, partitions=parts, tip_tiles=tip, mem=sp.MEM_HOST if world == 1 else sp.MEM_DEVICE,
+                         rank=rank, nranks=world, row_offset=bounds[rank], n_global=n)
+            if L.spk_set_band_dense(h._h, n_loc, k, rows.data_ptr(), sp.LAYOUT_ROWS, sp.MEM_HOST):
+                raise SystemExit("e2e upload failed")
+            h.n, h.k = n_loc, k
+            if world == 1:
+                h.factor()
+                L.spk_solve(h._h, bh.data_ptr(), xh.data_ptr(), 1)
+            else:
+                Sh = sp.ShardedSpike(h, rank, world)
+                bd = bh.to(dev, non_blocking=True); xd = torch.empty_like(bd)
+                Sh.factor(bd); Sh.solve(bd, xd)
+                xh.copy_(xd, non_blocking=True)
+            barrier()
+            times.append((time.perf_counter() - t0) * 1e3)
+            if world > 1:
+                Sh.check(); Sh = None
+            h.close()
+        tt = torch.tensor([min(times)], dtype=torch.float64, device=dev)
+        e2 = torch.tensor([float(((xh - 1.0) ** 2).sum())], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(e2)
+        e2e = {"value": tt.item(), "unit": "ms", "h2d_bytes_per_step": int(n * (2 * k + 1) * 8 + n * 8), "d2h_bytes_per_step": int(n * 8),
+               "rel_err": float((e2.item() / n) ** 0.5),
+               "note": "spk_set_band_dense(pinned host rows band) + factor + solve(host b -> host x), every rank its own slab over its own "
+                       "PCIe link; H2D of the band dominates"}
+    else:
+        eng.close()
+    mean = lambda v: sum(v) / len(v)  # noqa: E731
+    st = [mean([s[i] for s in stages]) for i in range(6)]
+    return {"cfg": cfg, "world": world, "ms": mean(step_ms), "step_ms_all": [round(v, 4) for v in step_ms], "factor_ms": mean(fms), "solve_ms": mean(sms),
+            "stage": st, "relerr": relerr, "info": info, "per_rank": per_rank, "clocks": clocks, "e2e": e2e, "krylov": kry,
+            "exchange": ("NVLink peer mailboxes (kernel stores + flags, csrc/peer.cu)" if world > 1 and os.environ.get("SPIKE_B200_PEER", "1") != "0" else "NCCL p2p"),
+            "delta": delta, "parts": parts, "tip": tip}
+
+
+def rooflines(r):
+    """roofline object of the dominant kernel + whole-step fractions for one run_band() result."""
+    cfg, world = r["cfg"], r["world"]
+    n, k, nrhs = cfg["n"], cfg["k"], cfg["nrhs"]
+    peak, which = measured_peak()
+    band_alg = 8.0 * n * (2 * k + 1)
+    lu = r["stage"][1]
+    flops = n * (2.0 * k * k + k) / world
+    if k > 128:
+        tpeak, tsrc = fp64_tensor_peak()
+        ach = flops / (lu * 1e-3) / 1e12
+        return {"bound": "fp64_tensor", "kernel": "k_wide_lu (trailing updates: 64^3 DMMA products)", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
+                "frac": ach / tpeak, "peak_source": tsrc, "traffic": None, "algorithmic_flops_per_launch": flops,
+                "note": "the FP64 tensor peak is not in MEASURED_PEAKS.json (HBM and bf16 only); profiles/MEASURED_FP64_PEAKS.json",
+                "whole_step_tflops": (flops + 2.0 * n * (2 * k + 1) * nrhs / world) / (r["ms"] * 1e-3) / 1e12,
+                "solve_hbm_frac": (band_alg + 32.0 * n * nrhs) / world / (r["solve_ms"] * 1e-3) / 1e9 / peak}
+    lu_bytes = 2.0 * band_alg / world
+    ach = lu_bytes / (lu * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "k_band_lu", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": which,
+            "traffic": traffic_from_profiles() if (world == 1 and k == 100) else None, "algorithmic_bytes_per_launch": lu_bytes,
+            "whole_step_frac": (3 * band_alg + 32.0 * n * nrhs) / world / (r["ms"] * 1e-3) / 1e9 / peak,
+            "factor_frac": 2 * band_alg / world / (r["factor_ms"] * 1e-3) / 1e9 / peak,
+            "solve_frac": (band_alg + 32.0 * n * nrhs) / world / (r["solve_ms"] * 1e-3) / 1e9 / peak,
+            "fp64_tflops": flops / (lu * 1e-3) / 1e12}
+
+
+def stage_dict(st):
+    return {"tip_windows": st[0], "band_lu": st[1], "spike_tips": st[2], "sweeps": st[3], "reduced": st[4], "corrections": st[5]}
+
+
+def c4_block(args):
+    """BASELINE config 4 end to end on one GPU (tests/test_gpu_c4.py is the parity test): sparse N = 2M, WBM + RCM
+    stand-in for the absent MC73, PCBANDED(50, 0.95), SPIKE-preconditioned BiCGStab rtol 1e-5.  MC64 itself lives under
+    oracle/_ref (the reference's own source, test infrastructure), so this leg takes the matching by construction: the
+    generator's row scramble R is an involution and MC64 returns exactly R (asserted at N = 2M by the test)."""
+    import ctypes as C
+    import numpy as np
+    import scipy.sparse as spm
+    import spike_petsc_b200 as sp
+    from spike_petsc_b200 import synthetic
+    n = 2_000_000
+    t0 = time.perf_counter()
+    A, Q, R = synthetic.c4_matrix(n)
+    t_gen = time.perf_counter() - t0
+    ia, ja, a = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+    glue = C.CDLL(os.path.join(ROOT, "spike_petsc_b200", "lib", "libspike_petsc.so"))
+    glue.SpkOrderingRCM.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    t0 = time.perf_counter()
+    PM = spm.csr_matrix(A[:, R]); PM.sort_indices()
+    pi, pj = PM.indptr.astype(np.int32), PM.indices.astype(np.int32)
+    p2 = np.zeros(n, dtype=np.int32)
+    if glue.SpkOrderingRCM(n, pi.ctypes.data, pj.ctypes.data, p2.ctypes.data):
+        raise SystemExit("RCM failed")
+    rp, cp = synthetic.compose_wbm_then_symmetric(R, p2)
+    t_ord = time.perf_counter() - t0
+    S = sp.Spike(mem=sp.MEM_HOST)
+    t0 = time.perf_counter()
+    k, f = S.set_band_csr(ia, ja, a, 50, 0.95, rowperm=rp, colperm=cp)
+    t_pack = time.perf_counter() - t0
+    S.set_operator_csr(ia, ja, a, rowperm=rp, colperm=cp)
+    S.factor()
+    b = np.ascontiguousarray((A @ np.ones(n))[rp])
+    t0 = time.perf_counter()
+    x, its, rn, conv = S.krylov(b, method=sp.BCGS, rtol=1e-5, maxit=500)
+    t_kry = time.perf_counter() - t0
+    info = S.view()
+    xu = np.empty(n); xu[cp] = x
+    S.close()
+    return {"workload": "synthetic sparse nonsymmetric N=2M nnz~22M, WBM (matching known by construction) + RCM stand-in for MC73, PCBANDED(50,0.95), BiCGStab rtol 1e-5",
+            "k": k, "frac": f, "iterations": its, "converged": bool(conv), "err_per_entry": float(np.linalg.norm(xu - 1.0) / np.sqrt(n)),
+            "factor_ms": info["factor_ms"], "krylov_ms_host_buffers": t_kry * 1e3, "band_select_and_pack_s": t_pack,
+            "ordering_host_s": t_ord, "generator_s": t_gen, "partitions": info["partitions"]}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
@@ -172,143 +416,56 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    bounds = sp.shard_rows(N_ROWS, world)
-    n_loc = bounds[rank + 1] - bounds[rank]
-    parts = args.partitions if args.partitions > 0 else 296   # 2 CTAs/SM per GPU (the LU kernel interleaves two partitions per SM)
-    eng = sp.Spike(device=local, partitions=parts, tip_tiles=args.tip_tiles, mem=sp.MEM_DEVICE, rank=rank, nranks=world,
-                   row_offset=bounds[rank], n_global=N_ROWS)
-    eng.keep_original(True)                        # pristine copy: the factorisation is in place
-    eng.set_band_synthetic(n_loc, K_HALF, SEED, DELTA)
-    S = sp.ShardedSpike(eng, rank, world)
-    u = torch.ones(n_loc, dtype=torch.float64, device=dev)
-    b = torch.empty_like(u)
-    x = torch.empty_like(u)
-    S.mult(u, b)                                   # b = A*1 (src/testbed2.c:120-122), halos over NVLink
-    # the band is restored from the kept original between steps, outside the timed brackets
-    L = sp.lib()
-    import ctypes as C
-    L.spk_debug_restore_band.argtypes = [C.c_void_p]
-
-    def restore():
-        # Nothing to restore: with the unfactored band kept, spk_factor reads it (16 GB, far beyond L2) and writes the
-        # factors into the working band, so every step is a complete factorisation of the same matrix with the same
-        # 2B of traffic as an in-place one and no copy in between.  (SPIKE_B200_BENCH_RESTORE=1: old behaviour.)
-        if os.environ.get("SPIKE_B200_BENCH_RESTORE", "0") == "1":
-            rc = L.spk_debug_restore_band(eng._h)
-            if rc:
-                raise SystemExit(f"restore failed ({rc})")
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local, args.clock_interval_ms)
+    sampler = ClockSampler(local, args.clock_interval_ms) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.1)
+    name = args.config
+    r = run_band(name, args, args.steps, args.warmup, parts=args.partitions or None, tip=args.tip_tiles, sampler=sampler,
+                 want_e2e=(not args.no_e2e and CONFIGS[name]["nrhs"] == 1 and CONFIGS[name]["k"] <= 128))
+    cfg = r["cfg"]
+    others = None
+    if rank == 0 and world == 1 and name == "c3" and not args.no_others:
+        others = {}
+        for tag, cn, dl in [("c1", "c1", 1.2), ("c2_delta1.2", "c2", 1.2), ("c2_delta1.0", "c2", 1.0), ("c5_1gpu", "c5", 1.2)]:
+            o = run_band(cn, args, 3, 2, delta=dl, krylov=(cn == "c1"))
+            oc = o["cfg"]
+            others[tag] = {"workload": f"N={oc['n']} K={oc['k']} nrhs={oc['nrhs']} delta={dl}", "partitions": o["info"]["partitions"], "tip_tiles": o["info"]["tip_tiles"],
+                           "ms_per_step": o["ms"], "factor_ms": o["factor_ms"], "solve_ms": o["solve_ms"], "stage_ms": stage_dict(o["stage"]),
+                           "rel_err_vs_exact_u": o["relerr"], "roofline": rooflines(o), "krylov": o["krylov"]}
+        try:
+            others["c4_end_to_end"] = c4_block(args)
+        except Exception as exc:   # noqa: BLE001 -- C4 is a report, not the headline
+            others["c4_end_to_end"] = {"error": str(exc)}
     if rank == 0:
-        sampler.start()
-        time.sleep(0.1)
-    step_ms, lu_ms, stage = [], [], None
-    for it in range(args.warmup + args.steps):
-        restore()
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        S.factor(u)
-        S.solve(b, x)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        local_ms = ms.item()
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        if it >= args.warmup:
-            step_ms.append(ms.item())
-            stage = eng.view()["stage_ms"]
-            lu_ms.append(stage[1])
-    clocks = sampler.stop() if rank == 0 else None
-    per_rank = None
-    if world > 1:   # last step, every rank: its own event time, factor / solve split and stage times (where the ranks wait)
-        iv = eng.view()
-        mine = torch.tensor([local_ms, iv["factor_ms"], iv["solve_ms"]] + list(stage[:6]), dtype=torch.float64, device=dev)
-        allr = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allr, mine)
-        per_rank = [[round(v, 4) for v in t.tolist()] for t in allr]
-    S.check()                                      # a timed-out mailbox spin would have left garbage in x
-    exchange = "NVLink peer mailboxes (kernel stores + flags, csrc/peer.cu)" if getattr(S, "_peer", False) else "NCCL p2p"
-    err = ((x - u).norm() ** 2)
-    cnt = torch.tensor([float(n_loc)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(err); dist.all_reduce(cnt)
-    relerr = (err.sqrt() / cnt.sqrt()).item()
-    info = eng.view()
-
-    # ---- end-to-end through the C ABI with HOST buffers (PCSetUp + PCApply as the glue calls them):
-    #      pinned host band -> device (pack), factor, solve with host b / x.  Single GPU only.
-    e2e = None
-    if world == 1 and not args.no_e2e:
-        import numpy as np
-        if L.spk_debug_restore_band(eng._h):      # the working band holds factors: fetch the unfactored rows
-            raise SystemExit("restore failed")
-        torch.cuda.synchronize()
-        rows = torch.empty((N_ROWS, 2 * K_HALF + 1), dtype=torch.float64).pin_memory()
-        L.spk_get_band_rows(eng._h, rows.data_ptr())
-        bh = b.cpu().pin_memory()
-        xh = torch.empty_like(bh).pin_memory()
-        eng.close()
-        torch.cuda.empty_cache()
-        times = []
-        for it in range(2):
-            t0 = time.perf_counter()
-            h = sp.Spike(device=local, partitions=parts, tip_tiles=args.tip_tiles, mem=sp.MEM_HOST)
-            L.spk_set_band_dense(h._h, N_ROWS, K_HALF, rows.data_ptr(), sp.LAYOUT_ROWS, sp.MEM_HOST)
-            h.n, h.k = N_ROWS, K_HALF
-            h.factor()
-            L.spk_solve(h._h, bh.data_ptr(), xh.data_ptr(), 1)
-            torch.cuda.synchronize()
-            times.append((time.perf_counter() - t0) * 1e3)
-            h.close()
-        e2e_err = float((xh - 1.0).norm() / (N_ROWS ** 0.5))
-        e2e = {"value": min(times), "unit": "ms", "h2d_bytes_per_step": int(rows.numel() * 8 + bh.numel() * 8),
-               "d2h_bytes_per_step": int(xh.numel() * 8), "rel_err": e2e_err,
-               "note": "spk_set_band_dense(host rows band, pinned) + spk_factor + spk_solve(host b -> host x); PCIe H2D of the 16 GB band dominates"}
-
-    if rank == 0:
-        ms = sum(step_ms) / len(step_ms)
-        lu = sum(lu_ms) / len(lu_ms)
-        peak, which = measured_peak()
-        band_alg = 8.0 * N_ROWS * (2 * K_HALF + 1)
-        lu_bytes = 2.0 * band_alg / world          # LU kernel: read + write every band entry of this rank's rows once
-        achieved = lu_bytes / (lu * 1e-3) / 1e9
+        info = r["info"]
         line = {
-            "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "synthetic diagonally dominant band N=10M K=100 fp64, in-place SPIKE factor + solve of b=A*1",
-                       "seed": SEED, "delta": DELTA, "partitions_per_gpu": info["partitions"], "tip_tiles": info["tip_tiles"],
-                       "parallelism": f"row-block x{world}, spike-tip exchange over {exchange}" if world > 1 else "row-block x1",
-                       "l2": "inputs (16 GB band) exceed the 126 MB L2; every step factors the kept unfactored band again (out of place: read original, write factors)"},
-            "rel_err_vs_exact_u": relerr,
-            "step_ms_all": [round(v, 4) for v in step_ms],
-            "stage_ms": {"tip_windows": stage[0], "band_lu": stage[1], "spike_tips": stage[2], "sweeps": stage[3],
-                         "reduced": stage[4], "corrections": stage[5]},
-            "roofline": {"bound": "hbm", "kernel": "k_band_lu", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": which, "traffic": traffic_from_profiles() if world == 1 else None,
-                         "algorithmic_bytes_per_launch": lu_bytes,
-                         "whole_step_frac": (2 * band_alg + band_alg + 32.0 * N_ROWS) / world / (ms * 1e-3) / 1e9 / peak,
-                         "fp64_tflops": N_ROWS * (2.0 * K_HALF * K_HALF + K_HALF) / world / (lu * 1e-3) / 1e12},
-            "gpu_launches": info["kernel_launches"],
+            "metric": cfg["metric"], "value": r["ms"], "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic diagonally dominant band N={cfg['n']} K={cfg['k']} fp64, SPIKE factor (out of place from the kept original)"
+                                   f" + solve of b=A*u, {cfg['nrhs']} right-hand side(s)" if cfg["k"] <= 128 else
+                                   f"synthetic diagonally dominant band N={cfg['n']} K={cfg['k']} fp64, wide-band SPIKE factor (in place, band regenerated between steps)"
+                                   f" + solve of {cfg['nrhs']} right-hand sides",
+                       "seed": SEED, "delta": r["delta"], "partitions_per_gpu": info["partitions"], "tip_tiles": info["tip_tiles"],
+                       "parallelism": f"row-block x{world}, spike-tip exchange over {r['exchange']}" if world > 1 else "row-block x1",
+                       "l2": "inputs (band >> 126 MB L2) are re-read from HBM every step; nothing is cached between steps"},
+            "rel_err_vs_exact_u": r["relerr"], "step_ms_all": r["step_ms_all"], "factor_ms": r["factor_ms"], "solve_ms": r["solve_ms"],
+            "stage_ms": stage_dict(r["stage"]), "roofline": rooflines(r), "gpu_launches": info["kernel_launches"],
             "per_rank_ms": {"columns": ["step", "factor", "solve", "tip_windows", "band_lu", "spike_tips", "sweeps", "reduced", "corrections"],
-                            "rows": per_rank} if per_rank else None,
-            "clocks": clocks,
-            "e2e": e2e if e2e is not None else {"value": None, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                                                "note": "host-buffer path measured at N=1 only"},
+                            "rows": r["per_rank"]} if r["per_rank"] else None,
+            "clocks": r["clocks"],
+            "e2e": r["e2e"] if r["e2e"] is not None else {"value": None, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                         "note": "host-buffer path not measured for this configuration"},
         }
+        if others is not None:
+            line["other_configs"] = others
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_sample()
+            line["cpu_baseline"] = cpu_baseline_block(cfg, cpu_port_run(cfg, min(cfg["n"], 1_000_000 if cfg["k"] <= 128 else 100_000), 1, 0))
         print(json.dumps(line), flush=True)
+    bad = not (r["relerr"] < ERR_BAR) or (r["e2e"] is not None and not (r["e2e"]["rel_err"] < ERR_BAR))
     if world > 1:
         dist.destroy_process_group()
+    if bad:
+        raise SystemExit(f"solution error above {ERR_BAR}: rel_err {r['relerr']}, e2e {r['e2e']}")
 
 
 def main():
@@ -317,10 +474,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--partitions", type=int, default=0)
-    ap.add_argument("--tip-tiles", type=int, default=78)   # 6 bandwidths: 1e-13 (profiles/r01_truncation_window.md)
+    ap.add_argument("--tip-tiles", type=int, default=None)   # default per config (C3: 78 tiles = 6 bandwidths, 1e-13)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true")
+    ap.add_argument("--reference-sample", action="store_true", help="reference arm: time a 1/10 sample even when the full band fits host memory")
     ap.add_argument("--clock-interval-ms", type=int, default=20)   # nvidia-smi sampling period during the timed region
     args = ap.parse_args()
     if args.impl == "reference":

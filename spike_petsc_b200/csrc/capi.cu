@@ -844,6 +844,17 @@ extern "C" int spk_debug_set_lu_trace(spk_ctx* c, void* dev_buf) { if (!c) retur
 // restored between timed steps, and a reset of the "factored" flag after such a restore.
 extern "C" void* spk_debug_band_ptr(spk_ctx* c) { return c ? (void*)c->band : nullptr; }
 extern "C" int spk_debug_reset_factored(spk_ctx* c) { if (!c) return SPK_ERR_ARG; c->factored = 0; c->launches = 0; return SPK_OK; }
+// bench.py hook: regenerate the synthetic band in place (same layout / partitions / mailboxes), so an in-place
+// factorisation can be timed again without re-planning the context
+extern "C" int spk_debug_regen_synthetic(spk_ctx* c, uint64_t seed, double delta) {
+  if (!c || !c->have_band) return SPK_ERR_STATE;
+  SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  int rc = spk_launch_generate(c, seed, delta);
+  if (rc) return rc;
+  if (c->orig) SPK_CUDA(c, cudaMemcpyAsync(c->orig, c->band, sizeof(double) * (size_t)c->L.elems(), cudaMemcpyDeviceToDevice, c->stream));
+  c->factored = 0; c->launches = 0;
+  return SPK_OK;
+}
 // restore the unfactored band from the copy kept by spk_keep_original(ctx,1) (device-to-device, async)
 extern "C" int spk_debug_restore_band(spk_ctx* c) {
   if (!c || !c->orig) return SPK_ERR_STATE;

@@ -140,17 +140,19 @@ int spk_launch_vec_scale(spk_ctx* c, double* out, const double* in, const double
 }
 
 // tile-major band -> ROWS layout (test/debug hook)
-__global__ void k_unpack_rows(const double* __restrict__ band, double* __restrict__ dst, BandLayout L) {
+// (columns [jlo, jhi) exist in the GLOBAL matrix: a shard's rows keep their coupling entries, like the pack kernels)
+__global__ void k_unpack_rows(const double* __restrict__ band, double* __restrict__ dst, BandLayout L, int64_t jlo, int64_t jhi) {
   const int64_t bw = 2 * (int64_t)L.k + 1;
   const int64_t total = L.n * bw;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = e / bw, dk = e - i * bw;
     const int64_t j = i + dk - L.k;
-    dst[e] = (j < 0 || j >= L.n) ? 0.0 : band[L.elem_off(i, j)];
+    dst[e] = (j < jlo || j >= jhi) ? 0.0 : band[L.elem_off(i, j)];
   }
 }
 int spk_launch_unpack_rows(spk_ctx* c, const double* band, double* rows_dev) {
-  k_unpack_rows<<<c->sm_count * 8, 256, 0, c->stream>>>(band, rows_dev, c->L);
+  const int64_t ng = c->opts.n_global > 0 ? c->opts.n_global : c->L.n;
+  k_unpack_rows<<<c->sm_count * 8, 256, 0, c->stream>>>(band, rows_dev, c->L, -c->opts.row_offset, ng - c->opts.row_offset);
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }
