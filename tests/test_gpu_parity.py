@@ -481,3 +481,95 @@ def test_full_size_manufactured_solution(spk, n, k):
     assert torch.equal(y, 2.0 * x)                                # scaling by 2 is exact in fp64
     assert S.view()["boosted_pivots"] == 0
     S.close()
+
+
+# ------------------------------------------------------------------ the configurations bench.py times, as it times them
+@pytest.mark.parametrize("delta", [1.2, 1.0])
+def test_bench_config_c2_against_oracle(spk, oracle, delta):
+    """BASELINE config 2 exactly as bench.py runs it (N = 1M, K = 50, 592 partitions, 48-tile truncation window):
+    the whole solution against the oracle's exact no-pivot band LU solve (it fits: 0.8 GB), delta = 1.2 and 1.0."""
+    import sys
+    sys.path.insert(0, ".")
+    from bench import CONFIGS
+    cfg = CONFIGS["c2"]
+    n, k = cfg["n"], cfg["k"]
+    a = oracle.gen_band(n, k, 20140601, delta)
+    u = oracle.gen_vec(n, 5)
+    b = oracle.band_mult(a, u)
+    lu, nb = oracle.band_lu(a)
+    xref = oracle.band_solve(lu, b)
+    S = spk.Spike(partitions=cfg["parts"], tip_tiles=cfg["tip"])
+    S.set_band_synthetic(n, k, seed=20140601, delta=delta)       # the band bench.py generates (bit-identical to `a`)
+    S.factor()
+    x = S.solve(b)
+    info = S.view()
+    assert info["partitions"] == cfg["parts"] and info["tip_tiles"] == cfg["tip"] and info["boosted_pivots"] == nb == 0
+    assert relerr(x, xref) < RTOL
+    S.close()
+
+
+@pytest.mark.parametrize("delta", [1.2, 1.0])
+def test_bench_config_c3_window_and_partitions(spk, oracle, delta):
+    """BASELINE config 3 exactly as bench.py runs it (N = 10M, K = 100, 296 partitions, 78-tile window): random
+    manufactured solution, error and residual through the kept original; and the oracle on a 1M-row system with the
+    same partition length and window (30 partitions of ~33k rows), where the exact band solve still fits."""
+    import sys
+    import torch
+    sys.path.insert(0, ".")
+    from bench import CONFIGS
+    cfg = CONFIGS["c3"]
+    n, k = cfg["n"], cfg["k"]
+    S = spk.Spike(partitions=cfg["parts"], tip_tiles=cfg["tip"], mem=spk.MEM_DEVICE)
+    S.keep_original(True)
+    S.set_band_synthetic(n, k, seed=20140601, delta=delta)
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    u = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    b = torch.empty_like(u); x = torch.empty_like(u); y = torch.empty_like(u)
+    S.mult(u.data_ptr(), b.data_ptr())
+    S.factor()
+    S.solve(b.data_ptr(), x.data_ptr())
+    S.mult(x.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    info = S.view()
+    assert info["partitions"] == cfg["parts"] and info["tip_tiles"] == cfg["tip"] and info["boosted_pivots"] == 0
+    assert ((x - u).norm() / u.norm()).item() < RTOL
+    assert ((y - b).norm() / b.norm()).item() < 1e-11
+    S.close(); del u, b, x, y
+    n1 = 1_000_000
+    a = oracle.gen_band(n1, k, 20140601, delta)
+    u1 = oracle.gen_vec(n1, 5)
+    b1 = oracle.band_mult(a, u1)
+    lu, _ = oracle.band_lu(a)
+    S = spk.Spike(partitions=30, tip_tiles=cfg["tip"])
+    S.set_band_synthetic(n1, k, seed=20140601, delta=delta)
+    S.factor()
+    assert relerr(S.solve(b1), oracle.band_solve(lu, b1)) < RTOL
+    S.close()
+
+
+@pytest.mark.parametrize("n,k,P,nrhs", [(60_000, 100, 8, 1), (30_000, 37, 6, 9), (16_384, 256, 3, 4), (12_288, 512, 2, 1)])
+def test_repeated_runs_are_bit_identical(spk, oracle, n, k, P, nrhs):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer_closed.log), so the barrier-free dataflow of
+    the LU kernels (mbarrier packages, release/acquire flags between CTAs) is checked for races the indirect way: five
+    factor + solve runs of the same input must give bit-identical factors and solutions -- a missed dependency shows up
+    as run-to-run differences -- and the result must agree with the oracle."""
+    a = oracle.gen_band(n, k)
+    U = np.stack([oracle.gen_vec(n, 20 + c) for c in range(nrhs)])
+    Bm = np.stack([oracle.band_mult(a, u) for u in U])
+    first = None
+    for rep in range(5):
+        S = spk.Spike(partitions=P, tip_tiles=0)
+        S.set_band_dense(a, k)
+        S.factor()
+        X = S.solve(Bm if nrhs > 1 else Bm[0], nrhs=nrhs)
+        F = S.get_band_rows()                                   # the factored band
+        S.close()
+        if first is None:
+            first = (F, X)
+        else:
+            np.testing.assert_array_equal(F, first[0])
+            np.testing.assert_array_equal(X, first[1])
+    lu, _ = oracle.band_lu(a)
+    X = first[1] if nrhs > 1 else first[1][None, :]
+    for c in range(nrhs):
+        assert relerr(X[c], oracle.band_solve(lu, Bm[c])) < RTOL
