@@ -32,7 +32,9 @@ CONFIGS = {
     "c3": dict(n=10_000_000, k=100, nrhs=1, parts=296, tip=78, metric="spike_factor_plus_solve_ms_N10M_K100_fp64"),
     "c2": dict(n=1_000_000, k=50, nrhs=1, parts=592, tip=48, metric="spike_factor_plus_solve_ms_N1M_K50_fp64"),
     "c1": dict(n=100_000, k=10, nrhs=1, parts=296, tip=24, metric="spike_factor_plus_solve_ms_N100k_K10_fp64"),
-    "c5": dict(n=1_000_000, k=512, nrhs=32, parts=64, tip=320, metric="spike_factor_plus_solve_ms_N1M_K512_32rhs_fp64"),
+    # C5: 32 partitions on one GPU (fewer: the sweeps starve; more: tips and windows grow), 16 per GPU when sharded;
+    # 288-tile window = 4.5 bandwidths: 8e-12 (256 tiles: 6e-11, too close to the 1e-10 bar)
+    "c5": dict(n=1_000_000, k=512, nrhs=32, parts=32, tip=288, metric="spike_factor_plus_solve_ms_N1M_K512_32rhs_fp64"),
 }
 ERR_BAR = 1e-10
 
@@ -205,9 +207,10 @@ def run_band(cfgname, args, steps, warmup, delta=DELTA, parts=None, tip=None, sa
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
     wide = k > 128
+    explicit_parts = bool(parts)
     parts = parts if parts else cfg["parts"]
-    if wide and world > 1:
-        parts = max(parts // world, 2)
+    if wide and world > 1 and not explicit_parts:
+        parts = 16
     tip = cfg["tip"] if tip is None else tip
     bounds = sp.shard_rows(n, world, k)
     n_loc = bounds[rank + 1] - bounds[rank]

@@ -128,6 +128,13 @@ int spk_krylov(spk_ctx *ctx, int method, int restart, double rtol, int maxit, co
  * live in this rank's halo tiles); entries towards a missing neighbour are ignored. */
 int spk_set_scaling(spk_ctx *ctx, const double *rscale, const double *cscale);
 
+/* Self-check of the factorisation (no reference counterpart: the reference's inner PC is an exact LU): with the
+ * unfactored band kept (spk_keep_original), solves B x = B v for a fixed probe v and returns ||x - v|| / ||v||.  The
+ * truncated SPIKE apply equals the exact band solve only where the spikes decay inside the truncation window
+ * (diagonally dominant bands); elsewhere this is its error as an approximation of B^-1.  opts.partitions = 1 is the
+ * exact mode (one partition, no truncation). */
+int spk_check(spk_ctx *ctx, double *rel_err);
+
 /* PCView_Banded (src/matbanded.c:196-211) */
 int spk_view(spk_ctx *ctx, spk_info *info);
 

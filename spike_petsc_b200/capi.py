@@ -76,6 +76,7 @@ def lib():
         L.spk_set_operator_csr.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
         L.spk_krylov.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, ip, dp, ip]
         L.spk_view.argtypes = [vp, C.POINTER(Info)]
+        L.spk_check.argtypes = [vp, dp]
         L.spk_tip_size.argtypes = [vp, ip]
         L.spk_get_boundary.argtypes = [vp, C.c_int, vp]
         L.spk_set_boundary.argtypes = [vp, C.c_int, vp]
@@ -279,6 +280,12 @@ class Spike:
 
     def peer_check(self):
         self._ck(lib().spk_peer_check(self._h), "spk_peer_check")
+
+    def check(self) -> float:
+        """||x - v|| / ||v|| of one probe solve through the kept unfactored band (spk_check)."""
+        e = C.c_double(0.0)
+        self._ck(lib().spk_check(self._h, C.byref(e)), "spk_check")
+        return e.value
 
     def view(self) -> dict:
         info = Info()

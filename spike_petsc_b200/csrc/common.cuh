@@ -92,7 +92,8 @@ struct spk_ctx {
   double* rband;             // reduced matrices I - W V in band format (P partitions of 8*kb tile rows), factored for R
   double* VbT;               // V^(b) transposed (right operand of the reduced-matrix product)
   int64_t *d_wpstart, *d_rpstart;   // partition boundaries (tile rows) inside wband / rband
-  void* d_wjobs; int wjobs_cap;     // device array of sweep jobs
+  void* d_wjobs; int wjobs_cap;     // device arrays of sweep jobs, one per call site
+  void* h_wjobs;                    // host copies of what those arrays hold (upload only on change)
   double* redw; int redw_cols;      // scratch of the wide reduced solve: g_b, g_t, t, x_t, x_b (kp x columns per interface)
   int bnd_cols;                     // right-hand-side columns the boundary exchange buffers (remoteGtop, remoteXbot, xbBoundary) hold
   double *rscale, *cscale;   // optional equilibration (spk_set_scaling): the factored band is diag(r) A diag(c)

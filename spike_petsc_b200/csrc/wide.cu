@@ -16,8 +16,10 @@
 #include "wide.cuh"
 #include <algorithm>
 #include <vector>
+#include <cstring>
 
 #define WIDE_CUDA(ctx, call) SPK_CUDA(ctx, call)
+enum { WJ_WT = 0, WJ_VB, WJ_RED, WJ_MAIN, WJ_CORR, WJ_SITES };   // call sites of the sweep kernel (run_jobs)
 
 int spk_wide_alloc(spk_ctx* c) {
   const BandLayout& L = c->L;
@@ -39,7 +41,8 @@ int spk_wide_alloc(spk_ctx* c) {
   WIDE_CUDA(c, cudaMemcpy(c->d_wpstart, wp.data(), sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice));
   WIDE_CUDA(c, cudaMemcpy(c->d_rpstart, rp.data(), sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice));
   c->wjobs_cap = 2 * P + 8;
-  WIDE_CUDA(c, cudaMalloc(&c->d_wjobs, sizeof(WideSweepJob) * (size_t)c->wjobs_cap));
+  WIDE_CUDA(c, cudaMalloc(&c->d_wjobs, sizeof(WideSweepJob) * (size_t)c->wjobs_cap * WJ_SITES));
+  c->h_wjobs = new std::vector<WideSweepJob>[WJ_SITES];
   return SPK_OK;
 }
 
@@ -47,6 +50,7 @@ void spk_wide_free(spk_ctx* c) {
   auto F = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
   F(c->wide_flags); F(c->wide_abort); F(c->wband); F(c->rband); F(c->VbT); F(c->d_wpstart); F(c->d_rpstart);
   if (c->d_wjobs) { cudaFree(c->d_wjobs); c->d_wjobs = nullptr; }
+  if (c->h_wjobs) { delete[] (std::vector<WideSweepJob>*)c->h_wjobs; c->h_wjobs = nullptr; }
   F(c->redw); c->redw_cols = 0;
   c->wide = 0; c->kb = 0;
 }
@@ -61,15 +65,21 @@ int spk_wide_check(spk_ctx* c) {
   return SPK_OK;
 }
 
-static int run_jobs(spk_ctx* c, const std::vector<WideSweepJob>& jobs, int max_cols) {
+// Sweep jobs of one call site (W tips, V tips, reduced inverses, partition sweeps, corrections).  The job list of a
+// site is the same from call to call as long as the caller's pointers are (repeated factorisations, Krylov
+// iterations): it is uploaded only when it differs from the copy already on the device, so the steady state has no
+// host-to-device copy (and none of its implicit synchronisation) in front of the sweep kernels.
+static int run_jobs(spk_ctx* c, const std::vector<WideSweepJob>& jobs, int max_cols, int site) {
   if (jobs.empty()) return SPK_OK;
-  for (size_t j0 = 0; j0 < jobs.size(); j0 += (size_t)c->wjobs_cap) {
-    const size_t nj = std::min(jobs.size() - j0, (size_t)c->wjobs_cap);
-    SPK_CUDA(c, cudaMemcpyAsync(c->d_wjobs, jobs.data() + j0, sizeof(WideSweepJob) * nj, cudaMemcpyHostToDevice, c->stream));
-    const int rc = spk_wide_sweep(c, (const WideSweepJob*)c->d_wjobs, (int)nj, max_cols);
-    if (rc) return rc;
+  if ((int)jobs.size() > c->wjobs_cap) { SPK_SET_ERR(c, "wide sweep: %zu jobs exceed the job array (%d)", jobs.size(), c->wjobs_cap); return SPK_ERR_STATE; }
+  WideSweepJob* dev = (WideSweepJob*)c->d_wjobs + (size_t)site * c->wjobs_cap;
+  std::vector<WideSweepJob>* all = (std::vector<WideSweepJob>*)c->h_wjobs;
+  std::vector<WideSweepJob>& mine = all[site];
+  if (mine.size() != jobs.size() || memcmp(mine.data(), jobs.data(), sizeof(WideSweepJob) * jobs.size()) != 0) {
+    SPK_CUDA(c, cudaMemcpyAsync(dev, jobs.data(), sizeof(WideSweepJob) * jobs.size(), cudaMemcpyHostToDevice, c->stream));
+    mine = jobs;
   }
-  return SPK_OK;
+  return spk_wide_sweep(c, dev, (int)jobs.size(), max_cols);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -236,7 +246,7 @@ static int wide_wt(spk_ctx* c, int first, int cnt) {   // W^(t) of partitions fi
     j.row0 = j.sb_hi * 64 - kp; j.nrow_valid = kp; j.ncols = kp;
     jobs.push_back(j);
   }
-  return run_jobs(c, jobs, kp);
+  return run_jobs(c, jobs, kp, WJ_WT);
 }
 
 static int wide_vb(spk_ctx* c, int cnt) {   // V^(b) of partitions 0 .. cnt-1 (+ their transposes)
@@ -253,7 +263,7 @@ static int wide_vb(spk_ctx* c, int cnt) {   // V^(b) of partitions 0 .. cnt-1 (+
     j.row0 = j.sb_hi * 64 - kp; j.nrow_valid = kp; j.ncols = kp;
     jobs.push_back(j);
   }
-  int rc = run_jobs(c, jobs, kp);
+  int rc = run_jobs(c, jobs, kp, WJ_VB);
   if (rc) return rc;
   k_wide_transpose<<<dim3(kp / 32, kp / 32, cnt), dim3(32, 8), 0, c->stream>>>(c->Vb, c->VbT, kp, 0);
   SPK_KERNEL_CHECK(c);
@@ -276,7 +286,7 @@ static int wide_reduced(spk_ctx* c, int first, int cnt, int remote_iface) {   //
     j.row0 = (long long)i * kp; j.nrow_valid = kp; j.ncols = kp;
     jobs.push_back(j);
   }
-  return run_jobs(c, jobs, kp);
+  return run_jobs(c, jobs, kp, WJ_RED);
 }
 
 // same contract as spk_launch_tips (tips.cu)
@@ -310,7 +320,7 @@ int spk_wide_main_sweep(spk_ctx* c, const double* b, double* x, int nrhs, int64_
     j.row0 = 0; j.nrow_valid = c->L.n; j.ncols = nrhs;
     jobs.push_back(j);
   }
-  return run_jobs(c, jobs, nrhs);
+  return run_jobs(c, jobs, nrhs, WJ_MAIN);
 }
 
 // x_i -= A_i^-1 [r_top; 0] + A_i^-1 [0; r_bot] over the truncation windows; tips: column r at rtop/rbot + r*tip_stride;
@@ -348,7 +358,7 @@ int spk_wide_corrections(spk_ctx* c, double* x, int nrhs, int64_t ld, const doub
       jobs.push_back(j);
     }
   }
-  int rc = run_jobs(c, jobs, nrhs);
+  int rc = run_jobs(c, jobs, nrhs, WJ_CORR);
   if (rc) return rc;
   k_wide_corr_apply<<<dim3(2 * c->P, nrhs), 256, 0, c->stream>>>(a);
   SPK_KERNEL_CHECK(c);

@@ -58,6 +58,10 @@ typedef struct {
   PetscInt  partitions, tip_tiles;
   const PetscInt *rowperm, *colperm;   /* borrowed from KSPREORDER: B = band(pmat(rowperm, colperm)) */
   PetscInt  nsetup;                    /* factorisations performed (diagnostics / tests) */
+  PetscInt  verify;                    /* -spike_verify: probe solve after the factorisation (default 1) */
+  PetscReal verify_tol;                /* -spike_verify_tol: above it the PC falls back to the exact mode (1 partition) */
+  PetscReal apply_err;                 /* ||x - v|| / ||v|| of the probe solve, -1 = not measured */
+  PetscInt  exact_fallback;            /* the fallback was taken */
 } PC_Banded;
 
 static PetscErrorCode PCReset_Banded(PC pc) {          /* :120-129 */
@@ -78,6 +82,8 @@ static PetscErrorCode PCSetFromOptions_Banded(PC pc) { /* :149-161 */
   char inner[192]; snprintf(inner, sizeof inner, "%sbanded_", SPK_PREFIX(pc));
   PetscOptionsGetInt(inner, "-spike_partitions", &b->partitions, NULL);
   PetscOptionsGetInt(inner, "-spike_tip_tiles", &b->tip_tiles, NULL);
+  PetscOptionsGetInt(inner, "-spike_verify", &b->verify, NULL);
+  PetscOptionsGetReal(inner, "-spike_verify_tol", &b->verify_tol, NULL);
   return 0;
 }
 /* First call (setupcalled == 0, :171): choose k, extract the band, factor.  A later call means PETSc saw the operator
@@ -88,20 +94,36 @@ static PetscErrorCode PCSetUp_Banded(PC pc) {          /* :165-180 */
   PetscInt n; const PetscInt *ai, *aj; const PetscScalar *aa;
   PetscErrorCode ierr;
   if (!pc->pmat) SPK_ERR(PETSC_ERR_ARG_WRONGSTATE, "PCBANDED: no preconditioner matrix set");
-  if (b->ctx) spk_destroy(&b->ctx);
-  spk_opts o; spk_default_opts(&o);
-  o.partitions = b->partitions; o.tip_tiles = b->tip_tiles; o.mem = SPK_MEM_HOST;
-  if (spk_create(&b->ctx, &o)) SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(NULL));
-  b->k = b->kmax; b->f = b->frac;                      /* :172-173 */
-  int k = b->k; double f = b->f;
-  /* MatCreateSubMatrixBanded(pc->pmat, &b->k, &b->f, &b->B) (:174), on the (permuted) operator */
-  ierr = SpkMatGetCSR(pc->pmat, &n, &ai, &aj, &aa);CHKERRQ(ierr);
-  if (spk_set_band_csr(b->ctx, n, ai, aj, aa, b->rowperm, b->colperm, &k, &f))
-    SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
-  ierr = SpkMatRestoreCSR(pc->pmat, &n, &ai, &aj, &aa);CHKERRQ(ierr);
-  b->k = k; b->f = f;
-  /* PCSetUp(b->pc) (:178): the SPIKE factorisation */
-  if (spk_factor(b->ctx)) SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
+  /* The reference's inner PC is an exact LU of B (:178).  The truncated SPIKE is exact only for bands whose spikes decay
+   * inside the truncation window (diagonally dominant ones), and a reordered band need not be one: after factoring,
+   * one probe solve through the kept unfactored band measures ||B^-1 b - x||; above -spike_verify_tol the PC refactors
+   * in the exact mode (-spike_partitions 1: one partition, nothing truncated) and says so in PCView. */
+  b->apply_err = -1.0; b->exact_fallback = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (b->ctx) spk_destroy(&b->ctx);
+    spk_opts o; spk_default_opts(&o);
+    o.partitions = attempt ? 1 : b->partitions; o.tip_tiles = attempt ? -1 : b->tip_tiles; o.mem = SPK_MEM_HOST;
+    if (spk_create(&b->ctx, &o)) SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(NULL));
+    if (b->verify) spk_keep_original(b->ctx, 1);
+    b->k = b->kmax; b->f = b->frac;                      /* :172-173 */
+    int k = b->k; double f = b->f;
+    /* MatCreateSubMatrixBanded(pc->pmat, &b->k, &b->f, &b->B) (:174), on the (permuted) operator */
+    ierr = SpkMatGetCSR(pc->pmat, &n, &ai, &aj, &aa);CHKERRQ(ierr);
+    if (spk_set_band_csr(b->ctx, n, ai, aj, aa, b->rowperm, b->colperm, &k, &f))
+      SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
+    ierr = SpkMatRestoreCSR(pc->pmat, &n, &ai, &aj, &aa);CHKERRQ(ierr);
+    b->k = k; b->f = f;
+    /* PCSetUp(b->pc) (:178): the SPIKE factorisation */
+    if (spk_factor(b->ctx)) SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
+    if (!b->verify) break;
+    double e = 0.0;
+    if (spk_check(b->ctx, &e)) SPK_ERR(PETSC_ERR_LIB, "PCBANDED: %s", spk_last_error(b->ctx));
+    b->apply_err = e;
+    if (attempt == 1) { b->exact_fallback = 1; break; }
+    if (e <= b->verify_tol) break;
+    spk_info info; memset(&info, 0, sizeof info); spk_view(b->ctx, &info);
+    if (info.partitions <= 1) break;                     /* already exact: the error is the LU's own */
+  }
   b->nsetup++;
   return 0;
 }
@@ -120,8 +142,11 @@ static PetscErrorCode PCView_Banded(PC pc, char *buf, size_t len) {  /* :196-211
   PC_Banded *b = (PC_Banded *)pc->data;
   spk_info info; memset(&info, 0, sizeof info);
   if (b->ctx) spk_view(b->ctx, &info);
-  snprintf(buf, len, "  Banded: k = %d (%d max), frac = %g (%g max)\n    SPIKE (B200): partitions = %d, tip window = %d tiles, boosted pivots = %lld\n",
+  int w = snprintf(buf, len, "  Banded: k = %d (%d max), frac = %g (%g max)\n    SPIKE (B200): partitions = %d, tip window = %d tiles, boosted pivots = %lld\n",
            b->k, b->kmax, b->f, b->frac, info.partitions, info.tip_tiles, (long long)info.boosted_pivots);
+  if (w > 0 && (size_t)w < len && b->apply_err >= 0.0)
+    snprintf(buf + w, len - (size_t)w, "    probe solve vs the exact band solve: relative error %.3e%s\n", b->apply_err,
+             b->exact_fallback ? " (truncated SPIKE rejected: refactored with 1 partition, the exact mode)" : "");
   return 0;
 }
 
@@ -130,6 +155,7 @@ PetscErrorCode PCCreate_Banded(PC pc) {                /* :251-283 */
   pc->data = (void *)b;
   b->kmax = 50;
   b->frac = 0.95;
+  b->verify = 1; b->verify_tol = 1e-6; b->apply_err = -1.0;
   pc->ops->apply          = PCApply_Banded;
   pc->ops->applytranspose = NULL;
   pc->ops->setup          = PCSetUp_Banded;
@@ -157,4 +183,6 @@ PetscErrorCode PCBandedGetInfo(PC pc, PetscInt *k, PetscReal *f, PetscInt *parti
 PetscErrorCode PCBandedSetPermutation_Private(PC pc, const PetscInt *rowperm, const PetscInt *colperm) {
   PC_Banded *b = (PC_Banded *)pc->data; b->rowperm = rowperm; b->colperm = colperm; return 0; }
 spk_ctx *PCBandedGetContext_Private(PC pc) { return ((PC_Banded *)pc->data)->ctx; }
+PetscErrorCode PCBandedGetApplyError(PC pc, PetscReal *err, PetscInt *exact_fallback) {
+  PC_Banded *b = (PC_Banded *)pc->data; if (err) *err = b->apply_err; if (exact_fallback) *exact_fallback = b->exact_fallback; return 0; }
 PetscErrorCode PCBandedGetSetupCount(PC pc, PetscInt *nsetup) { *nsetup = ((PC_Banded *)pc->data)->nsetup; return 0; }

@@ -22,6 +22,9 @@ PetscErrorCode PCBandedSetMaxHalfBandwith(PC pc, PetscInt kmax);   /* (sic) refe
 PetscErrorCode PCBandedSetNormFraction(PC pc, PetscReal frac);
 PetscErrorCode PCBandedGetInfo(PC pc, PetscInt *k, PetscReal *f, PetscInt *partitions, long long *boosted);
 PetscErrorCode PCBandedGetSetupCount(PC pc, PetscInt *nsetup);
+/* error of a probe solve against the exact band solve measured at setup (-spike_verify 1, the default), and whether
+ * the PC fell back to the exact single-partition mode because it exceeded -spike_verify_tol (default 1e-6) */
+PetscErrorCode PCBandedGetApplyError(PC pc, PetscReal *err, PetscInt *exact_fallback);
 PetscErrorCode KSPCreate_Reorder(KSP ksp);
 PetscErrorCode KSPReorderGetPC(KSP ksp, PC *pc);
 /* MATBANDED Mat type (matbanded_type.c): MatRegister("banded", MatCreate_Banded); ops mult / lufactor / solve / matsolve /

@@ -573,3 +573,43 @@ def test_repeated_runs_are_bit_identical(spk, oracle, n, k, P, nrhs):
     X = first[1] if nrhs > 1 else first[1][None, :]
     for c in range(nrhs):
         assert relerr(X[c], oracle.band_solve(lu, Bm[c])) < RTOL
+
+
+# ------------------------------------------------------------------ bands whose spikes do not decay
+def _slow_decay_band(n):
+    """shifted second difference tridiag(-1, 2.0001, -1): well conditioned (4e4), the no-pivot LU is stable, but the
+    spikes of a partitioned solve decay like 0.99^rows -- truncation inside any reasonable window is not admissible."""
+    a = np.zeros((n, 3))
+    a[:, 0], a[:, 1], a[:, 2] = -1.0, 2.0001, -1.0
+    a[0, 0] = 0; a[-1, 2] = 0
+    return a
+
+
+def test_self_check_flags_truncation_on_non_dominant_band(spk, oracle):
+    """spk_check: on a non-dominant band several partitions give an O(1) apply error (and say so); one partition --
+    the exact mode -- reproduces the reference CPU path (exact band LU)."""
+    n = 40_000
+    a = _slow_decay_band(n)
+    lu, _ = oracle.band_lu(a)
+    b = oracle.band_mult(a, oracle.gen_vec(n, 3))
+    xref = oracle.band_solve(lu, b)
+    S = spk.Spike(partitions=8)
+    S.keep_original(True)
+    S.set_band_dense(a, 1)
+    S.factor()
+    assert S.check() > 1e-3                      # truncated SPIKE is not an exact solve here ...
+    S.close()
+    S = spk.Spike(partitions=1)
+    S.keep_original(True)
+    S.set_band_dense(a, 1)
+    S.factor()
+    assert S.check() < 1e-10                     # ... one partition is
+    assert relerr(S.solve(b), xref) < RTOL
+    S.close()
+    # and on a dominant band the check confirms the truncated solve
+    S = spk.Spike(partitions=8)
+    S.keep_original(True)
+    S.set_band_synthetic(n, 20)
+    S.factor()
+    assert S.check() < 1e-12
+    S.close()

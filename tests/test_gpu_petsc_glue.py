@@ -303,3 +303,36 @@ def test_kspsolve_sets_up_once_per_operator(glue):
     L.PCBandedGetSetupCount(inner_pc, C.byref(cnt))
     assert cnt.value == 2
     L.KSPDestroy(C.byref(ksp))
+
+
+def test_pcbanded_falls_back_to_exact_mode_on_non_dominant_band(glue, oracle):
+    """The reference's inner PC is an exact LU of B (src/matbanded.c:178).  On a band whose spikes do not decay the
+    truncated SPIKE would be O(1) away from B^-1; PCSetUp measures that with a probe solve and refactors in the exact
+    single-partition mode, so PCApply still equals the exact band solve; PCView reports it."""
+    L = glue
+    L.PCBandedGetApplyError.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    n = 30_000
+    # shifted second difference: condition number 4e4, but its spikes decay like 0.99^rows -- far too slowly for any
+    # truncation window
+    A = sp.diags([-1.0, 2.0001, -1.0], [-1, 0, 1], shape=(n, n), format="csr")
+    A.sort_indices()
+    L.PetscOptionsClear()
+    L.PetscOptionsSetValue(b"-pc_banded_kmax", b"10")
+    L.PetscOptionsSetValue(b"-pc_banded_frac", b"1.0")
+    L.PetscOptionsSetValue(b"-banded_spike_partitions", b"8")
+    m = _mat(L, A)
+    pc = C.c_void_p(); L.PCCreate(C.byref(pc)); L.PCCreate_Banded(pc)
+    L.PCSetFromOptions(pc); L.PCSetOperators(pc, m, m)
+    assert L.PCSetUp(pc) == 0, L.PetscLastErrorMessage()
+    err, fb = C.c_double(), C.c_int()
+    L.PCBandedGetApplyError(pc, C.byref(err), C.byref(fb))
+    assert fb.value == 1 and err.value < 1e-9
+    u = oracle.gen_vec(n, 2); b = np.ascontiguousarray(A @ u); y = np.zeros(n)
+    assert L.PCApply(pc, _vec(L, b), _vec(L, y)) == 0
+    kk = C.c_int(); L.PCBandedGetInfo(pc, C.byref(kk), None, None, None)
+    band = oracle.csr_to_band(A.indptr, A.indices, A.data, kk.value)
+    lu, _ = oracle.band_lu(band)
+    assert np.linalg.norm(y - oracle.band_solve(lu, b)) / np.linalg.norm(y) < 1e-10
+    buf = C.create_string_buffer(1024); L.PCView(pc, buf, 1024)
+    assert "exact mode" in buf.value.decode()
+    L.PCDestroy(C.byref(pc))
