@@ -5,7 +5,7 @@ ARCH    := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v $(NVEXTRA)
 CSRC    := spike_petsc_b200/csrc
 LIBDIR  := spike_petsc_b200/lib
-OBJS    := $(LIBDIR)/layout.o $(LIBDIR)/lu.o $(LIBDIR)/tips.o $(LIBDIR)/solve.o $(LIBDIR)/msweep.o $(LIBDIR)/krylov.o $(LIBDIR)/peer.o $(LIBDIR)/wide_lu.o $(LIBDIR)/wide_sweep.o $(LIBDIR)/wide.o $(LIBDIR)/capi.o
+OBJS    := $(LIBDIR)/layout.o $(LIBDIR)/lu.o $(LIBDIR)/tips.o $(LIBDIR)/solve.o $(LIBDIR)/msweep.o $(LIBDIR)/krylov.o $(LIBDIR)/peer.o $(LIBDIR)/wide_lu.o $(LIBDIR)/wide_sweep.o $(LIBDIR)/wide.o $(LIBDIR)/awbm.o $(LIBDIR)/capi.o
 
 HOST    := spike_petsc_b200/host
 

@@ -128,6 +128,18 @@ int spk_krylov(spk_ctx *ctx, int method, int restart, double rtol, int maxit, co
  * live in this rank's halo tiles); entries towards a missing neighbour are ignored. */
 int spk_set_scaling(spk_ctx *ctx, const double *rscale, const double *cscale);
 
+/* MatGetOrdering_AWBM (src/petsc_mat_awbm.c:42-225) on the GPU: approximate weighted bipartite
+ * matching of a square CSR matrix, bit-identical to the reference's serial algorithm.  Weights, duals, edge tightness
+ * and scalings are streaming kernels; the order-dependent greedy pass (:98-112) runs as rounds of proposals that
+ * reproduce the serial outcome exactly; the repair passes for columns left without a free tight row (:115-193,
+ * normally a handful of columns) finish on the host by the same serial rules.  All pointers are host memory.
+ * permR[match[c]] = c is the row IS the reference returns (:201-203; its column IS is the identity, :204);
+ * match (CSR row c -> matched index), scalR = exp(v)/amax and scalC = exp(u) (:212-215, computed and discarded by the
+ * reference; usable with spk_set_scaling) and stats[4] = {device rounds, columns matched on the device, columns
+ * finished by the serial greedy rule on the host, columns that needed a repair pass} are optional (NULL). */
+int spk_awbm_csr(spk_ctx *ctx, int n, const int *ia, const int *ja, const double *a, int *permR, int *match,
+                 double *scalR, double *scalC, int *stats);
+
 /* Self-check of the factorisation (no reference counterpart: the reference's inner PC is an exact LU): with the
  * unfactored band kept (spk_keep_original), solves B x = B v for a fixed probe v and returns ||x - v|| / ||v||.  The
  * truncated SPIKE apply equals the exact band solve only where the spikes decay inside the truncation window

@@ -38,7 +38,8 @@ class Info(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "lib", "libspike_b200.so")
+    # SPIKE_B200_LIB: an alternative build of the same library (kernel experiments of tools/, never set in tests/bench)
+    return os.environ.get("SPIKE_B200_LIB") or os.path.join(_HERE, "lib", "libspike_b200.so")
 
 
 def exported_symbols() -> list[str]:
@@ -77,6 +78,7 @@ def lib():
         L.spk_krylov.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, ip, dp, ip]
         L.spk_view.argtypes = [vp, C.POINTER(Info)]
         L.spk_check.argtypes = [vp, dp]
+        L.spk_awbm_csr.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
         L.spk_tip_size.argtypes = [vp, ip]
         L.spk_get_boundary.argtypes = [vp, C.c_int, vp]
         L.spk_set_boundary.argtypes = [vp, C.c_int, vp]
@@ -280,6 +282,19 @@ class Spike:
 
     def peer_check(self):
         self._ck(lib().spk_peer_check(self._h), "spk_peer_check")
+
+    def awbm(self, ia, ja, a, want_scalings=False):
+        """MatGetOrdering_AWBM on the GPU (spk_awbm_csr) -> (permR, match, stats[, scalR, scalC])."""
+        ia = np.ascontiguousarray(ia, dtype=np.int32)
+        ja = np.ascontiguousarray(ja, dtype=np.int32)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        n = ia.size - 1
+        permR, match, stats = np.empty(n, np.int32), np.empty(n, np.int32), np.zeros(4, np.int32)
+        sr = np.empty(n) if want_scalings else None
+        sc = np.empty(n) if want_scalings else None
+        self._ck(lib().spk_awbm_csr(self._h, n, _addr(ia), _addr(ja), _addr(a), _addr(permR), _addr(match), _addr(sr), _addr(sc),
+                                    _addr(stats)), "spk_awbm_csr")
+        return (permR, match, stats, sr, sc) if want_scalings else (permR, match, stats)
 
     def check(self) -> float:
         """||x - v|| / ||v|| of one probe solve through the kept unfactored band (spk_check)."""

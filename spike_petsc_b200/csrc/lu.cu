@@ -329,6 +329,23 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     fetch_tail(1); fetch_tail(2);
     if (KT <= FD) fetch_tail(KT > 2 ? KT : 0);
     double2 af = afn;
+#if LU_OPAHEAD
+    // operand of tile i+2 requested right after the last DMMA that reads the registers it lands in (tile i's second
+    // k-chunk): two DMMAs, not one, sit between a shared-memory load and its first use, with the same two buffers
+    if (KT >= 2) afn = load_operand(2);
+    dmma884(LU_TILE(1).x, LU_TILE(1).y, af.x, w.x);
+#pragma unroll
+    for (int i = 1; i <= KT; ++i) {
+      if (i + 2 < KT) fetch_tail(i + 2);
+      if (KT > FD && i + FD == KT) fetch_tail(KT);
+      dmma884(LU_TILE(i).x, LU_TILE(i).y, af.y, w.y);
+      if (i + 2 <= KT) af = load_operand(i + 2);
+      if (i < KT) dmma884(LU_TILE(i + 1).x, LU_TILE(i + 1).y, afn.x, w.x);
+      if (i == 1 && own_next) give_d(LU_TILE(1));
+      if (i >= 2) pub(i - 1, LU_TILE(i - 1));
+      const double2 nx = af; af = afn; afn = nx;
+    }
+#else
     dmma884(LU_TILE(1).x, LU_TILE(1).y, af.x, w.x);
 #pragma unroll
     for (int i = 1; i <= KT; ++i) {
@@ -342,6 +359,7 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
       if (i >= 2) pub(i - 1, LU_TILE(i - 1));
       af = afn;
     }
+#endif
     pub(KT, fT);
 #undef LU_TILE
     __syncwarp();

@@ -13,6 +13,7 @@
  * Registered like the reference's orderings (src/testbed2.c:66-68): MatOrderingRegister("fiedler", MatGetOrdering_Fiedler).
  */
 #include "petsc_access.h"
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -115,3 +116,32 @@ PetscErrorCode MatGetOrdering_RCM(Mat A, const char *type, IS *row, IS *col) {
 }
 /* the "fiedler" slot of the reference (MC73 absent): see the header of this file */
 PetscErrorCode MatGetOrdering_Fiedler(Mat A, const char *type, IS *row, IS *col) { return MatGetOrdering_RCM(A, type, row, col); }
+
+/* "awbm" (src/petsc_mat_awbm.c:42-225, registered at src/testbed2.c:67) with the matching computed on the GPU by
+ * spk_awbm_csr: row IS = permR, column IS = identity (:201-205); the scalings are computed and dropped like in the
+ * reference (:221-222).  A short-lived engine context carries the device and the error text. */
+#include "../../include/spike_b200.h"
+PetscErrorCode MatGetOrdering_AWBM(Mat A, const char *type, IS *row, IS *col) {
+  PetscInt n; const PetscInt *ai, *aj; const PetscScalar *aa; PetscErrorCode ierr;
+  (void)type;
+  ierr = SpkMatGetCSR(A, &n, &ai, &aj, &aa);CHKERRQ(ierr);
+  spk_ctx *ctx = NULL; spk_opts o;
+  spk_default_opts(&o);
+  if (spk_create(&ctx, &o)) SPK_ERR(PETSC_ERR_LIB, "AWBM ordering: %s", spk_last_error(NULL));
+  PetscInt *pr = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(n > 0 ? n : 1));
+  PetscInt *pc = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(n > 0 ? n : 1));
+  if (!pr || !pc) { free(pr); free(pc); spk_destroy(&ctx); SPK_ERR(PETSC_ERR_LIB, "AWBM ordering: out of memory"); }
+  const int rc = spk_awbm_csr(ctx, (int)n, (const int *)ai, (const int *)aj, aa, (int *)pr, NULL, NULL, NULL, NULL);
+  if (rc) {
+    char msg[256]; snprintf(msg, sizeof msg, "%s", spk_last_error(ctx));
+    free(pr); free(pc); spk_destroy(&ctx);
+    SPK_ERR(PETSC_ERR_LIB, "AWBM ordering failed (%d): %s", rc, msg);
+  }
+  spk_destroy(&ctx);
+  ierr = SpkMatRestoreCSR(A, &n, &ai, &aj, &aa);CHKERRQ(ierr);
+  for (PetscInt i = 0; i < n; ++i) pc[i] = i;
+  ierr = ISCreateGeneral(n, pr, row);CHKERRQ(ierr);
+  ierr = ISCreateGeneral(n, pc, col);CHKERRQ(ierr);
+  free(pr); free(pc);
+  return 0;
+}

@@ -38,6 +38,8 @@ PetscErrorCode MatBandedGetInfo(Mat B, PetscInt *k, PetscReal *f, PetscInt *nfac
 int SpkOrderingRCM(PetscInt n, const PetscInt *ai, const PetscInt *aj, PetscInt *perm);
 PetscErrorCode MatGetOrdering_RCM(Mat A, const char *type, IS *row, IS *col);
 PetscErrorCode MatGetOrdering_Fiedler(Mat A, const char *type, IS *row, IS *col);
+/* "awbm" with the matching computed on the GPU (spk_awbm_csr), bit-identical to src/petsc_mat_awbm.c:42-225 */
+PetscErrorCode MatGetOrdering_AWBM(Mat A, const char *type, IS *row, IS *col);
 /* on-disk formats of the reference's drivers (matio.c): PETSc binary Mat/Vec (MatLoad, src/testbed2.c:93-96),
  * MatrixMarket export (src/wbm.c:520-523).  0-based CSR, arrays malloc'd for the caller (SpkFree). */
 int SpkMatLoadBinary(const char *path, int *rows, int *cols, int **ia, int **ja, double **a);
