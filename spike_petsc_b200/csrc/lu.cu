@@ -329,9 +329,10 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
     fetch_tail(1); fetch_tail(2);
     if (KT <= FD) fetch_tail(KT > 2 ? KT : 0);
     double2 af = afn;
-#if LU_OPAHEAD
-    // operand of tile i+2 requested right after the last DMMA that reads the registers it lands in (tile i's second
-    // k-chunk): two DMMAs, not one, sit between a shared-memory load and its first use, with the same two buffers
+    // Two operand buffers, af / afn.  The operand of tile i+2 is requested right after the last DMMA that reads the
+    // registers it lands in (the second k-chunk of tile i), so TWO DMMAs sit between a shared-memory load and its first
+    // use; requesting it an iteration later (one DMMA in between) left the tensor pipe waiting on the short scoreboard
+    // (ncu source view: 28 % of the samples on the DMMA behind each LDS; 8.83 -> 8.59 ms at C3).
     if (KT >= 2) afn = load_operand(2);
     dmma884(LU_TILE(1).x, LU_TILE(1).y, af.x, w.x);
 #pragma unroll
@@ -345,21 +346,6 @@ __global__ void __launch_bounds__((KT + 1) * 32, (KT >= 14 ? 1 : (KT >= 10 ? 2 :
       if (i >= 2) pub(i - 1, LU_TILE(i - 1));
       const double2 nx = af; af = afn; afn = nx;
     }
-#else
-    dmma884(LU_TILE(1).x, LU_TILE(1).y, af.x, w.x);
-#pragma unroll
-    for (int i = 1; i <= KT; ++i) {
-      if (i + 2 < KT) fetch_tail(i + 2);
-      if (KT > FD && i + FD == KT) fetch_tail(KT);
-      if (i < KT) afn = load_operand(i + 1);
-      dmma884(LU_TILE(i).x, LU_TILE(i).y, af.y, w.y);
-      if (i < KT) dmma884(LU_TILE(i + 1).x, LU_TILE(i + 1).y, afn.x, w.x);
-      // tile i-1 is final by now (its last DMMA was issued an iteration ago)
-      if (i == 1 && own_next) give_d(LU_TILE(1));
-      if (i >= 2) pub(i - 1, LU_TILE(i - 1));
-      af = afn;
-    }
-#endif
     pub(KT, fT);
 #undef LU_TILE
     __syncwarp();

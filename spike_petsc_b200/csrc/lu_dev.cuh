@@ -12,9 +12,6 @@
 #define LU_NSM_WIDE 0
 #endif
 #define LU_TRACE_STEPS 64
-#ifndef LU_OPAHEAD
-#define LU_OPAHEAD 0      // 1: package operands requested two DMMAs ahead of their use instead of one
-#endif
 // optional clock64 trace of CTA 0 (tools/lu_trace.py): [step-100][16]; 0..7 column warp 0, 8..15 inverter warp
 // LU_TRV: stamp once a register value has been produced
 #define LU_TRV(slot, val) do { if (TRACE && blockIdx.x == 0 && s >= 100 && s < 100 + LU_TRACE_STEPS) { double e_; asm volatile("add.f64 %0, %1, %1;" : "=d"(e_) : "d"(val)); if (lane == 0) a.trace[(s - 100) * 16 + (slot)] = clock64() + (e_ == 1.2345e300 ? 1 : 0); } } while (0)
