@@ -389,6 +389,11 @@ def c4_block(args):
     rp, cp = synthetic.compose_wbm_then_symmetric(R, p2)
     t_ord = time.perf_counter() - t0
     S = sp.Spike(mem=sp.MEM_HOST)
+    # AWBM on the GPU (spk_awbm_csr) on the same matrix: the dominant entry of CSR row c sits in column R[c]
+    S.awbm(ia[:1001].copy(), ja[:ia[1000]].copy() % 1000, a[:ia[1000]].copy())   # warm-up (context, allocations)
+    t0 = time.perf_counter()
+    a_perm, a_match, a_stats = S.awbm(ia, ja, a)
+    t_awbm = time.perf_counter() - t0
     t0 = time.perf_counter()
     k, f = S.set_band_csr(ia, ja, a, 50, 0.95, rowperm=rp, colperm=cp)
     t_pack = time.perf_counter() - t0
@@ -404,7 +409,9 @@ def c4_block(args):
     return {"workload": "synthetic sparse nonsymmetric N=2M nnz~22M, WBM (matching known by construction) + RCM stand-in for MC73, PCBANDED(50,0.95), BiCGStab rtol 1e-5",
             "k": k, "frac": f, "iterations": its, "converged": bool(conv), "err_per_entry": float(np.linalg.norm(xu - 1.0) / np.sqrt(n)),
             "factor_ms": info["factor_ms"], "krylov_ms_host_buffers": t_kry * 1e3, "band_select_and_pack_s": t_pack,
-            "ordering_host_s": t_ord, "generator_s": t_gen, "partitions": info["partitions"]}
+            "ordering_host_s": t_ord, "generator_s": t_gen, "partitions": info["partitions"],
+            "awbm_gpu": {"ms_host_csr_in_perm_out": t_awbm * 1e3, "device_rounds": int(a_stats[0]), "matched_on_device": int(a_stats[1]),
+                         "finished_on_host": int(a_stats[2] + a_stats[3]), "recovers_row_scramble": bool((a_match == R).all())}}
 
 
 def run_ours(args):

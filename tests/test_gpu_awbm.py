@@ -39,8 +39,10 @@ def test_awbm_known_answer_of_the_reference(spk, oracle):
 def test_awbm_random_sparse(spk, oracle, n, density, seed):
     """unstructured random matrices: many columns compete for the same tight rows, some need the repair passes"""
     rng = np.random.default_rng(seed)
-    A = sp.random(n, n, density=density, random_state=seed, format="csr", data_rvs=lambda m: rng.uniform(-1, 1, m))
+    m = int(density * n * n)
+    A = sp.csr_matrix((rng.uniform(-1, 1, m), (rng.integers(0, n, m), rng.integers(0, n, m))), shape=(n, n))
     A = A + sp.diags(rng.uniform(-1, 1, n) * (rng.random(n) < 0.7))      # 30 % of the diagonal is structurally absent
+    A = sp.csr_matrix(A); A.sum_duplicates()
     S = spk.Spike()
     _compare(S, oracle, A)
 
@@ -82,7 +84,8 @@ def test_awbm_zero_entries_and_empty_rows(spk, oracle):
     """explicit zeros get weight DBL_MAX (:77), rows without entries fall to the completion pass (:181-193)"""
     rng = np.random.default_rng(11)
     n = 3000
-    A = sp.random(n, n, density=0.003, random_state=5, format="lil")
+    m = int(0.003 * n * n)
+    A = sp.csr_matrix((rng.uniform(0.1, 1, m), (rng.integers(0, n, m), rng.integers(0, n, m))), shape=(n, n)).tolil()
     for r in rng.choice(n, 40, replace=False):
         A.rows[r], A.data[r] = [], []
     A = sp.csr_matrix(A)
