@@ -391,9 +391,11 @@ def c4_block(args):
     S = sp.Spike(mem=sp.MEM_HOST)
     # AWBM on the GPU (spk_awbm_csr) on the same matrix: the dominant entry of CSR row c sits in column R[c]
     S.awbm(ia[:1001].copy(), ja[:ia[1000]].copy() % 1000, a[:ia[1000]].copy())   # warm-up (context, allocations)
-    t0 = time.perf_counter()
-    a_perm, a_match, a_stats = S.awbm(ia, ja, a)
-    t_awbm = time.perf_counter() - t0
+    t_awbm = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter()
+        a_perm, a_match, a_stats = S.awbm(ia, ja, a)
+        t_awbm = min(t_awbm, time.perf_counter() - t0)
     t0 = time.perf_counter()
     k, f = S.set_band_csr(ia, ja, a, 50, 0.95, rowperm=rp, colperm=cp)
     t_pack = time.perf_counter() - t0

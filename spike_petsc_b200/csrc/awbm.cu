@@ -26,6 +26,7 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <chrono>
 #include <vector>
 #include "common.cuh"
 
@@ -144,6 +145,15 @@ extern "C" int spk_awbm_csr(spk_ctx* c, int n, const int* ia, const int* ja, con
   for (long long q = 0; q < nnz; ++q) if (ja[q] < 0 || ja[q] >= n) { SPK_SET_ERR(c, "awbm: column index %d out of range at %lld", ja[q], q); return SPK_ERR_ARG; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   cudaStream_t st = c->stream;
+  const bool timing = getenv("SPIKE_AWBM_TIMING") != nullptr;   // debug: host wall time per phase on stderr
+  auto tprev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(st);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[awbm] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tprev).count());
+    tprev = now;
+  };
   Dev D;
   int *d_ia, *d_ja, *d_match, *d_matchR, *d_ptr, *d_cnt;
   double *d_a, *d_amax, *d_w, *d_u, *d_v, *d_sr, *d_sc;
@@ -168,6 +178,7 @@ extern "C" int spk_awbm_csr(spk_ctx* c, int n, const int* ia, const int* ja, con
     SPK_CUDA(c, cudaMemcpyAsync(d_ptr, d_ia, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));
     SPK_CUDA(c, cudaStreamSynchronize(st));   // `big` leaves scope
   }
+  lap("alloc + upload + init");
   const double eps = sqrt(DBL_EPSILON);   // PETSC_SQRT_MACHINE_EPSILON (:59)
   const int TB = 256;
   const unsigned warp_grid = (unsigned)(((size_t)n * 32 + TB - 1) / TB), col_grid = (unsigned)((n + TB - 1) / TB);
@@ -175,6 +186,7 @@ extern "C" int spk_awbm_csr(spk_ctx* c, int n, const int* ia, const int* ja, con
   SPK_KERNEL_CHECK(c);
   k_awbm_duals<<<warp_grid, TB, 0, st>>>(n, d_ia, d_ja, d_w, d_u, d_v, d_tight, eps);
   SPK_KERNEL_CHECK(c);
+  lap("weights + duals kernels");
   int rounds = 0, on_device = 0, open = n;
   while (open > 0 && rounds < AWBM_MAX_ROUNDS) {
     ++rounds;
@@ -190,6 +202,7 @@ extern "C" int spk_awbm_csr(spk_ctx* c, int n, const int* ia, const int* ja, con
     open = cnt[1];
     if (cnt[0] < AWBM_MIN_PROGRESS) break;   // a chain: the serial rule on the host is faster than a round per link
   }
+  lap("matching rounds");
   if (scalR || scalC) {
     SPK_CUDA(c, D.alloc(&d_sr, (size_t)n)); SPK_CUDA(c, D.alloc(&d_sc, (size_t)n));
     k_awbm_scalings<<<col_grid, TB, 0, st>>>(n, d_u, d_v, d_amax, d_sr, d_sc);
@@ -202,6 +215,7 @@ extern "C" int spk_awbm_csr(spk_ctx* c, int n, const int* ia, const int* ja, con
   SPK_CUDA(c, cudaMemcpyAsync(matchR.data(), d_matchR, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
   SPK_CUDA(c, cudaStreamSynchronize(st));
 
+  lap("scalings + download");
   // ---- host: what is left of the greedy pass, then the reference's repair passes, all by the serial rules ----
   int host_greedy = 0, repaired = 0;
   bool need_tight = false;
@@ -265,5 +279,6 @@ extern "C" int spk_awbm_csr(spk_ctx* c, int n, const int* ia, const int* ja, con
   for (int col = 0; col < n; ++col) permR[match[col]] = col;   // :201
   if (match_out) std::copy(match.begin(), match.end(), match_out);
   if (stats) { stats[0] = rounds; stats[1] = on_device; stats[2] = host_greedy; stats[3] = repaired; }
+  lap("host finish + permutation");
   return SPK_OK;
 }
