@@ -88,6 +88,7 @@ struct spk_ctx {
   int wide_G;                // column CTAs per partition group of the wide LU (0 = kb)
   unsigned long long* wide_flags; int wide_flag_parts;   // dataflow flags of the wide LU (WIDE_FLAGS_PER_PART words per partition)
   unsigned int* wide_abort;  // set by a wide kernel whose bounded wait expired
+  double* wide_zero;         // 4 KB of zeros: the factor run of a window row outside a sweep job (wide_sweep.cu)
   double* wband;             // row/column-reversed copies of the top tip windows (P partitions of tipT tile rows), factored for W^(t)
   double* rband;             // reduced matrices I - W V in band format (P partitions of 8*kb tile rows), factored for R
   double* VbT;               // V^(b) transposed (right operand of the reduced-matrix product)

@@ -29,6 +29,8 @@ int spk_wide_alloc(spk_ctx* c) {
   WIDE_CUDA(c, cudaMalloc(&c->wide_flags, sizeof(unsigned long long) * (size_t)c->wide_flag_parts * WIDE_FLAGS_PER_PART));
   WIDE_CUDA(c, cudaMalloc(&c->wide_abort, sizeof(unsigned int)));
   WIDE_CUDA(c, cudaMemsetAsync(c->wide_abort, 0, sizeof(unsigned int), c->stream));
+  WIDE_CUDA(c, cudaMalloc(&c->wide_zero, 4096));
+  WIDE_CUDA(c, cudaMemsetAsync(c->wide_zero, 0, 4096, c->stream));
   const size_t tile_row = (size_t)L.tpr * SPK_TILE_ELEMS;
   WIDE_CUDA(c, cudaMalloc(&c->wband, sizeof(double) * tile_row * (size_t)c->tipT * P));
   WIDE_CUDA(c, cudaMalloc(&c->rband, sizeof(double) * tile_row * (size_t)(8 * c->kb) * P));
@@ -48,7 +50,7 @@ int spk_wide_alloc(spk_ctx* c) {
 
 void spk_wide_free(spk_ctx* c) {
   auto F = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
-  F(c->wide_flags); F(c->wide_abort); F(c->wband); F(c->rband); F(c->VbT); F(c->d_wpstart); F(c->d_rpstart);
+  F(c->wide_flags); F(c->wide_abort); F(c->wide_zero); F(c->wband); F(c->rband); F(c->VbT); F(c->d_wpstart); F(c->d_rpstart);
   if (c->d_wjobs) { cudaFree(c->d_wjobs); c->d_wjobs = nullptr; }
   if (c->h_wjobs) { delete[] (std::vector<WideSweepJob>*)c->h_wjobs; c->h_wjobs = nullptr; }
   F(c->redw); c->redw_cols = 0;

@@ -17,10 +17,13 @@
 #include "wide.cuh"
 #include <algorithm>
 
-struct WideSweepArgs { const WideSweepJob* jobs; int tpr, kts, KB; long long* trace; };
+struct WideSweepArgs { const WideSweepJob* jobs; int tpr, kts, KB; long long* trace; const double* zero; };
 #define WS_ADD(slot) do { if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { const long long n_ = clock64(); tr[slot] += n_ - tmark; tmark = n_; } } while (0)
 
 #define WS_THREADS 256
+#ifndef WS_PFA
+#define WS_PFA 0   // L2 bulk prefetch of the sweeps' factor runs, in super-block steps ahead; 0 = none (measured: 2 costs 8 %, r02_summary)
+#endif
 #define WS_WARPS 8
 
 // one TMA-engine request pulls a whole 4 KB run (a tile row of a super-block) into L2
@@ -32,9 +35,15 @@ __device__ __forceinline__ double2 ldnc_v2(const double* p) {
 }
 
 // NSLOT = KB (window in super-blocks); warp r of the CTA owns tile row r of every super-block of the window: NSLOT
-// accumulator tiles per right-hand-side tile column, slot of super-block J = J % NSLOT.  255 registers per thread
-// (8 warps): the factor-tile ring (PFT tiles = 4*PFT registers) never spills -- a spilled ring slot would turn its
-// load into a synchronous wait for HBM.
+// accumulator tiles per right-hand-side tile column, acc[d] = the rows of super-block I+d (forward) / I-d (backward)
+// at step I; the window slides by register renaming / moves.
+// Addressing is affine: with P(I) = the warp's tile row of the DIAGONAL super-block of step I and DS = 512 (tpr - 1),
+//     tile k of  Lb(I+d, I) = P(I) + d DS + 64 k,     Ub(I-d, I) = P(I) - d DS + 64 k,     D_I^-1 = P(I) + 64 k,
+// so a step keeps one base pointer per window row (a zero run replaces rows outside the job) and every factor tile is
+// ONE load with an immediate offset.  (The first version indexed the window by super-block % NSLOT: ~25 integer
+// instructions per tile -- 64-bit multiplies, slot arithmetic, null-pointer branches -- made the kernel issue bound at
+// 3x its DMMA time; see profiles/r02_summary.md.)  The factor tiles of the coming PFT positions sit in a register ring
+// (255 registers per thread, 8 warps; a spilled ring slot would turn its load into a synchronous wait for HBM).
 template <int NSLOT, int NCT, int PFT>
 __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArgs a) {
   __shared__ __align__(16) double Cbuf[8][NCT][64];
@@ -46,21 +55,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
   const int g = lane >> 2, tq = lane & 3;
   const int tpr = a.tpr, kts = a.kts;
   constexpr int NIT = 8 * NSLOT;                       // factor tiles per warp and step
-  constexpr int GS = (NSLOT % 4 == 0) ? 4 : 2;         // slots interleaved in the update loop (independent DMMA chains)
-  static_assert(NIT % PFT == 0 && NSLOT % GS == 0, "ring depth must divide the tiles per step");
+  constexpr int GS = (NSLOT % 4 == 0) ? 4 : 2;         // window rows interleaved in the update loop (independent DMMA chains)
+  static_assert(NIT % PFT == 0 && NSLOT % GS == 0 && PFT % GS == 0, "ring depth must divide the tiles per step");
   const long long lo = job.sb_lo, hi = job.sb_hi;
-  auto tile = [&](long long I, long long J) -> const double* { return job.band + (I * tpr + (J - I + kts)) * SPK_TILE_ELEMS; };
-  // the super-block held in slot q when the window starts at super-block wb
-  auto sb_of = [&](long long wb, int q) -> long long {
-    long long m = wb % NSLOT;
-    if (m < 0) m += NSLOT;
-    long long d = q - m;
-    if (d < 0) d += NSLOT;
-    return wb + d;
-  };
-  // tile n of the update loop -> (slot q, k): groups of GS slots, k-major inside a group
-  auto slot_of = [](int n) -> int { return (n / (8 * GS)) * GS + (n % GS); };
+  // tile n of the update loop -> (window row d = 1..NSLOT, k): groups of GS rows, k-major inside a group
+  auto d_of = [](int n) -> int { return (n / (8 * GS)) * GS + (n % GS) + 1; };
   auto k_of = [](int n) -> int { return (n % (8 * GS)) / GS; };
+  const long long DS = 512ll * (tpr - 1);              // doubles between a window row's run and the next one's
+  const long long STEP = 512ll * tpr;                  // doubles between P(I) and P(I+1)
+  const double* const zrun = a.zero + 2 * lane;        // 4 KB of zeros: the run of a window row outside the job
+  auto diag_run = [&](long long I) -> const double* { return job.band + ((I * 8 + warp) * (long long)tpr + (kts - warp)) * SPK_TILE_ELEMS + 2 * lane; };
   auto rhs_pair = [&](const double* src, long long rs, long long cs, long long t, int ct, bool identity) -> double2 {
     const long long r = t * 8 + g - job.row0;
     const int c = col0 + ct * 8 + 2 * tq;
@@ -85,55 +89,83 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
 
   double2 acc[NSLOT][NCT];
   double2 ring[PFT];
+  const double* pd[NSLOT];   // run of window row d+1 at the current step
+  const double* pn[NSLOT];   // ... at the next step
   long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tmark = a.trace ? clock64() : 0;
+
+  // the update loop of one step, shared by both directions: acc[d-1] <- acc[d] + (factor tile row d) * Ybuf (which holds
+  // the NEGATED solved block), d = 1..NSLOT with acc[NSLOT] = the entering rows `ent`
+  auto update = [&](const double2 (&ent)[NCT], int par) {
+    double2 nxt[NSLOT][NCT];
+#pragma unroll
+    for (int d = 1; d <= NSLOT; ++d)
+#pragma unroll
+      for (int ct = 0; ct < NCT; ++ct) nxt[d - 1][ct] = (d < NSLOT) ? acc[d < NSLOT ? d : 0][ct] : ent[ct];
+#pragma unroll
+    for (int n0 = 0; n0 < NIT; n0 += GS) {
+      double2 fa[GS], yb[NCT];
+#pragma unroll
+      for (int qi = 0; qi < GS; ++qi) {
+        const int n = n0 + qi;
+        fa[qi] = ring[n % PFT];
+        const int nn = n + PFT;   // refill the ring slot with the tile PFT positions ahead (possibly of the next step)
+        ring[n % PFT] = (nn < NIT) ? ldnc_v2(pd[d_of(nn) - 1] + 64 * k_of(nn)) : ldnc_v2(pn[d_of(nn - NIT) - 1] + 64 * k_of(nn - NIT));
+      }
+      const int k = k_of(n0);
+#pragma unroll
+      for (int ct = 0; ct < NCT; ++ct) yb[ct] = *reinterpret_cast<const double2*>(&Ybuf[par][k][ct][2 * lane]);
+#pragma unroll
+      for (int ct = 0; ct < NCT; ++ct)
+#pragma unroll
+        for (int qi = 0; qi < GS; ++qi) dmma884(nxt[d_of(n0 + qi) - 1][ct].x, nxt[d_of(n0 + qi) - 1][ct].y, fa[qi].x, yb[ct].x);
+#pragma unroll
+      for (int ct = 0; ct < NCT; ++ct)
+#pragma unroll
+        for (int qi = 0; qi < GS; ++qi) dmma884(nxt[d_of(n0 + qi) - 1][ct].x, nxt[d_of(n0 + qi) - 1][ct].y, fa[qi].y, yb[ct].y);
+    }
+#pragma unroll
+    for (int d = 0; d < NSLOT; ++d)
+#pragma unroll
+      for (int ct = 0; ct < NCT; ++ct) acc[d][ct] = nxt[d][ct];
+  };
 
   // =========================================== forward ===========================================
   {
     const long long I0 = job.sb_fwd;
     const bool ident = (job.in == nullptr);
-    // window of step I0 before its update: super-block rows I0 .. I0+KB-1
+    // window of step I0: super-block rows I0 .. I0+KB-1
 #pragma unroll
-    for (int q = 0; q < NSLOT; ++q) {
-      const long long sb = sb_of(I0, q);
+    for (int d = 0; d < NSLOT; ++d)
 #pragma unroll
-      for (int ct = 0; ct < NCT; ++ct) acc[q][ct] = (sb < hi) ? rhs_pair(job.in, job.in_rs, job.in_cs, sb * 8 + warp, ct, ident) : make_double2(0.0, 0.0);
-    }
-    // factor tile n of step I: Lb(8*sb + warp, 8I + k), sb = the super-block in slot q of the window I+1 .. I+KB
-    auto ftile = [&](long long I, int n) -> const double* {
-      const long long sb = sb_of(I + 1, slot_of(n));
-      return (I < hi && sb < hi) ? tile(sb * 8 + warp, I * 8 + k_of(n)) + 2 * lane : nullptr;
+      for (int ct = 0; ct < NCT; ++ct) acc[d][ct] = (I0 + d < hi) ? rhs_pair(job.in, job.in_rs, job.in_cs, (I0 + d) * 8 + warp, ct, ident) : make_double2(0.0, 0.0);
+    // runs of Lb(I+d, I), d = 1..NSLOT, for step I (zero run when the row or the step is outside the job)
+    auto set_runs = [&](const double* (&pp)[NSLOT], long long I) {
+      const double* P = diag_run(I);
+#pragma unroll
+      for (int d = 1; d <= NSLOT; ++d) pp[d - 1] = (I < hi && I + d < hi) ? P + d * DS : zrun;
     };
+    set_runs(pd, I0);
+    set_runs(pn, I0 + 1);
 #pragma unroll
-    for (int n = 0; n < PFT; ++n) { const double* p = ftile(I0, n); ring[n] = p ? ldnc_v2(p) : make_double2(0.0, 0.0); }
+    for (int n = 0; n < PFT; ++n) ring[n] = ldnc_v2(pd[d_of(n) - 1] + 64 * k_of(n));
+    double2 dv[8];
+    {
+      const double* dsrc = (I0 < hi) ? diag_run(I0) : zrun;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dv[k] = ldnc_v2(dsrc + 64 * k);
+    }
     for (long long I = I0; I < hi; ++I) {
       const int par = (int)(I & 1);
       WS_ADD(3);
-      // ---- phase 1: every warp hands its tile row of c_I over and takes its tile row of the entering row I+KB
-      long long mq = I % NSLOT;
-      if (mq < 0) mq += NSLOT;
-      const int qs = (int)mq;
+      // ---- phase 1: every warp hands its tile row of c_I over
 #pragma unroll
-      for (int q = 0; q < NSLOT; ++q) {
-        if (q == qs) {
-#pragma unroll
-          for (int ct = 0; ct < NCT; ++ct) {
-            store_transposed(&Cbuf[warp][ct][0], acc[q][ct], g, tq);
-            acc[q][ct] = (I + NSLOT < hi) ? rhs_pair(job.in, job.in_rs, job.in_cs, (I + NSLOT) * 8 + warp, ct, ident) : make_double2(0.0, 0.0);
-          }
-        }
-      }
-      // D_I^-1 row tile for phase 2 (requested before the barrier)
-      double2 dv[8];
-      {
-        const double* dsrc = tile(I * 8 + warp, I * 8) + 2 * lane;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dv[k] = ldnc_v2(dsrc + k * 64);
-      }
+      for (int ct = 0; ct < NCT; ++ct) store_transposed(&Cbuf[warp][ct][0], acc[0][ct], g, tq);
       WS_ADD(0);
       __syncthreads();
       WS_ADD(1);
-      // ---- phase 2: y_I = D_I^-1 c_I  (8 independent DMMA chains per column tile)
+      // ---- phase 2: y_I = D_I^-1 c_I  (8 independent DMMA chains per column tile); the NEGATED block is what the
+      //      updates multiply by
 #pragma unroll
       for (int ct = 0; ct < NCT; ++ct) {
         double2 yk[8];
@@ -145,46 +177,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
         for (int k = 0; k < 8; ++k) { const double2 cb = *reinterpret_cast<const double2*>(&Cbuf[k][ct][2 * lane]); dmma884(yk[k].x, yk[k].y, dv[k].y, cb.y); }
         const double2 y = make_double2(((yk[0].x + yk[1].x) + (yk[2].x + yk[3].x)) + ((yk[4].x + yk[5].x) + (yk[6].x + yk[7].x)),
                                        ((yk[0].y + yk[1].y) + (yk[2].y + yk[3].y)) + ((yk[4].y + yk[5].y) + (yk[6].y + yk[7].y)));
-        store_transposed(&Ybuf[par][warp][ct][0], y, g, tq);
+        store_transposed(&Ybuf[par][warp][ct][0], neg2(y), g, tq);
         out_pair(I * 8 + warp, ct, y);
+      }
+      // D^-1 of the next step: requested a whole update phase ahead of its use
+      {
+        const double* dsrc = (I + 1 < hi) ? diag_run(I + 1) : zrun;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dv[k] = ldnc_v2(dsrc + 64 * k);
       }
       WS_ADD(2);
       __syncthreads();
       WS_ADD(1);
-      // ---- phase 3: c_J -= Lb(J,I) y_I for the window rows below
-      // (the factor tiles and D^-1 of step I+2 are pulled into L2 now, one bulk prefetch per 4 KB run: the
-      //  register ring and the D^-1 loads of the coming steps then pay L2 latency, not HBM latency)
-      if (I + 2 < hi) {
-#pragma unroll
-        for (int q = 0; q < NSLOT; ++q) {
-          const long long sb = sb_of(I + 3, q);
-          if (sb < hi && lane == q) prefetch_l2_4k(tile(sb * 8 + warp, (I + 2) * 8));
-        }
-        if (lane == NSLOT) prefetch_l2_4k(tile((I + 2) * 8 + warp, (I + 2) * 8));
+      // ---- phase 3: c_J -= Lb(J,I) y_I for the window rows below; row I+KB enters
+#if WS_PFA > 0
+      if (I + WS_PFA < hi) {   // factor tiles and D^-1 of a later step pulled into L2, one bulk prefetch per 4 KB run
+        const double* P = diag_run(I + WS_PFA) - 2 * lane;
+        if (lane <= NSLOT && I + WS_PFA + lane < hi) prefetch_l2_4k(P + lane * DS);
       }
+#endif
+      double2 ent[NCT];
 #pragma unroll
-      for (int n0 = 0; n0 < NIT; n0 += GS) {
-        double2 na[GS], yb[NCT];
+      for (int ct = 0; ct < NCT; ++ct) ent[ct] = (I + NSLOT < hi) ? rhs_pair(job.in, job.in_rs, job.in_cs, (I + NSLOT) * 8 + warp, ct, ident) : make_double2(0.0, 0.0);
+      update(ent, par);
 #pragma unroll
-        for (int qi = 0; qi < GS; ++qi) {
-          const int n = n0 + qi;
-          na[qi] = neg2(ring[n % PFT]);
-          const int nn = n + PFT;   // refill the ring slot with the tile PFT positions ahead
-          const double* p = (nn < NIT) ? ftile(I, nn) : ftile(I + 1, nn - NIT);
-          ring[n % PFT] = p ? ldnc_v2(p) : make_double2(0.0, 0.0);
-        }
-        const int k = k_of(n0);
-#pragma unroll
-        for (int ct = 0; ct < NCT; ++ct) yb[ct] = *reinterpret_cast<const double2*>(&Ybuf[par][k][ct][2 * lane]);
-#pragma unroll
-        for (int ct = 0; ct < NCT; ++ct)
-#pragma unroll
-          for (int qi = 0; qi < GS; ++qi) dmma884(acc[slot_of(n0 + qi)][ct].x, acc[slot_of(n0 + qi)][ct].y, na[qi].x, yb[ct].x);
-#pragma unroll
-        for (int ct = 0; ct < NCT; ++ct)
-#pragma unroll
-          for (int qi = 0; qi < GS; ++qi) dmma884(acc[slot_of(n0 + qi)][ct].x, acc[slot_of(n0 + qi)][ct].y, na[qi].y, yb[ct].y);
-      }
+      for (int d = 0; d < NSLOT; ++d) pd[d] = pn[d];
+      set_runs(pn, I + 2);
     }
   }
   WS_ADD(3);
@@ -192,70 +210,45 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
   // =========================================== backward ==========================================
   {
     const long long I0 = hi - 1;
-    // window of step I0 before its update: super-block rows I0-KB+1 .. I0, right-hand side = y (in `out`)
+    // window of step I0: super-block rows I0, I0-1, .. I0-KB+1, right-hand side = y (in `out`)
 #pragma unroll
-    for (int q = 0; q < NSLOT; ++q) {
-      const long long sb = sb_of(I0 + 1 - NSLOT, q);
+    for (int d = 0; d < NSLOT; ++d)
 #pragma unroll
-      for (int ct = 0; ct < NCT; ++ct) acc[q][ct] = (sb >= lo) ? rhs_pair(job.out, job.out_rs, job.out_cs, sb * 8 + warp, ct, false) : make_double2(0.0, 0.0);
-    }
-    // factor tile n of step I: Ub(8*sb + warp, 8I + k), sb = the super-block in slot q of the window I-KB .. I-1
-    auto ftile = [&](long long I, int n) -> const double* {
-      const long long sb = sb_of(I - NSLOT, slot_of(n));
-      return (I >= lo && sb >= lo) ? tile(sb * 8 + warp, I * 8 + k_of(n)) + 2 * lane : nullptr;
+      for (int ct = 0; ct < NCT; ++ct) acc[d][ct] = (I0 - d >= lo) ? rhs_pair(job.out, job.out_rs, job.out_cs, (I0 - d) * 8 + warp, ct, false) : make_double2(0.0, 0.0);
+    // runs of Ub(I-d, I), d = 1..NSLOT: row I-d, i.e. the diagonal run of step I-d moved 8d tiles to the right
+    auto set_runs = [&](const double* (&pp)[NSLOT], long long I) {
+      const double* P = diag_run(I);
+#pragma unroll
+      for (int d = 1; d <= NSLOT; ++d) pp[d - 1] = (I >= lo && I - d >= lo) ? P - d * DS : zrun;
     };
+    set_runs(pd, I0);
+    set_runs(pn, I0 - 1);
 #pragma unroll
-    for (int n = 0; n < PFT; ++n) { const double* p = ftile(I0, n); ring[n] = p ? ldnc_v2(p) : make_double2(0.0, 0.0); }
+    for (int n = 0; n < PFT; ++n) ring[n] = ldnc_v2(pd[d_of(n) - 1] + 64 * k_of(n));
     for (long long I = I0; I >= lo; --I) {
       const int par = (int)(I & 1);
       WS_ADD(6);
-      long long mq = I % NSLOT;
-      if (mq < 0) mq += NSLOT;
-      const int qs = (int)mq;
 #pragma unroll
-      for (int q = 0; q < NSLOT; ++q) {
-        if (q == qs) {
-#pragma unroll
-          for (int ct = 0; ct < NCT; ++ct) {
-            store_transposed(&Ybuf[par][warp][ct][0], acc[q][ct], g, tq);
-            out_pair(I * 8 + warp, ct, acc[q][ct]);
-            acc[q][ct] = (I - NSLOT >= lo) ? rhs_pair(job.out, job.out_rs, job.out_cs, (I - NSLOT) * 8 + warp, ct, false) : make_double2(0.0, 0.0);
-          }
-        }
+      for (int ct = 0; ct < NCT; ++ct) {
+        store_transposed(&Ybuf[par][warp][ct][0], neg2(acc[0][ct]), g, tq);
+        out_pair(I * 8 + warp, ct, acc[0][ct]);
       }
       WS_ADD(4);
       __syncthreads();
       WS_ADD(5);
-      if (I - 2 >= lo) {
-#pragma unroll
-        for (int q = 0; q < NSLOT; ++q) {
-          const long long sb = sb_of(I - 2 - NSLOT, q);
-          if (sb >= lo && lane == q) prefetch_l2_4k(tile(sb * 8 + warp, (I - 2) * 8));
-        }
+#if WS_PFA > 0
+      if (I - WS_PFA >= lo) {
+        const double* P = diag_run(I - WS_PFA) - 2 * lane;
+        if (lane >= 1 && lane <= NSLOT && I - WS_PFA - lane >= lo) prefetch_l2_4k(P - lane * DS);
       }
+#endif
+      double2 ent[NCT];
 #pragma unroll
-      for (int n0 = 0; n0 < NIT; n0 += GS) {
-        double2 na[GS], yb[NCT];
+      for (int ct = 0; ct < NCT; ++ct) ent[ct] = (I - NSLOT >= lo) ? rhs_pair(job.out, job.out_rs, job.out_cs, (I - NSLOT) * 8 + warp, ct, false) : make_double2(0.0, 0.0);
+      update(ent, par);
 #pragma unroll
-        for (int qi = 0; qi < GS; ++qi) {
-          const int n = n0 + qi;
-          na[qi] = neg2(ring[n % PFT]);
-          const int nn = n + PFT;
-          const double* p = (nn < NIT) ? ftile(I, nn) : ftile(I - 1, nn - NIT);
-          ring[n % PFT] = p ? ldnc_v2(p) : make_double2(0.0, 0.0);
-        }
-        const int k = k_of(n0);
-#pragma unroll
-        for (int ct = 0; ct < NCT; ++ct) yb[ct] = *reinterpret_cast<const double2*>(&Ybuf[par][k][ct][2 * lane]);
-#pragma unroll
-        for (int ct = 0; ct < NCT; ++ct)
-#pragma unroll
-          for (int qi = 0; qi < GS; ++qi) dmma884(acc[slot_of(n0 + qi)][ct].x, acc[slot_of(n0 + qi)][ct].y, na[qi].x, yb[ct].x);
-#pragma unroll
-        for (int ct = 0; ct < NCT; ++ct)
-#pragma unroll
-          for (int qi = 0; qi < GS; ++qi) dmma884(acc[slot_of(n0 + qi)][ct].x, acc[slot_of(n0 + qi)][ct].y, na[qi].y, yb[ct].y);
-      }
+      for (int d = 0; d < NSLOT; ++d) pd[d] = pn[d];
+      set_runs(pn, I - 2);
     }
   }
   WS_ADD(6);
@@ -272,12 +265,13 @@ static int launch_ws(spk_ctx* c, const WideSweepArgs& a, int njobs, int groups) 
 // run the jobs (device array); max_cols = the largest ncols among them
 int spk_wide_sweep(spk_ctx* c, const WideSweepJob* d_jobs, int njobs, int max_cols) {
   if (njobs <= 0 || max_cols <= 0) return SPK_OK;
-  WideSweepArgs a; a.jobs = d_jobs; a.tpr = c->L.tpr; a.kts = c->L.kt; a.KB = c->kb;
+  WideSweepArgs a; a.jobs = d_jobs; a.tpr = c->L.tpr; a.kts = c->L.kt; a.KB = c->kb; a.zero = c->wide_zero;
   a.trace = (c->lu_trace && d_jobs == (const WideSweepJob*)c->d_wjobs + (size_t)3 * c->wjobs_cap) ? (long long*)c->lu_trace + 128 : nullptr;   // (debug: the partition sweeps)
   const int nslot = c->kb;
   // 16 columns per CTA (the band is streamed once per 16 columns) unless that leaves most of the GPU idle: few jobs
   // (partitions) -> 8 columns per CTA, twice the CTAs, the second reader of a factor tile hits L2
-  const bool one = max_cols <= 8 || (int64_t)njobs * ((max_cols + 15) / 16) * 4 < (int64_t)c->sm_count * 3;
+  bool one = max_cols <= 8 || (int64_t)njobs * ((max_cols + 15) / 16) * 4 < (int64_t)c->sm_count * 3;
+  if (const char* e = getenv("SPIKE_WS_NCT")) one = max_cols <= 8 || atoi(e) == 1;   // tools: force 8 / 16 columns per CTA
   const int groups = one ? (max_cols + 7) / 8 : (max_cols + 15) / 16;
   for (int j0 = 0; j0 < njobs; j0 += 65535) {
     WideSweepArgs b = a; b.jobs = d_jobs + j0;
