@@ -32,7 +32,7 @@ def test_wide_band_storage_bit_exact(spk, oracle, n, k):
     S.close()
 
 
-@pytest.mark.parametrize("n,k", [(1024, 136), (2048, 256), (1500, 200), (4096, 512), (2500, 400)])
+@pytest.mark.parametrize("n,k", [(1024, 136), (2048, 256), (1500, 200), (4096, 512), (2500, 400), (2200, 350)])
 def test_wide_single_partition_exact(spk, oracle, n, k):
     """One partition: the super-block LU + sweeps are an exact band solve (no truncation involved)."""
     a = oracle.gen_band(n, k)
@@ -51,7 +51,7 @@ def test_wide_single_partition_exact(spk, oracle, n, k):
 
 
 @pytest.mark.parametrize("n,k,P,tip", [(6000, 136, 3, -1), (12_000, 256, 4, -1), (16_384, 512, 3, -1), (20_000, 256, 4, 0),
-                                       (40_000, 512, 4, 320)])
+                                       (40_000, 512, 4, 320), (14_000, 350, 3, -1)])
 def test_wide_partitioned_solve(spk, oracle, n, k, P, tip):
     """Several partitions: spike tips through the sweeps, reduced blocks through the LU kernel, window corrections.
     tip = -1: whole-partition windows (SaP-style exact); otherwise truncated windows on a dominant band."""
@@ -69,7 +69,7 @@ def test_wide_partitioned_solve(spk, oracle, n, k, P, tip):
     S.close()
 
 
-@pytest.mark.parametrize("n,k,P,nrhs", [(8192, 256, 2, 32), (16_384, 512, 3, 32), (5000, 136, 2, 9), (9000, 512, 2, 17)])
+@pytest.mark.parametrize("n,k,P,nrhs", [(8192, 256, 2, 32), (16_384, 512, 3, 32), (5000, 136, 2, 9), (9000, 512, 2, 17), (7000, 350, 2, 20)])
 def test_wide_multi_rhs(spk, oracle, n, k, P, nrhs):
     """BASELINE config 5 in small: 32 right-hand sides, solved 16 columns per CTA on the tensor cores."""
     a = oracle.gen_band(n, k)
