@@ -9,9 +9,13 @@
 
 int spk_solve_dev(spk_ctx* c, const double* b, double* x);
 
-// out[v] = <V_v, w>, v < nv <= 8, all in one pass over w (warp-shuffle + atomic accumulation)
+// Inner products <V_v, w>, v < nv <= 8, in one pass over w -- DETERMINISTIC: every block reduces its share in a fixed
+// order (registers -> warp shuffles -> shared memory, warps in index order) and writes one partial per vector; k_dot_finish
+// adds the partials of all blocks in a fixed order.  (The first version accumulated with atomicAdd: the rounding, and with
+// it an iteration count at the convergence threshold, depended on the order the blocks happened to finish in.)
 __global__ void k_multi_dot(const double* __restrict__ V, int64_t ld, int nv, const double* __restrict__ w, int64_t n,
-                            double* __restrict__ out) {
+                            double* __restrict__ partial) {
+  __shared__ double sh[8][8];   // [warp][vector]
   double acc[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v) acc[v] = 0.0;
@@ -22,11 +26,31 @@ __global__ void k_multi_dot(const double* __restrict__ V, int64_t ld, int nv, co
   }
 #pragma unroll
   for (int v = 0; v < 8; ++v) {
-    if (v < nv) {
-      double s = acc[v];
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if ((threadIdx.x & 31) == 0) atomicAdd(out + v, s);
+    double s = acc[v];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][v] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s = 0.0;
+    for (int wp = 0; wp < (int)(blockDim.x >> 5); ++wp) s += sh[wp][threadIdx.x];
+    partial[(size_t)blockIdx.x * 8 + threadIdx.x] = s;
+  }
+}
+// out[v] = sum over blocks of partial[b][v], one block of 256 threads, fixed order (strided sums, then a shared-memory tree)
+__global__ void k_dot_finish(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ out) {
+  __shared__ double sh[256];
+  for (int v = 0; v < nv; ++v) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(size_t)b * 8 + v];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
     }
+    if (threadIdx.x == 0) out[v] = sh[0];
+    __syncthreads();
   }
 }
 // w -= sum_v h[v] V_v
@@ -52,6 +76,7 @@ namespace {
 struct Kry {
   spk_ctx* c; int64_t n; int grid;
   double* hdev;  // 64 doubles scratch on device (c->d_scalar)
+  double* part;  // grid x 8 block partials of the inner products
   int fail = 0;
   void check() { if (cudaGetLastError() != cudaSuccess) fail = 1; c->launches++; }
   int amul(const double* x, double* y) {
@@ -62,8 +87,8 @@ struct Kry {
   void dots(const double* V, int64_t ld, int nv, const double* w, double* host) {
     for (int v0 = 0; v0 < nv; v0 += 8) {
       const int m = nv - v0 < 8 ? nv - v0 : 8;
-      cudaMemsetAsync(hdev + v0, 0, sizeof(double) * m, c->stream);
-      k_multi_dot<<<grid, 256, 0, c->stream>>>(V + (int64_t)v0 * ld, ld, m, w, n, hdev + v0);
+      k_multi_dot<<<grid, 256, 0, c->stream>>>(V + (int64_t)v0 * ld, ld, m, w, n, part);
+      k_dot_finish<<<1, 256, 0, c->stream>>>(part, grid, m, hdev + v0);
       check();
     }
     cudaMemcpyAsync(host, hdev, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream);
@@ -74,8 +99,8 @@ struct Kry {
   void dots_dev(const double* V, int64_t ld, int nv, const double* w, int off) {
     for (int v0 = 0; v0 < nv; v0 += 8) {
       const int m = nv - v0 < 8 ? nv - v0 : 8;
-      cudaMemsetAsync(hdev + off + v0, 0, sizeof(double) * m, c->stream);
-      k_multi_dot<<<grid, 256, 0, c->stream>>>(V + (int64_t)v0 * ld, ld, m, w, n, hdev + off + v0);
+      k_multi_dot<<<grid, 256, 0, c->stream>>>(V + (int64_t)v0 * ld, ld, m, w, n, part);
+      k_dot_finish<<<1, 256, 0, c->stream>>>(part, grid, m, hdev + off + v0);
       check();
     }
   }
@@ -91,7 +116,9 @@ struct Kry {
 int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, const double* b, double* x, int* its,
                    double* rnorm, int* converged) {
   const int64_t n = c->L.n;
-  Kry K{c, n, c->sm_count * 8, c->d_scalar};
+  Kry K{c, n, c->sm_count * 8, c->d_scalar, nullptr};
+  struct PartGuard { double*& p; ~PartGuard() { if (p) cudaFree(p); } } part_guard{K.part};
+  SPK_CUDA(c, cudaMalloc(&K.part, sizeof(double) * (size_t)K.grid * 8));
   const int m = restart > 0 ? restart : 30;
   if (m > 60) { SPK_SET_ERR(c, "restart %d too large (max 60)", m); return SPK_ERR_ARG; }
   int it = 0, conv = 0;

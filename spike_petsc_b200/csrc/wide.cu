@@ -81,7 +81,7 @@ static int run_jobs(spk_ctx* c, const std::vector<WideSweepJob>& jobs, int max_c
     SPK_CUDA(c, cudaMemcpyAsync(dev, jobs.data(), sizeof(WideSweepJob) * jobs.size(), cudaMemcpyHostToDevice, c->stream));
     mine = jobs;
   }
-  return spk_wide_sweep(c, dev, (int)jobs.size(), max_cols);
+  return spk_wide_sweep(c, dev, (int)jobs.size(), max_cols, site == WJ_MAIN || site == WJ_CORR);
 }
 
 // --------------------------------------------------------------------------------------------

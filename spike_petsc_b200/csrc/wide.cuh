@@ -73,4 +73,4 @@ struct WideSweepJob {
   int pad;
 };
 int spk_wide_lu(spk_ctx* c, double* band, const int64_t* d_pstart, int P);                 // wide_lu.cu
-int spk_wide_sweep(spk_ctx* c, const WideSweepJob* d_jobs, int njobs, int max_cols);       // wide_sweep.cu
+int spk_wide_sweep(spk_ctx* c, const WideSweepJob* d_jobs, int njobs, int max_cols, bool long_jobs);   // wide_sweep.cu (long_jobs: partition sweeps / corrections)

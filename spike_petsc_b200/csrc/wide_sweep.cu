@@ -44,10 +44,11 @@ __device__ __forceinline__ double2 ldnc_v2(const double* p) {
 // instructions per tile -- 64-bit multiplies, slot arithmetic, null-pointer branches -- made the kernel issue bound at
 // 3x its DMMA time; see profiles/r02_summary.md.)  The factor tiles of the coming PFT positions sit in a register ring
 // (255 registers per thread, 8 warps; a spilled ring slot would turn its load into a synchronous wait for HBM).
-template <int NSLOT, int NCT, int PFT>
+template <int NSLOT, int NCT, int PFT, bool SR>
 __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArgs a) {
   __shared__ __align__(16) double Cbuf[8][NCT][64];
   __shared__ __align__(16) double Ybuf[2][8][NCT][64];
+  extern __shared__ __align__(128) double ws_ring[];   // [8 warps][PFT tiles][64]: the factor-tile ring, filled by cp.async
   const WideSweepJob job = a.jobs[blockIdx.x];
   const int col0 = blockIdx.y * 8 * NCT;
   if (col0 >= job.ncols) return;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
   constexpr int NIT = 8 * NSLOT;                       // factor tiles per warp and step
   constexpr int GS = (NSLOT % 4 == 0) ? 4 : 2;         // window rows interleaved in the update loop (independent DMMA chains)
   static_assert(NIT % PFT == 0 && NSLOT % GS == 0 && PFT % GS == 0, "ring depth must divide the tiles per step");
+  static_assert(PFT <= NIT, "a refill reaches at most into the next step");
   const long long lo = job.sb_lo, hi = job.sb_hi;
   // tile n of the update loop -> (window row d = 1..NSLOT, k): groups of GS rows, k-major inside a group
   auto d_of = [](int n) -> int { return (n / (8 * GS)) * GS + (n % GS) + 1; };
@@ -88,7 +90,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
   };
 
   double2 acc[NSLOT][NCT];
-  double2 ring[PFT];
+  // The factor-tile ring of a warp, PFT tiles deep, in one of two places (SR):
+  //  * SHARED memory, private to the warp: lane l copies bytes [32 l, 32 l + 16) of a tile with cp.async and reads the same
+  //    bytes back, so a cp.async.wait_group is all the synchronisation there is; 32-48 tiles in flight per warp without
+  //    holding a register.  For the long jobs (partition sweeps, corrections), where a 16-tile register ring left the kernel
+  //    waiting on the long scoreboard: 3.84 -> 2.77 ms at C5.
+  //  * REGISTERS (16 tiles): for the many short jobs of the spike tips and reduced inverses (8-36 steps, 32 column groups
+  //    per job), where the deeper ring's fill and drain per sweep cost more than its depth buys (0.63 vs 0.86 ms).
+  double2 ring[SR ? 1 : PFT];
+  double* const rbase = ws_ring + (size_t)warp * PFT * 64 + 2 * lane;
+  const uint32_t rbase_s = smem_u32(rbase);
+  constexpr int NG = PFT / GS;   // groups in flight
+  auto ring_fill = [&](int slot, const double* src) {
+    if (SR) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rbase_s + (uint32_t)slot * 512u), "l"(src) : "memory");
+    else ring[SR ? 0 : slot] = ldnc_v2(src);
+  };
+  auto ring_commit = [&]() { if (SR) asm volatile("cp.async.commit_group;" ::: "memory"); };
   const double* pd[NSLOT];   // run of window row d+1 at the current step
   const double* pn[NSLOT];   // ... at the next step
   long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -105,12 +122,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
 #pragma unroll
     for (int n0 = 0; n0 < NIT; n0 += GS) {
       double2 fa[GS], yb[NCT];
+      if (SR) asm volatile("cp.async.wait_group %0;" ::"n"(NG - 1) : "memory");   // the group of this iteration's tiles has landed
 #pragma unroll
       for (int qi = 0; qi < GS; ++qi) {
-        const int n = n0 + qi;
-        fa[qi] = ring[n % PFT];
-        const int nn = n + PFT;   // refill the ring slot with the tile PFT positions ahead (possibly of the next step)
-        ring[n % PFT] = (nn < NIT) ? ldnc_v2(pd[d_of(nn) - 1] + 64 * k_of(nn)) : ldnc_v2(pn[d_of(nn - NIT) - 1] + 64 * k_of(nn - NIT));
+        const int n = n0 + qi, nn = n + PFT;
+        if (SR) fa[qi] = *reinterpret_cast<const double2*>(rbase + (n % PFT) * 64);
+        else {   // register ring: the slot is renamed into the operand and refilled at once
+          fa[qi] = ring[SR ? 0 : n % PFT];
+          ring_fill(n % PFT, (nn < NIT) ? pd[d_of(nn) - 1] + 64 * k_of(nn) : pn[d_of(nn - NIT) - 1] + 64 * k_of(nn - NIT));
+        }
       }
       const int k = k_of(n0);
 #pragma unroll
@@ -123,6 +143,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
       for (int ct = 0; ct < NCT; ++ct)
 #pragma unroll
         for (int qi = 0; qi < GS; ++qi) dmma884(nxt[d_of(n0 + qi) - 1][ct].x, nxt[d_of(n0 + qi) - 1][ct].y, fa[qi].y, yb[ct].y);
+      // refill the slots just consumed (the DMMAs above have read them) with the tiles PFT positions ahead, possibly of
+      // the next step; one group per iteration
+      if (SR) {
+#pragma unroll
+        for (int qi = 0; qi < GS; ++qi) {
+          const int n = n0 + qi, nn = n + PFT;
+          ring_fill(n % PFT, (nn < NIT) ? pd[d_of(nn) - 1] + 64 * k_of(nn) : pn[d_of(nn - NIT) - 1] + 64 * k_of(nn - NIT));
+        }
+        ring_commit();
+      }
     }
 #pragma unroll
     for (int d = 0; d < NSLOT; ++d)
@@ -148,7 +178,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
     set_runs(pd, I0);
     set_runs(pn, I0 + 1);
 #pragma unroll
-    for (int n = 0; n < PFT; ++n) ring[n] = ldnc_v2(pd[d_of(n) - 1] + 64 * k_of(n));
+    for (int n = 0; n < PFT; ++n) {
+      ring_fill(n, pd[d_of(n) - 1] + 64 * k_of(n));
+      if (n % GS == GS - 1) ring_commit();
+    }
     double2 dv[8];
     {
       const double* dsrc = (I0 < hi) ? diag_run(I0) : zrun;
@@ -206,6 +239,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
     }
   }
   WS_ADD(3);
+  if (SR) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   // =========================================== backward ==========================================
   {
@@ -224,7 +258,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
     set_runs(pd, I0);
     set_runs(pn, I0 - 1);
 #pragma unroll
-    for (int n = 0; n < PFT; ++n) ring[n] = ldnc_v2(pd[d_of(n) - 1] + 64 * k_of(n));
+    for (int n = 0; n < PFT; ++n) {
+      ring_fill(n, pd[d_of(n) - 1] + 64 * k_of(n));
+      if (n % GS == GS - 1) ring_commit();
+    }
     for (long long I = I0; I >= lo; --I) {
       const int par = (int)(I & 1);
       WS_ADD(6);
@@ -252,18 +289,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wide_sweep(const WideSweepArg
     }
   }
   WS_ADD(6);
+  if (SR) asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) for (int q = 0; q < 8; ++q) a.trace[q] = tr[q];
 }
 
-template <int NSLOT, int NCT, int PFT>
-static int launch_ws(spk_ctx* c, const WideSweepArgs& a, int njobs, int groups) {
-  k_wide_sweep<NSLOT, NCT, PFT><<<dim3(njobs, groups), WS_THREADS, 0, c->stream>>>(a);
+template <int NSLOT, int NCT, int PFT, bool SR>
+static int launch_ws2(spk_ctx* c, const WideSweepArgs& a, int njobs, int groups) {
+  const size_t smem = SR ? sizeof(double) * (size_t)WS_WARPS * PFT * 64 : 0;
+  if (SR) SPK_CUDA(c, cudaFuncSetAttribute(k_wide_sweep<NSLOT, NCT, PFT, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_wide_sweep<NSLOT, NCT, PFT, SR><<<dim3(njobs, groups), WS_THREADS, smem, c->stream>>>(a);
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }
+// long jobs: shared-memory ring, as deep as a step allows (a refill reaches at most into the next step); short jobs: 16 registers-tiles
+template <int NSLOT, int NCT>
+static int launch_ws(spk_ctx* c, const WideSweepArgs& a, int njobs, int groups, bool long_jobs) {
+  constexpr int DEEP = (8 * NSLOT <= 48) ? 8 * NSLOT : 32;
+  return long_jobs ? launch_ws2<NSLOT, NCT, DEEP, true>(c, a, njobs, groups) : launch_ws2<NSLOT, NCT, 16, false>(c, a, njobs, groups);
+}
 
 // run the jobs (device array); max_cols = the largest ncols among them
-int spk_wide_sweep(spk_ctx* c, const WideSweepJob* d_jobs, int njobs, int max_cols) {
+int spk_wide_sweep(spk_ctx* c, const WideSweepJob* d_jobs, int njobs, int max_cols, bool long_jobs) {
   if (njobs <= 0 || max_cols <= 0) return SPK_OK;
   WideSweepArgs a; a.jobs = d_jobs; a.tpr = c->L.tpr; a.kts = c->L.kt; a.KB = c->kb; a.zero = c->wide_zero;
   a.trace = (c->lu_trace && d_jobs == (const WideSweepJob*)c->d_wjobs + (size_t)3 * c->wjobs_cap) ? (long long*)c->lu_trace + 128 : nullptr;   // (debug: the partition sweeps)
@@ -278,12 +324,12 @@ int spk_wide_sweep(spk_ctx* c, const WideSweepJob* d_jobs, int njobs, int max_co
     const int nj = std::min(njobs - j0, 65535);
     int rc;
     switch (nslot * 2 + (one ? 0 : 1)) {
-      case 8: rc = launch_ws<4, 1, 16>(c, b, nj, groups); break;
-      case 9: rc = launch_ws<4, 2, 16>(c, b, nj, groups); break;
-      case 12: rc = launch_ws<6, 1, 16>(c, b, nj, groups); break;
-      case 13: rc = launch_ws<6, 2, 16>(c, b, nj, groups); break;
-      case 16: rc = launch_ws<8, 1, 16>(c, b, nj, groups); break;
-      case 17: rc = launch_ws<8, 2, 16>(c, b, nj, groups); break;
+      case 8: rc = launch_ws<4, 1>(c, b, nj, groups, long_jobs); break;
+      case 9: rc = launch_ws<4, 2>(c, b, nj, groups, long_jobs); break;
+      case 12: rc = launch_ws<6, 1>(c, b, nj, groups, long_jobs); break;
+      case 13: rc = launch_ws<6, 2>(c, b, nj, groups, long_jobs); break;
+      case 16: rc = launch_ws<8, 1>(c, b, nj, groups, long_jobs); break;
+      case 17: rc = launch_ws<8, 2>(c, b, nj, groups, long_jobs); break;
       default: SPK_SET_ERR(c, "wide sweep: unsupported window of %d super-blocks", c->kb); return SPK_ERR_UNSUPPORTED;
     }
     if (rc) return rc;

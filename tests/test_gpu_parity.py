@@ -433,6 +433,29 @@ def test_krylov_iteration_parity(spk, oracle, method):
     S.close()
 
 
+@pytest.mark.parametrize("method", ["gmres", "bcgs"])
+def test_krylov_runs_are_bit_identical(spk, method):
+    """The inner products of the device Krylov loop are reduced in a fixed order (block partials + one finishing block,
+    csrc/krylov.cu), so iteration count, residual norm and solution of repeated runs are bit-identical."""
+    n, k = 20_000, 12
+    A = _sparse_case(n, k, seed=33, extra=4)
+    b = A @ np.linspace(0.5, 1.5, n)
+    first = None
+    for rep in range(4):
+        S = spk.Spike(partitions=8, tip_tiles=-1)
+        S.set_band_csr(A.indptr, A.indices, A.data, 6, 1.0)            # a narrower band than the matrix: a real preconditioner
+        S.set_operator_csr(A.indptr, A.indices, A.data)
+        S.factor()
+        x, its, rn, conv = S.krylov(b, spk.GMRES if method == "gmres" else spk.BCGS, rtol=1e-10)
+        S.close()
+        assert conv and its > 2
+        if first is None:
+            first = (x.copy(), its, rn)
+        else:
+            assert its == first[1] and rn == first[2]
+            np.testing.assert_array_equal(x, first[0])
+
+
 def test_reordered_solve_end_to_end(spk, oracle):
     """testbed2 flow (src/testbed2.c:110-132) through KSPREORDER semantics (src/kspreorder.c:17-24,
     122-127): b = A u, permute operators and vectors, SPIKE-preconditioned BiCGStab, un-permute."""
