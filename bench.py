@@ -431,15 +431,18 @@ def c4_block(args):
     S.set_operator_csr(ia, ja, a, rowperm=rp, colperm=cp)
     S.factor()
     b = np.ascontiguousarray((A @ np.ones(n))[rp])
-    t0 = time.perf_counter()
-    x, its, rn, conv = S.krylov(b, method=sp.BCGS, rtol=1e-5, maxit=500)
-    t_kry = time.perf_counter() - t0
+    t_kry_all = []
+    for _ in range(2):   # the first call pays one-time costs (kernel loading, buffer growth); both are reported
+        t0 = time.perf_counter()
+        x, its, rn, conv = S.krylov(b, method=sp.BCGS, rtol=1e-5, maxit=500)
+        t_kry_all.append(time.perf_counter() - t0)
+    t_kry = min(t_kry_all)
     info = S.view()
     xu = np.empty(n); xu[cp] = x
     S.close()
     return {"workload": "synthetic sparse nonsymmetric N=2M nnz~22M, WBM (matching known by construction) + RCM stand-in for MC73, PCBANDED(50,0.95), BiCGStab rtol 1e-5",
             "k": k, "frac": f, "iterations": its, "converged": bool(conv), "err_per_entry": float(np.linalg.norm(xu - 1.0) / np.sqrt(n)),
-            "factor_ms": info["factor_ms"], "krylov_ms_host_buffers": t_kry * 1e3, "band_select_and_pack_s": t_pack,
+            "factor_ms": info["factor_ms"], "krylov_ms_host_buffers": t_kry * 1e3, "krylov_ms_first_call": t_kry_all[0] * 1e3, "band_select_and_pack_s": t_pack,
             "ordering_host_s": t_ord, "generator_s": t_gen, "partitions": info["partitions"],
             "awbm_gpu": {"ms_host_csr_in_perm_out": t_awbm * 1e3, "device_rounds": int(a_stats[0]), "matched_on_device": int(a_stats[1]),
                          "finished_on_host": int(a_stats[2] + a_stats[3]), "recovers_row_scramble": bool((a_match == R).all())}}
