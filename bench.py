@@ -493,7 +493,9 @@ def run_ours(args):
                        "parallelism": f"row-block x{world}, spike-tip exchange over {r['exchange']}" if world > 1 else "row-block x1",
                        "l2": "inputs (band >> 126 MB L2) are re-read from HBM every step; nothing is cached between steps",
                        "timing": ("W warm-up steps, then the K steps back to back inside one barrier+synchronize bracket, CUDA events, max over ranks; "
-                                  "step_ms_all from events between the steps; stage_ms = the engine's event timers of the last timed step") if cfg["k"] <= 128 else
+                                  "step_ms_all from events between the steps; stage_ms = the engine's event timers of the last timed step; the spike-tip stage "
+                                  "runs on the engine's side stream next to the solve's partition sweeps (joined before the reduced solve), so "
+                                  "factor_ms + solve_ms and the sum of stage_ms exceed ms_per_step by the overlap") if cfg["k"] <= 128 else
                                  ("every step in its own barrier+synchronize bracket (the in-place factorisation needs the band regenerated between steps, "
                                   "outside the brackets); value = mean of the K brackets, max over ranks")},
             "rel_err_vs_exact_u": r["relerr"], "step_ms_all": r["step_ms_all"], "factor_ms": r["factor_ms"], "solve_ms": r["solve_ms"],

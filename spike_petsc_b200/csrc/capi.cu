@@ -42,6 +42,34 @@ static const char* const k_stage_name[8] = {"spike:tip_windows", "spike:band_lu"
                                             "spike:reduced_solve", "spike:corrections", "spike:stage6", "spike:stage7"};
 #define STAGE_BEGIN(c, i) do { nvtxRangePushA(k_stage_name[i]); cudaEventRecord((c)->evst[i][0], (c)->stream); } while (0)
 #define STAGE_END(c, i) do { cudaEventRecord((c)->evst[i][1], (c)->stream); (c)->stage_timed[i] = 1; nvtxRangePop(); } while (0)
+
+// Side stream of the narrow-band path.  The spike tips and reduced blocks (three 13-step Gauss-Jordan launches, latency
+// chains that need only the last window of every factored partition) are the one stage of a factorisation whose
+// results nothing needs before the reduced solve: factor phases 1 / 2 queue them on c->side behind an event of the
+// band LU, so that the first solve's partition sweeps on c->stream do not wait for them.  Every consumer of V^(b),
+// W^(t) or the reduced blocks calls side_join() first (the reduced solve; the boundary getters); entry points that
+// replace or modify the band join as well.  Measured (tools/side_ab.py, profiles/r02_side_stream_ab.log): the tip
+// kernels should run BEFORE the sweep CTAs fill the SMs -- queued behind the sweeps they slow them by more than
+// they take -- which is the order the hardware picks when both are eligible at the end of the LU.
+// SPIKE_B200_SIDE_STREAM=0 keeps everything on c->stream.
+static inline int side_join(spk_ctx* c) {
+  if (c->side_pending) { cudaStreamWaitEvent(c->stream, c->ev_join, 0); c->side_pending = 0; }
+  return SPK_OK;
+}
+struct SideScope {   // launches between construction and destruction go to the side stream, behind everything queued on c->stream so far
+  spk_ctx* c; cudaStream_t main; bool on;
+  SideScope(spk_ctx* c_, bool enable) : c(c_), main(c_->stream), on(false) {
+    if (!enable || !c->side) return;
+    if (cudaEventRecord(c->ev_fork, c->stream) != cudaSuccess || cudaStreamWaitEvent(c->side, c->ev_fork, 0) != cudaSuccess) { cudaGetLastError(); return; }
+    c->stream = c->side; on = true;
+  }
+  ~SideScope() {
+    if (!on) return;
+    cudaEventRecord(c->ev_join, c->side);
+    c->stream = main; c->side_pending = 1;
+  }
+};
+extern "C" void spk_side_join(spk_ctx* c) { if (c) side_join(c); }   // for the other translation units (peer.cu)
 struct NvtxScope { explicit NvtxScope(const char* n) { nvtxRangePushA(n); } ~NvtxScope() { nvtxRangePop(); } };
 
 extern "C" const char* spk_version(void) { return "spike_b200 0.1 (sm_100a, fp64 DMMA)"; }
@@ -102,6 +130,18 @@ extern "C" int spk_create(spk_ctx** out, const spk_opts* opts) {
     return SPK_ERR_CUDA;
   }
   for (int i = 0; i < 8; ++i) { cudaEventCreate(&c->evst[i][0]); cudaEventCreate(&c->evst[i][1]); }
+  const char* sidev = getenv("SPIKE_B200_SIDE_STREAM");
+  if (!sidev || sidev[0] != '0') {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = the least urgent: the tips yield to the sweeps whenever both wait for SM slots
+    if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      if (c->side) cudaStreamDestroy(c->side);
+      c->side = nullptr;
+    }
+  }
   *out = c;
   return SPK_OK;
 }
@@ -110,8 +150,10 @@ extern "C" int spk_destroy(spk_ctx** pc) {
   if (!pc || !*pc) return SPK_OK;
   spk_ctx* c = *pc;
   cudaSetDevice(c->opts.device);
+  side_join(c);
   cudaStreamSynchronize(c->stream);
   free_band(c);
+  if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); c->side = nullptr; }
   cudaFree(c->d_boost); cudaFree(c->d_scalar);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evs0); cudaEventDestroy(c->evs1);
   for (int i = 0; i < 8; ++i) { cudaEventDestroy(c->evst[i][0]); cudaEventDestroy(c->evst[i][1]); }
@@ -132,6 +174,7 @@ static int plan(spk_ctx* c, int64_t n, int k) {
     return SPK_ERR_UNSUPPORTED;
   }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  side_join(c);
   free_band(c);
   BandLayout& L = c->L;
   const bool wide = kt > SPK_MAX_KT;
@@ -559,6 +602,7 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
   int rc = SPK_OK;
   if ((phase == 0 || phase == 10) && spk_peer_failed(c)) return SPK_ERR_STATE;
+  if (phase == 0 || phase == 10) side_join(c);   // tips of an earlier factorisation still read what this one rewrites
   if (phase == 0) {
     if (c->factored && spk_lu_source(c) == c->band) { SPK_SET_ERR(c, "band already factored (the factorisation is in place unless spk_keep_original(ctx,1) kept the unfactored band)"); return SPK_ERR_STATE; }
     c->factored = 0;
@@ -591,24 +635,28 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
     // local tips and reduced blocks; the boundary block rides along when the neighbour's W^(t) is already here
     const bool has_right = c->opts.rank + 1 < c->opts.nranks;
     const bool with_boundary = has_right && c->have_remote_wt;
-    STAGE_BEGIN(c, 2); rc = spk_launch_tips(c, with_boundary ? 3 : 0, 0); STAGE_END(c, 2);
-    if (rc) return rc;
-    if (with_boundary) c->boundary_done = 1;
-    if (!has_right || with_boundary) {
-      SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-      c->factored = 1; c->timed_factor = 1;
-      return spk_peer_note(c);
+    const bool done = !has_right || with_boundary;
+    {
+      SideScope side(c, !c->wide);   // everything up to the closing brace goes to the side stream (when there is one)
+      STAGE_BEGIN(c, 2); rc = spk_launch_tips(c, with_boundary ? 3 : 0, 0); STAGE_END(c, 2);
+      if (rc) return rc;
+      if (done) SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     }
+    if (with_boundary) c->boundary_done = 1;
+    if (done) { c->factored = 1; c->timed_factor = 1; return spk_peer_note(c); }
     return SPK_OK;
   }
   if (phase == 2) {  // after SPK_BND_REMOTE_WT has been set
-    if (!c->boundary_done) {
-      rc = spk_launch_tips(c, 1, 0);
-      if (rc) return rc;
-      c->boundary_done = 1;
+    {
+      SideScope side(c, !c->wide && (c->side_pending || !c->boundary_done));   // behind the local tips if those are still on the side stream
+      if (!c->boundary_done) {
+        rc = spk_launch_tips(c, 1, 0);
+        if (rc) return rc;
+        c->boundary_done = 1;
+      }
+      SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+      c->factored = 1; c->timed_factor = 1;
     }
-    SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    c->factored = 1; c->timed_factor = 1;
     return spk_peer_note(c);
   }
   SPK_SET_ERR(c, "bad factor phase %d", phase);
@@ -636,6 +684,7 @@ int spk_solve_dev(spk_ctx* c, const double* b, double* x) {
   STAGE_BEGIN(c, 3);
   rc = spk_launch_sweep(c, b, x, 1, c->L.n);
   STAGE_END(c, 3);
+  side_join(c);   // the reduced solve is the first consumer of the spike tips
   if (rc) return rc;
   if (c->P > 1) {
     STAGE_BEGIN(c, 4);
@@ -665,6 +714,7 @@ static int solve_multi_dev(spk_ctx* c, const double* b, double* x, int nrhs) {
   STAGE_BEGIN(c, 3);
   rc = spk_launch_msweep(c, b, x, nrhs, n);
   STAGE_END(c, 3);
+  side_join(c);
   if (rc) return rc;
   if (c->P > 1) {
     // scratch for all columns: coupling right-hand sides (2*P*kp each) and the forward results of the window sweeps
@@ -727,6 +777,7 @@ extern "C" int spk_solve_phase(spk_ctx* c, int phase, const double* b, double* x
   if (!c->cur_x) { SPK_SET_ERR(c, "solve phase %d without phase 0", phase); return SPK_ERR_STATE; }
   nrhs = c->cur_nrhs;
   if (phase == 1) {
+    side_join(c);
     STAGE_BEGIN(c, 4);
     if (nrhs >= 2) {
       rc = ensure_multi_scratch(c, nrhs);
@@ -912,6 +963,7 @@ extern "C" int spk_view(spk_ctx* c, spk_info* info) {
   memset(info, 0, sizeof(*info));
   if (!c->have_band) return SPK_OK;
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  side_join(c);
   SPK_CUDA(c, cudaStreamSynchronize(c->stream));
   { const int wrc = spk_wide_check(c); if (wrc) return wrc; }
   SPK_CUDA(c, cudaMemcpy(&c->boosted, c->d_boost, sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -946,6 +998,7 @@ extern "C" int spk_get_boundary(spk_ctx* c, int which, double* buf) {
   double* p; size_t n; int out;
   if (spk_bnd_desc(c, which, &p, &n, &out) || !out) { SPK_SET_ERR(c, "spk_get_boundary: bad or unavailable item %d", which); return SPK_ERR_ARG; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  if (which == SPK_BND_WT_FIRST) side_join(c);   // W^(t) may come from the side stream (factor phases 0 + 1)
   SPK_CUDA(c, cudaMemcpyAsync(buf, p, sizeof(double) * n, c->opts.mem == SPK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
   if (c->opts.mem != SPK_MEM_DEVICE) SPK_CUDA(c, cudaStreamSynchronize(c->stream));
   return SPK_OK;
@@ -967,12 +1020,13 @@ extern "C" int spk_debug_set_lu_trace(spk_ctx* c, void* dev_buf) { if (!c) retur
 // bench.py hooks (not in the public header): address of the device band so a pristine copy can be
 // restored between timed steps, and a reset of the "factored" flag after such a restore.
 extern "C" void* spk_debug_band_ptr(spk_ctx* c) { return c ? (void*)c->band : nullptr; }
-extern "C" int spk_debug_reset_factored(spk_ctx* c) { if (!c) return SPK_ERR_ARG; c->factored = 0; c->launches = 0; return SPK_OK; }
+extern "C" int spk_debug_reset_factored(spk_ctx* c) { if (!c) return SPK_ERR_ARG; side_join(c); c->factored = 0; c->launches = 0; return SPK_OK; }
 // bench.py hook: regenerate the synthetic band in place (same layout / partitions / mailboxes), so an in-place
 // factorisation can be timed again without re-planning the context
 extern "C" int spk_debug_regen_synthetic(spk_ctx* c, uint64_t seed, double delta) {
   if (!c || !c->have_band) return SPK_ERR_STATE;
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  side_join(c);
   int rc = spk_launch_generate(c, seed, delta);
   if (rc) return rc;
   if (c->orig) SPK_CUDA(c, cudaMemcpyAsync(c->orig, c->band, sizeof(double) * (size_t)c->L.elems(), cudaMemcpyDeviceToDevice, c->stream));
@@ -984,6 +1038,7 @@ extern "C" int spk_debug_restore_band(spk_ctx* c) {
   if (!c || !c->orig) return SPK_ERR_STATE;
   if (c->rscale) { SPK_SET_ERR(c, "restore_band on an equilibrated context would drop the scaling"); return SPK_ERR_STATE; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  side_join(c);
   SPK_CUDA(c, cudaMemcpyAsync(c->band, c->orig, sizeof(double) * (size_t)c->L.elems(), cudaMemcpyDeviceToDevice, c->stream));
   c->factored = 0; c->launches = 0;
   return SPK_OK;

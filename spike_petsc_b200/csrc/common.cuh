@@ -41,6 +41,11 @@ struct CsrDev {
 struct spk_ctx {
   spk_opts opts;
   cudaStream_t stream;
+  // side stream (capi.cu): the spike tips and reduced blocks of a narrow-band factorisation run here, next to the
+  // first solve's partition sweeps on `stream`; the reduced solve joins on ev_join.  nullptr = everything on `stream`.
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  int side_pending;     // work recorded in ev_join has not been joined into `stream` yet
   int sm_count;
   BandLayout L;
   int have_band, factored, keep_orig;
@@ -121,6 +126,7 @@ struct spk_ctx {
 void spk_peer_release(spk_ctx* c);   // peer.cu
 int spk_peer_failed(spk_ctx* c);     // an earlier exchange expired (pinned mirror, no sync)
 int spk_peer_note(spk_ctx* c);       // enqueue the mirror copy of the error word
+extern "C" void spk_side_join(spk_ctx* c);   // capi.cu: make c->stream wait for the side-stream work of the last factorisation
 // band the LU and the tip windows read: the kept original if there is one that still equals the unfactored band
 static inline double* spk_lu_source(spk_ctx* c) { return (c->orig && !c->rscale) ? c->orig : c->band; }
 int spk_bnd_desc(spk_ctx* c, int which, double** ptr, size_t* count, int* is_out);   // capi.cu

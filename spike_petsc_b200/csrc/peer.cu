@@ -182,6 +182,7 @@ extern "C" int spk_peer_post(spk_ctx* c, int which) {
   double* p; size_t n; int out;
   if (spk_bnd_desc(c, which, &p, &n, &out) || !out) { SPK_SET_ERR(c, "spk_peer_post: item %d unavailable", which); return SPK_ERR_ARG; }
   SPK_CUDA(c, cudaSetDevice(c->opts.device));
+  if (which == SPK_BND_WT_FIRST) spk_side_join(c);   // W^(t) may have been computed on the side stream (capi.cu)
   const PeerLayout L = peer_layout(c);
   const unsigned long long seq = ++c->peer_seq_out[ch];
   const int slot = (int)(seq & 1ull);

@@ -249,6 +249,8 @@ template <int KT, int NST>
 static int launch_sweep_kt(spk_ctx* c, const SweepArgs& a, int grid) {
   const size_t smem = sizeof(SweepSmem<KT, NST>);
   SPK_CUDA(c, cudaFuncSetAttribute(k_sweep<KT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // largest shared-memory carve-out: the CTAs of the spike-tip kernels (side stream, capi.cu) fit next to two resident sweep CTAs
+  SPK_CUDA(c, cudaFuncSetAttribute(k_sweep<KT, NST>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   k_sweep<KT, NST><<<grid, SW_THREADS, smem, c->stream>>>(a);
   SPK_KERNEL_CHECK(c);
   return SPK_OK;

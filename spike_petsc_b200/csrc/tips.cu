@@ -455,9 +455,11 @@ static cudaError_t launch_tip_gj(spk_ctx* c, int grid, const TipArgs& t) {
   cudaError_t e;
   if (t.which == 0) {
     e = cudaFuncSetAttribute(k_spike_tip_gj2<KT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spike_tip_gj2<KT, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) k_spike_tip_gj2<KT, 0><<<grid, (KT + 1) * 32, smem, c->stream>>>(t);
   } else {
     e = cudaFuncSetAttribute(k_spike_tip_gj2<KT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spike_tip_gj2<KT, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) k_spike_tip_gj2<KT, 1><<<grid, (KT + 1) * 32, smem, c->stream>>>(t);
   }
   return e;
@@ -466,6 +468,7 @@ template <int KT>
 static cudaError_t launch_red_gj(spk_ctx* c, int grid, const RedArgs& r) {
   const size_t smem = sizeof(GjSmem<KT>) + sizeof(double) * 64 * KT * KT;
   cudaError_t e = cudaFuncSetAttribute(k_reduced_factor_gj2<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reduced_factor_gj2<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   k_reduced_factor_gj2<KT><<<grid, (KT + 1) * 32, smem, c->stream>>>(r);
   return cudaSuccess;

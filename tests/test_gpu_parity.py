@@ -598,6 +598,44 @@ def test_repeated_runs_are_bit_identical(spk, oracle, n, k, P, nrhs):
         assert relerr(X[c], oracle.band_solve(lu, Bm[c])) < RTOL
 
 
+@pytest.mark.parametrize("n,k,P,nrhs", [(60_000, 100, 8, 1), (40_000, 50, 12, 1), (30_000, 37, 6, 5)])
+def test_side_stream_is_transparent(spk, oracle, n, k, P, nrhs, monkeypatch):
+    """The spike tips / reduced blocks of a narrow-band factorisation are queued on the context's side stream and joined
+    by their first consumer (capi.cu SideScope / side_join).  Whatever the caller does between spk_factor and the
+    solve -- nothing, a second factorisation from the kept original, spk_view, a second solve -- the solution is
+    bit-identical to the one with SPIKE_B200_SIDE_STREAM=0 (everything on one stream) and agrees with the oracle."""
+    a = oracle.gen_band(n, k)
+    U = np.stack([oracle.gen_vec(n, 40 + c) for c in range(nrhs)])
+    Bm = np.stack([oracle.band_mult(a, u) for u in U])
+    rhs = Bm if nrhs > 1 else Bm[0]
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SPIKE_B200_SIDE_STREAM", mode)
+        res = []
+        for flow in ("plain", "refactor", "view", "twice"):
+            S = spk.Spike(partitions=P, tip_tiles=0)
+            S.keep_original(True)
+            S.set_band_dense(a, k)
+            S.factor()
+            if flow == "refactor":
+                S.factor()                      # joins the first factorisation's tips before rewriting what they read
+            if flow == "view":
+                assert S.view()["factored"]
+            X = S.solve(rhs, nrhs=nrhs)
+            if flow == "twice":
+                np.testing.assert_array_equal(S.solve(rhs, nrhs=nrhs), X)
+            res.append(X)
+            S.close()
+        for X in res[1:]:
+            np.testing.assert_array_equal(X, res[0])
+        out[mode] = res[0]
+    np.testing.assert_array_equal(out["0"], out["1"])
+    lu, _ = oracle.band_lu(a)
+    X = out["1"] if nrhs > 1 else out["1"][None, :]
+    for c in range(nrhs):
+        assert relerr(X[c], oracle.band_solve(lu, Bm[c])) < RTOL
+
+
 # ------------------------------------------------------------------ bands whose spikes do not decay
 def _slow_decay_band(n):
     """shifted second difference tridiag(-1, 2.0001, -1): well conditioned (4e4), the no-pivot LU is stable, but the
