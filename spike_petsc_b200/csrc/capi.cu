@@ -87,7 +87,7 @@ static void free_band(spk_ctx* c) {
   F(c->RedPiv); F(c->work); F(c->gtip); F(c->xtip); F(c->xb); F(c->xt); F(c->corr);
   F(c->remoteWt); F(c->remoteGtop); F(c->remoteXbot); F(c->gtopOut); F(c->xtopRemote); F(c->xbBoundary); F(c->haloL); F(c->haloR);
   for (int i = 0; i < 4; ++i) { if (c->stage[i]) { cudaFree(c->stage[i]); c->stage[i] = nullptr; } c->stage_bytes[i] = 0; }
-  F(c->opA.ia); F(c->opA.ja); F(c->opA.a); F(c->rscale); F(c->cscale_base); c->cscale = nullptr; F(c->tips_mr); F(c->work_mr); c->nrhs_mr = 0;
+  F(c->opA.ia); F(c->opA.ja); F(c->opA.a); F(c->rscale); F(c->cscale_base); c->cscale = nullptr; F(c->tips_mr); F(c->work_mr); c->nrhs_mr = 0; F(c->kry_ws); c->kry_ws_bytes = 0;
   free(c->h_pstart); c->h_pstart = nullptr;
   spk_wide_free(c);
   spk_peer_release(c);   // the mailbox layout depends on kp

@@ -105,6 +105,7 @@ struct spk_ctx {
   double *rscale, *cscale;   // optional equilibration (spk_set_scaling): the factored band is diag(r) A diag(c)
   double *cscale_base;       // allocation behind cscale: [kp left-halo scales | n local | kp right-halo scales]
   void* stage[4]; size_t stage_bytes[4];   // grow-only staging for host-vector calls (capi.cu)
+  double* kry_ws; size_t kry_ws_bytes;     // grow-only Krylov workspace (krylov.cu: dot partials + basis / work vectors), released with the band
   // operator for Krylov
   CsrDev opA;
   // bookkeeping

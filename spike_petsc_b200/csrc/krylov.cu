@@ -117,18 +117,30 @@ int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, 
                    double* rnorm, int* converged) {
   const int64_t n = c->L.n;
   Kry K{c, n, c->sm_count * 8, c->d_scalar, nullptr};
-  struct PartGuard { double*& p; ~PartGuard() { if (p) cudaFree(p); } } part_guard{K.part};
-  SPK_CUDA(c, cudaMalloc(&K.part, sizeof(double) * (size_t)K.grid * 8));
   const int m = restart > 0 ? restart : 30;
   if (m > 60) { SPK_SET_ERR(c, "restart %d too large (max 60)", m); return SPK_ERR_ARG; }
+  // workspace kept in the context (grow-only, released with the band): [dot partials | basis or work vectors].  A PC /
+  // KSP glue calls this once per right-hand side; a cudaMalloc + cudaFree pair per call costs more than a C1 solve.
+  const size_t part_elems = ((size_t)K.grid * 8 + 63) & ~(size_t)63;
+  const size_t vec_elems = (size_t)n * (method == SPK_KSP_GMRES ? (size_t)(m + 2) : 7);
+  const size_t ws_bytes = sizeof(double) * (part_elems + vec_elems);
+  if (c->kry_ws_bytes < ws_bytes) {
+    if (c->kry_ws) { cudaStreamSynchronize(c->stream); cudaFree(c->kry_ws); c->kry_ws = nullptr; c->kry_ws_bytes = 0; }
+    if (cudaMalloc(&c->kry_ws, ws_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      SPK_SET_ERR(c, "Krylov workspace of %zu bytes (%s) does not fit", ws_bytes, method == SPK_KSP_GMRES ? "GMRES basis" : "BiCGStab vectors");
+      return SPK_ERR_NOMEM;
+    }
+    c->kry_ws_bytes = ws_bytes;
+  }
+  K.part = c->kry_ws;
+  double* const vecs = c->kry_ws + part_elems;
   int it = 0, conv = 0;
   double res = 0.0;
   int rc = SPK_OK;
   SPK_CUDA(c, cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, c->stream));
   if (method == SPK_KSP_GMRES) {
-    double *V = nullptr, *t = nullptr;
-    if (cudaMalloc(&V, sizeof(double) * (size_t)n * (m + 2)) != cudaSuccess) { SPK_SET_ERR(c, "GMRES basis of %d vectors does not fit", m + 1); return SPK_ERR_NOMEM; }
-    t = V + (size_t)n * (m + 1);
+    double *V = vecs, *t = V + (size_t)n * (m + 1);
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
     if ((rc = K.pc(b, V))) goto gdone;
     {
@@ -193,10 +205,8 @@ int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, 
     }
   gdone:
     cudaStreamSynchronize(c->stream);
-    cudaFree(V);
   } else {
-    double *r, *rh, *p, *v, *s, *t, *tmp;
-    SPK_CUDA(c, cudaMalloc(&r, sizeof(double) * (size_t)n * 7));
+    double *r = vecs, *rh, *p, *v, *s, *t, *tmp;
     rh = r + n; p = rh + n; v = p + n; s = v + n; t = s + n; tmp = t + n;
     SPK_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * (size_t)n * 2, c->stream));
     double rho = 1.0, alpha = 1.0, omega = 1.0;
@@ -236,7 +246,6 @@ int spk_krylov_run(spk_ctx* c, int method, int restart, double rtol, int maxit, 
     }
   bdone:
     cudaStreamSynchronize(c->stream);
-    cudaFree(r);
   }
   if (K.fail && rc == SPK_OK) { SPK_SET_ERR(c, "CUDA failure inside the Krylov loop: %s", cudaGetErrorString(cudaGetLastError())); rc = SPK_ERR_CUDA; }
   *its = it; *rnorm = res; *converged = conv;

@@ -114,6 +114,8 @@ CASES = [
     # n, k, partitions, tip_tiles (-1 = full windows), delta
     (4000, 10, 4, -1, 1.2),
     (100_000, 10, 0, 0, 1.2),      # BASELINE config[0] shape: N=100k K=10
+    (100_000, 10, 592, 12, 1.2),   # ... at the partitions / window bench.py runs it with (tools/side_ab.py sweep)
+    (100_000, 10, 592, 12, 1.0),
     (20_000, 50, 8, -1, 1.2),
     (20_001, 37, 5, -1, 1.2),      # ragged: n not a multiple of 8, k not a multiple of 8
     (60_000, 100, 12, -1, 1.2),
