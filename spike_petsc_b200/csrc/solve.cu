@@ -25,6 +25,19 @@
 
 enum { SWEEP_MAIN = 0, SWEEP_CORR = 1 };
 
+// -DSW_TRACE (tools/sweep_trace.py, tools/build_variant.sh): clock64 stamps of CTA 0, forward sweep iterations
+// 32..63, per role (near warp: 8 points, far warp 1: 4 points, copy warp: 3 points).  Not in the product build.
+#ifdef SW_TRACE
+#ifndef SW_TRACE_CTA
+#define SW_TRACE_CTA 0   // 0: partition sweep of partition 0; 2: correction job (partition 1, top window) -- the last launch wins
+#endif
+__device__ long long g_sw_trace[32][16];
+#define SW_TR(slot_) do { if (tr_on && (threadIdx.x & 31) == 0) g_sw_trace[it - 32][slot_] = clock64(); } while (0)
+extern "C" int spk_debug_sweep_trace(long long* out) { return cudaMemcpyFromSymbol(out, g_sw_trace, sizeof(g_sw_trace)) == cudaSuccess ? 0 : 1; }
+#else
+#define SW_TR(slot_) do { } while (0)
+#endif
+
 struct SweepArgs {
   const double* band; int tpr;
   const int64_t* pstart; int P;
@@ -125,18 +138,42 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT, SW_NST>& S, const SweepA
     unsigned st = ib % SW_NST;
     double2 yp = make_double2(0.0, 0.0);
     for (int it = 0; it < nrows; ++it) {
+#ifdef SW_TRACE
+      const bool tr_on = blockIdx.x == SW_TRACE_CTA && DIR > 0 && it >= 32 && it < 64 && ib == 0;
+#endif
+      SW_TR(0);
       const int par = it & 1;
       const int64_t I = rstart + (int64_t)DIR * it;
       double rhs;
       if (rhs_bulk_ok(it)) rhs = S.stage[st][KT + 1][g];
       else rhs = (I * 8 + g < nvalid) ? vin[I * 8 + g] : 0.0;
       const double cg = rhs - (S.farpart[par][0][g] + S.farpart[par][1][g] + S.farpart[par][2][g]);
+#ifdef SW_TRACE
+      if (tr_on && cg == 1.2345e300) g_sw_trace[0][15] = 1;   // (dependence: the stamp below waits for cg)
+#endif
+      SW_TR(1);
       // adjacent tile: forward Lb(I,I-1) is stage tile KT-1 (d=-1); backward Ub(I,I+1) is stage tile 0 (d=+1)
+#ifdef SW_TRACE_FINE   // stamps between the single operations of the chain (each pinned by an empty asm on its result)
+      double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 0][2 * lane]);
+      asm volatile("" : "+d"(t.x), "+d"(t.y)); SW_TR(7);
+      double part = fma(t.x, yp.x, t.y * yp.y);
+      asm volatile("" : "+d"(part)); SW_TR(8);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      asm volatile("" : "+d"(part)); SW_TR(9);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      asm volatile("" : "+d"(part)); SW_TR(10);
+      double yv = cg - part;
+#else
       const double2 t = *reinterpret_cast<const double2*>(&S.stage[st][DIR > 0 ? KT - 1 : 0][2 * lane]);
       double part = fma(t.x, yp.x, t.y * yp.y);
       part += __shfl_xor_sync(0xffffffffu, part, 1);
       part += __shfl_xor_sync(0xffffffffu, part, 2);
       double yv = cg - part;  // replicated in the 4 lanes of row g
+#endif
+#ifdef SW_TRACE
+      if (tr_on && yv == 1.2345e300) g_sw_trace[0][15] = 1;
+#endif
+      SW_TR(2);
       if (DIR > 0) {
         // y_g = sum_c Dinv[g][c] t_c
         const double2 dv = *reinterpret_cast<const double2*>(&S.stage[st][KT][2 * lane]);
@@ -146,11 +183,18 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT, SW_NST>& S, const SweepA
         yv += __shfl_xor_sync(0xffffffffu, yv, 1);
         yv += __shfl_xor_sync(0xffffffffu, yv, 2);
       }
+#ifdef SW_TRACE
+      if (tr_on && yv == 1.2345e300) g_sw_trace[0][15] = 1;
+#endif
+      SW_TR(3);
       if (tq == 0) { S.ybuf[slot][g] = yv; S.ybuf[slot + RING][g] = yv; }
       yp.x = __shfl_sync(0xffffffffu, yv, 8 * tq);
       yp.y = __shfl_sync(0xffffffffu, yv, 8 * tq + 4);
+      SW_TR(4);
       __syncthreads();
+      SW_TR(5);
       if (tq == 0) sink(I, g, yv);
+      SW_TR(6);
       slot = slot + 1 == RING ? 0 : slot + 1;
       st = (st + 1) % SW_NST;
     }
@@ -159,9 +203,18 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT, SW_NST>& S, const SweepA
     int sn = 1 == RING ? 0 : 1;            // ring slot of iteration it+1
     unsigned gn = ib + 1u;
     for (int it = 0; it < nrows; ++it, ++gn) {
+#ifdef SW_TRACE
+#ifdef SW_TRACE_FINE
+      const bool tr_on = false;
+#else
+      const bool tr_on = blockIdx.x == SW_TRACE_CTA && DIR > 0 && it >= 32 && it < 64 && ib == 0 && warp == 1;
+#endif
+#endif
+      SW_TR(8);
       if (it + 1 < nrows) {
         const unsigned stn = gn % SW_NST;
         mbar_wait(reinterpret_cast<uint64_t*>(&S.full[stn]), (gn / SW_NST) & 1u);
+        SW_TR(9);
         const double* srow = &S.stage[stn][0][0];
         const double* ybase = &S.ybuf[sn + RING][0];
         double acc;
@@ -169,15 +222,26 @@ __device__ __forceinline__ void sweep_dir(SweepSmem<KT, SW_NST>& S, const SweepA
         else if (warp == 2) acc = far_partial<KT, DIR, 1>(srow, ybase, lane, tq);
         else acc = far_partial<KT, DIR, 2>(srow, ybase, lane, tq);
         if (tq == 0) S.farpart[(it + 1) & 1][warp - 1][g] = acc;
+#ifdef SW_TRACE
+        if (tr_on && acc == 1.2345e300) g_sw_trace[0][15] = 1;
+#endif
+        SW_TR(10);
       }
       __syncthreads();
+      SW_TR(11);
       sn = sn + 1 == RING ? 0 : sn + 1;
     }
   } else {
     // -------- copy warp: refill the stage the near warp finished one iteration ago
     for (int it = 0; it < nrows; ++it) {
+#ifdef SW_TRACE
+      const bool tr_on = blockIdx.x == SW_TRACE_CTA && DIR > 0 && it >= 32 && it < 64 && ib == 0;
+#endif
+      SW_TR(12);
       if (threadIdx.x == SW_COPY_THREAD && it >= 1 && it - 1 + SW_NST < nrows) issue(it - 1 + SW_NST);
+      SW_TR(13);
       __syncthreads();
+      SW_TR(14);
     }
   }
 }
