@@ -10,7 +10,12 @@
  *
  * Threading: one host thread per context (PETSc objects are not thread safe).
  * All work is enqueued on the context's CUDA stream; calls that return host-visible results
- * synchronise that stream before returning.  There is NO CPU fallback: every call fails with
+ * synchronise that stream before returning.  One exception, invisible to the caller: the spike tips and reduced
+ * blocks of a narrow-band spk_factor run on a context-owned side stream (ordered behind the band LU by an event) so
+ * that the first spk_solve's partition sweeps need not wait for them; the reduced solve of that spk_solve -- and
+ * every other entry point that reads the tips or rewrites the band -- makes the context stream wait for them first.
+ * Work the caller enqueues on the context stream after an spk_solve / spk_view is therefore ordered after all of
+ * the factorisation; SPIKE_B200_SIDE_STREAM=0 in the environment keeps everything on the one stream.  There is NO CPU fallback: every call fails with
  * SPK_ERR_CUDA when no sm_100 device is usable.
  */
 #ifndef SPIKE_B200_H
