@@ -193,3 +193,44 @@ def test_sharded_wide_and_multi_rhs(spk, oracle, n, k, R, parts, tip, nrhs, mail
     """BASELINE config 5's protocol in small: wide band, 32 right-hand sides, row blocks on several ranks; also the
     narrow kernels with several columns per sharded solve."""
     assert _run_sharded(spk, oracle, n, k, R, parts, tip, nrhs, mailbox) < RTOL
+
+
+def test_full_size_c5_32_right_hand_sides(spk):
+    """BASELINE config C5 (N = 1M, K = 512, 32 right-hand sides) on one GPU at the partitions / window bench.py runs it with
+    (32 partitions, 288-tile window), through size-independent properties: manufactured solutions u_r (uniform (0,1)),
+    B = A U built on the device with the kept original band; every column within 1e-10 of u_r; residual through the kept
+    band; a column solved alone agrees with the same column of the block solve; scaling by 2 is exact; bit-identical
+    second solve."""
+    import torch
+    n, k, nrhs = 1_000_000, 512, 32
+    S = spk.Spike(partitions=32, tip_tiles=288, mem=spk.MEM_DEVICE)
+    S.keep_original(True)
+    S.set_band_synthetic(n, k)
+    g = torch.Generator(device="cuda"); g.manual_seed(20140601)
+    U = torch.rand((nrhs, n), dtype=torch.float64, device="cuda", generator=g)
+    B = torch.empty_like(U); X = torch.empty_like(U); Y = torch.empty_like(U)
+    for r in range(nrhs):
+        S.mult(U[r].data_ptr(), B[r].data_ptr())
+    S.factor()
+    S.solve(B.data_ptr(), X.data_ptr(), nrhs=nrhs)
+    torch.cuda.synchronize()
+    info = S.view()
+    assert info["partitions"] == 32 and info["tip_tiles"] == 288 and info["boosted_pivots"] == 0, info
+    errs = ((X - U).norm(dim=1) / U.norm(dim=1))
+    assert errs.max().item() < RTOL, errs.tolist()
+    for r in (0, 13, 31):                                           # residual through the unfactored band
+        S.mult(X[r].data_ptr(), Y[r].data_ptr())
+        torch.cuda.synchronize()
+        assert ((Y[r] - B[r]).norm() / B[r].norm()).item() < 1e-11
+    y1 = torch.empty(n, dtype=torch.float64, device="cuda")
+    S.solve(B[5].data_ptr(), y1.data_ptr())                         # one column alone: same solution
+    torch.cuda.synchronize()
+    assert ((y1 - X[5]).norm() / X[5].norm()).item() < 1e-12
+    B2 = 2.0 * B
+    S.solve(B2.data_ptr(), Y.data_ptr(), nrhs=nrhs)
+    torch.cuda.synchronize()
+    assert torch.equal(Y, 2.0 * X)                                  # scaling by 2 is exact in fp64
+    S.solve(B.data_ptr(), Y.data_ptr(), nrhs=nrhs)
+    torch.cuda.synchronize()
+    assert torch.equal(Y, X)                                        # dataflow kernels: bit-identical repeat
+    S.close()
