@@ -54,7 +54,7 @@ typedef struct spk_info {
   int     factored;
   double  frac;                      /* norm fraction of the extracted band (PC_Banded.f)             */
   double  anorm_max;                 /* max |a_ij| of the band                                        */
-  double  factor_ms, solve_ms;       /* device time of the last spk_factor / spk_solve (CUDA events)  */
+  double  factor_ms, solve_ms;       /* device time of the last spk_factor / spk_solve (CUDA events; 0 unless spk_set_timing(ctx,1)) */
   int64_t band_bytes;                /* bytes of the device band (tile-major, padded)                 */
   int     kernel_launches;           /* kernels launched by the last spk_factor + spk_solve           */
   /* device time (ms, CUDA events on the context stream) of the kernels of the last factor / solve:
@@ -154,6 +154,12 @@ int spk_check(spk_ctx *ctx, double *rel_err);
 
 /* PCView_Banded (src/matbanded.c:196-211) */
 int spk_view(spk_ctx *ctx, spk_info *info);
+/* level 2: record the CUDA events behind spk_info.factor_ms / solve_ms / stage_ms in the following calls (the
+ * per-stage timers + JSON records of SURVEY section 5; what -log_view would show of the reference's PCSetUp / PCApply);
+ * level 1: only stage_ms[1], the band LU (one pair of records per factorisation); level 0: none.
+ * 0 by default: every event record between two kernels costs about 2 us of stream time, 25-30 us per factor +
+ * solve at level 2.  SPIKE_B200_STAGE_TIMERS=1 in the environment makes level 2 the default of every new context. */
+int spk_set_timing(spk_ctx *ctx, int level);
 
 /* ---- multi-GPU row-block sharding: spike-tip exchange hooks (the host moves these buffers between
  * neighbouring ranks with NCCL send/recv; sizes are (8*kt)^2 doubles for tips, 8*kt for vectors) -- */

@@ -77,6 +77,7 @@ def lib():
         L.spk_set_operator_csr.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
         L.spk_krylov.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, ip, dp, ip]
         L.spk_view.argtypes = [vp, C.POINTER(Info)]
+        L.spk_set_timing.argtypes = [vp, C.c_int]
         L.spk_check.argtypes = [vp, dp]
         L.spk_awbm_csr.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
         L.spk_tip_size.argtypes = [vp, ip]
@@ -108,7 +109,7 @@ class Spike:
     (src/matbanded.c:111-283): create -> set band (k,frac in/out) -> factor (PCSetUp) -> solve (PCApply)."""
 
     def __init__(self, device=0, partitions=0, tip_tiles=0, boost_rel=1e-13, mem=MEM_HOST, stream=None,
-                 rank=0, nranks=1, row_offset=0, n_global=0):
+                 rank=0, nranks=1, row_offset=0, n_global=0, timing=True):
         L = lib()
         o = Opts()
         L.spk_default_opts(C.byref(o))
@@ -122,6 +123,15 @@ class Spike:
             raise SpikeError(f"spk_create failed ({rc}): {L.spk_last_error(None).decode()}")
         self.n = 0
         self.k = 0
+        # the library's default is no event timers (they cost ~2 us each between kernels); tests and tools want the
+        # stage times of view(), bench.py switches them off for its timed region
+        if timing:
+            self.set_timing(True)
+
+    def set_timing(self, level):
+        """True / 2: all event timers; 1: only the band-LU stage; False / 0: none (the library default)."""
+        level = 2 if level is True else (0 if level is False else int(level))
+        self._ck(lib().spk_set_timing(self._h, level), "spk_set_timing")
 
     def _ck(self, rc, what):
         if rc:

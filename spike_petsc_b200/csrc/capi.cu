@@ -40,8 +40,14 @@ struct DevTmp {
 // per-stage CUDA-event timers (spk_info.stage_ms) + NVTX ranges of the same names (tracing)
 static const char* const k_stage_name[8] = {"spike:tip_windows", "spike:band_lu", "spike:spike_tips", "spike:sweeps",
                                             "spike:reduced_solve", "spike:corrections", "spike:stage6", "spike:stage7"};
-#define STAGE_BEGIN(c, i) do { nvtxRangePushA(k_stage_name[i]); cudaEventRecord((c)->evst[i][0], (c)->stream); } while (0)
-#define STAGE_END(c, i) do { cudaEventRecord((c)->evst[i][1], (c)->stream); (c)->stage_timed[i] = 1; nvtxRangePop(); } while (0)
+// The event records are opt-in (spk_set_timing; SPIKE_B200_STAGE_TIMERS=1 turns them on for every new context): an event
+// record between two kernels costs about 2 us of stream time -- 25-30 us per factor + solve step for the twelve stage
+// records, a fifth of a C1 step (tools/side_ab.py with SPIKE_B200_STAGE_TIMERS=0/1, profiles/r02_summary.md).
+// Levels: 0 nothing, 1 only the band-LU stage (the dominant kernel: one pair of records per factorisation), 2 everything.
+#define STAGE_ON(c, i) ((c)->timing >= 2 || ((c)->timing == 1 && (i) == 1))
+#define STAGE_BEGIN(c, i) do { nvtxRangePushA(k_stage_name[i]); if (STAGE_ON(c, i)) cudaEventRecord((c)->evst[i][0], (c)->stream); } while (0)
+#define STAGE_END(c, i) do { if (STAGE_ON(c, i)) { cudaEventRecord((c)->evst[i][1], (c)->stream); (c)->stage_timed[i] = 1; } nvtxRangePop(); } while (0)
+#define TIME_EVENT(c, ev) do { if ((c)->timing >= 2) SPK_CUDA(c, cudaEventRecord((c)->ev, (c)->stream)); } while (0)
 
 // Side stream of the narrow-band path.  The spike tips and reduced blocks (three 13-step Gauss-Jordan launches, latency
 // chains that need only the last window of every factored partition) are the one stage of a factorisation whose
@@ -130,6 +136,7 @@ extern "C" int spk_create(spk_ctx** out, const spk_opts* opts) {
     return SPK_ERR_CUDA;
   }
   for (int i = 0; i < 8; ++i) { cudaEventCreate(&c->evst[i][0]); cudaEventCreate(&c->evst[i][1]); }
+  { const char* tv = getenv("SPIKE_B200_STAGE_TIMERS"); c->timing = (tv && tv[0] != '0') ? 2 : 0; }
   const char* sidev = getenv("SPIKE_B200_SIDE_STREAM");
   if (!sidev || sidev[0] != '0') {
     int lo = 0, hi = 0;
@@ -608,7 +615,7 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
     c->factored = 0;
     c->launches = 0; c->have_remote_wt = 0; c->boundary_done = 0; c->wt_done = 0;
     SPK_CUDA(c, cudaMemsetAsync(c->d_boost, 0, sizeof(int64_t), c->stream));
-    SPK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    TIME_EVENT(c, ev0);
     // W^(t) needs the unfactored top windows: UL pass first (read only), then the in-place LU
     STAGE_BEGIN(c, 0); rc = spk_launch_ul_tips(c); STAGE_END(c, 0);
     if (rc == SPK_OK) { STAGE_BEGIN(c, 1); rc = spk_launch_lu(c); STAGE_END(c, 1); }
@@ -620,7 +627,7 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
     c->factored = 0;
     c->launches = 0; c->have_remote_wt = 0; c->boundary_done = 0; c->wt_done = 0;
     SPK_CUDA(c, cudaMemsetAsync(c->d_boost, 0, sizeof(int64_t), c->stream));
-    SPK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    TIME_EVENT(c, ev0);
     STAGE_BEGIN(c, 0);
     rc = spk_launch_ul_tips(c);
     if (rc == SPK_OK) rc = spk_launch_tips(c, 4, 0);   // all W^(t) now (one launch; no single-CTA kernel for the first one)
@@ -640,10 +647,10 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
       SideScope side(c, !c->wide);   // everything up to the closing brace goes to the side stream (when there is one)
       STAGE_BEGIN(c, 2); rc = spk_launch_tips(c, with_boundary ? 3 : 0, 0); STAGE_END(c, 2);
       if (rc) return rc;
-      if (done) SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+      if (done) TIME_EVENT(c, ev1);
     }
     if (with_boundary) c->boundary_done = 1;
-    if (done) { c->factored = 1; c->timed_factor = 1; return spk_peer_note(c); }
+    if (done) { c->factored = 1; c->timed_factor = c->timing >= 2; return spk_peer_note(c); }
     return SPK_OK;
   }
   if (phase == 2) {  // after SPK_BND_REMOTE_WT has been set
@@ -654,8 +661,8 @@ extern "C" int spk_factor_phase(spk_ctx* c, int phase) {
         if (rc) return rc;
         c->boundary_done = 1;
       }
-      SPK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-      c->factored = 1; c->timed_factor = 1;
+      TIME_EVENT(c, ev1);
+      c->factored = 1; c->timed_factor = c->timing >= 2;
     }
     return spk_peer_note(c);
   }
@@ -760,7 +767,7 @@ extern "C" int spk_solve_phase(spk_ctx* c, int phase, const double* b, double* x
     if (!b || !x) return SPK_ERR_ARG;
     if (spk_peer_failed(c)) return SPK_ERR_STATE;
     c->cur_x = x; c->cur_nrhs = nrhs;
-    SPK_CUDA(c, cudaEventRecord(c->evs0, c->stream));
+    TIME_EVENT(c, evs0);
     if (c->rscale) {   // equilibrated band: the sweeps run in place on diag(r) b
       for (int r = 0; r < nrhs && rc == SPK_OK; ++r) rc = spk_launch_vec_scale(c, x + (size_t)r * n, b + (size_t)r * n, c->rscale, n);
       if (rc) return rc;
@@ -800,8 +807,8 @@ extern "C" int spk_solve_phase(spk_ctx* c, int phase, const double* b, double* x
     }
     STAGE_END(c, 5);
     for (int r = 0; r < nrhs && rc == SPK_OK && c->cscale; ++r) rc = spk_launch_vec_scale(c, c->cur_x + (size_t)r * n, c->cur_x + (size_t)r * n, c->cscale, n);
-    SPK_CUDA(c, cudaEventRecord(c->evs1, c->stream));
-    c->timed_solve = 1;
+    TIME_EVENT(c, evs1);
+    c->timed_solve = c->timing >= 2;
     if (rc == SPK_OK) rc = spk_peer_note(c);
     return rc;
   }
@@ -824,13 +831,13 @@ extern "C" int spk_solve(spk_ctx* c, const double* b, double* x, int nrhs) {
     SPK_CUDA(c, cudaMemcpyAsync(tmp, b, sizeof(double) * (size_t)n * nrhs, cudaMemcpyHostToDevice, c->stream));
     bd = tmp; xd = tmp;
   }
-  SPK_CUDA(c, cudaEventRecord(c->evs0, c->stream));
+  TIME_EVENT(c, evs0);
   int rc = SPK_OK;
   if (nrhs >= 2) rc = solve_multi_dev(c, bd, xd, nrhs);
   else rc = spk_solve_dev(c, bd, xd);
   if (rc == SPK_OK) {
-    cudaError_t e = cudaEventRecord(c->evs1, c->stream);
-    c->timed_solve = 1;
+    cudaError_t e = c->timing >= 2 ? cudaEventRecord(c->evs1, c->stream) : cudaSuccess;
+    c->timed_solve = c->timing >= 2;
     if (e == cudaSuccess && tmp) e = cudaMemcpyAsync(x, tmp, sizeof(double) * (size_t)n * nrhs, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess && tmp) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { SPK_SET_ERR(c, "solve copy-back failed: %s", cudaGetErrorString(e)); rc = SPK_ERR_CUDA; }
@@ -955,6 +962,13 @@ extern "C" int spk_check(spk_ctx* c, double* rel_err) {
   SPK_CUDA(c, cudaMemcpyAsync(h, c->d_scalar, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   SPK_CUDA(c, cudaStreamSynchronize(c->stream));
   *rel_err = (h[1] > 0.0 && h[0] == h[0]) ? sqrt(h[0] / h[1]) : INFINITY;
+  return SPK_OK;
+}
+
+extern "C" int spk_set_timing(spk_ctx* c, int level) {
+  if (!c || level < 0 || level > 2) return SPK_ERR_ARG;
+  c->timing = level;
+  if (level < 2) { c->timed_factor = c->timed_solve = 0; for (int i = 0; i < 8; ++i) if (!STAGE_ON(c, i)) c->stage_timed[i] = 0; }
   return SPK_OK;
 }
 

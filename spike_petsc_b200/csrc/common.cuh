@@ -118,6 +118,7 @@ struct spk_ctx {
   cudaEvent_t ev0, ev1;     // factor start/stop
   cudaEvent_t evs0, evs1;   // solve start/stop
   int timed_factor, timed_solve;
+  int timing;               // spk_set_timing: record the factor / solve / per-stage events (each costs ~2 us between two kernels)
   cudaEvent_t evst[8][2];   // per-stage start/stop (see spk_info.stage_ms)
   int stage_timed[8];
   void* lu_trace;           // debug: device buffer for clock64 stamps of the LU kernel (tools only)
