@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "../../include/spike_b200.h"
 
 #define SPK_TILE 8
@@ -186,6 +187,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- programmatic dependent launch ------------------------------------------------------------
+// pdl_trigger(): the next kernel of the stream may start launching once every CTA of this grid has got here;
+// pdl_wait(): block until the previous kernel of the stream has completed and its memory is visible (a no-op for a
+// kernel launched without the attribute).  Nothing a predecessor writes may be touched before pdl_wait().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef __CUDACC__
+static inline bool spk_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SPIKE_B200_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute
+template <class... KArgs, class... Args>
+static inline cudaError_t spk_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = spk_pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
 
 // ---- kernels' host launchers (defined in the .cu files) ---------------------------------------
 int spk_launch_generate(spk_ctx* c, uint64_t seed, double delta);

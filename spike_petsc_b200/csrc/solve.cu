@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(SW_THREADS, SW_NST > 6 ? 3 : 4) k_sweep(const 
     for (int i = 0; i < SW_NST; ++i) mbar_init(reinterpret_cast<uint64_t*>(&S.full[i]), 1);
     fence_mbar_init();
   }
+  pdl_trigger();
   __syncthreads();
+  pdl_wait();   // everything above touched shared memory only
   unsigned itbase = 0;
   const int64_t n = a.n;
   if (a.mode == SWEEP_MAIN) {
@@ -315,7 +317,7 @@ static int launch_sweep_kt(spk_ctx* c, const SweepArgs& a, int grid) {
   SPK_CUDA(c, cudaFuncSetAttribute(k_sweep<KT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // largest shared-memory carve-out: the CTAs of the spike-tip kernels (side stream, capi.cu) fit next to two resident sweep CTAs
   SPK_CUDA(c, cudaFuncSetAttribute(k_sweep<KT, NST>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-  k_sweep<KT, NST><<<grid, SW_THREADS, smem, c->stream>>>(a);
+  SPK_CUDA(c, spk_launch_pdl(k_sweep<KT, NST>, dim3(grid), dim3(SW_THREADS), smem, c->stream, a));
   SPK_KERNEL_CHECK(c);
   return SPK_OK;
 }
@@ -415,6 +417,8 @@ __global__ void __launch_bounds__(1024) k_reduced_solve(const RedSolveArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int kp = a.L.kc * 8, KT = a.L.kc;
   double* gb = sm; double* gt = gb + kp; double* tv = gt + kp; double* xt = tv + kp; double* xb = xt + kp;
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x + a.first_iface;
   const bool bnd = (i == a.boundary_iface);
   const int64_t tb = a.pstart[i + 1];
@@ -492,7 +496,7 @@ int spk_launch_reduced_solve(spk_ctx* c, double* x, int nrhs, int64_t ld, int if
     // block mat-vec when there are at most two interfaces per SM
     const int per_sm = (n + c->sm_count - 1) / c->sm_count;
     const int threads = std::max(256, std::min(1024, (2048 / std::max(per_sm, 1)) / 32 * 32));
-    k_reduced_solve<<<n, threads, sizeof(double) * 5 * c->kp, c->stream>>>(a);
+    SPK_CUDA(c, spk_launch_pdl(k_reduced_solve, dim3(n), dim3(threads), sizeof(double) * 5 * c->kp, c->stream, a));
     SPK_KERNEL_CHECK(c);
   }
   return SPK_OK;
@@ -518,7 +522,7 @@ int spk_launch_reduced_solve_multi(spk_ctx* c, double* x, int nrhs, int64_t ld, 
     RedSolveArgs b = a;
     b.x = x + (size_t)r0 * ld; b.rtop = a.rtop + (size_t)r0 * a.tip_stride; b.rbot = a.rbot + (size_t)r0 * a.tip_stride;
     b.remoteGtop = a.remoteGtop + (size_t)r0 * a.bnd_stride; b.xbBoundary = a.xbBoundary + (size_t)r0 * a.bnd_stride;
-    k_reduced_solve<<<dim3(n, nr), threads, sizeof(double) * 5 * c->kp, c->stream>>>(b);
+    SPK_CUDA(c, spk_launch_pdl(k_reduced_solve, dim3(n, nr), dim3(threads), sizeof(double) * 5 * c->kp, c->stream, b));
     SPK_KERNEL_CHECK(c);
   }
   return SPK_OK;

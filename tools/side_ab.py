@@ -1,7 +1,8 @@
 """A/B of the side stream (spike tips + reduced blocks next to the first solve's sweeps, capi.cu SideScope):
 whole factor+solve step time with SPIKE_B200_SIDE_STREAM=0 / 1, CUDA events around K back-to-back steps,
 solution compared bit for bit between the two modes.  usage: side_ab.py [n,k,P,tip ...]
-(SIDE_AB_MODES=1: only the product mode, as a whole-step partition / window sweep)"""
+(SIDE_AB_MODES=1: only the product mode, as a whole-step partition / window sweep; SIDE_AB_TIMING=0: the engine's
+event timers off, as in the library default -- the stage columns are then zero)"""
 import os, sys; sys.path.insert(0, '.')
 import torch, spike_petsc_b200 as sp
 cases = [(10_000_000, 100, 296, 78), (1_250_000, 100, 296, 78), (1_000_000, 50, 592, 48), (100_000, 10, 296, 24)]
@@ -12,7 +13,7 @@ for n, k, P, tip in cases:
     xs = {}
     for mode in os.environ.get("SIDE_AB_MODES", "0,1,0,1").split(","):
         os.environ["SPIKE_B200_SIDE_STREAM"] = mode
-        S = sp.Spike(partitions=P, tip_tiles=tip, mem=sp.MEM_DEVICE); S.keep_original(True); S.set_band_synthetic(n, k)
+        S = sp.Spike(partitions=P, tip_tiles=tip, mem=sp.MEM_DEVICE, timing=os.environ.get('SIDE_AB_TIMING', '1') != '0'); S.keep_original(True); S.set_band_synthetic(n, k)
         u = torch.ones(n, dtype=torch.float64, device='cuda'); b = torch.empty_like(u); x = torch.empty_like(u)
         S.mult(u.data_ptr(), b.data_ptr())
         for _ in range(3):
